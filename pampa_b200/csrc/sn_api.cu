@@ -1,0 +1,737 @@
+// sn_api.cu -- the C ABI declared in include/pampa_sn.h: handle, device memory, iteration.
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "sn_kernels.cuh"
+
+using namespace pampa_sn;
+
+namespace {
+
+std::string g_create_error;
+
+// minimal NCCL surface, bound at run time so that one-GPU use has no NCCL dependency
+struct NcclUniqueId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+   void* lib = nullptr;
+   int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+   int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+   int (*CommDestroy)(NcclComm) = nullptr;
+   const char* (*GetErrorString)(int) = nullptr;
+   bool load(std::string& err) {
+      if (lib) return true;
+      lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (!lib) { err = std::string("unable to load libnccl.so.2: ") + dlerror(); return false; }
+      GetUniqueId = (int (*)(NcclUniqueId*))dlsym(lib, "ncclGetUniqueId");
+      CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(lib, "ncclCommInitRank");
+      AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+      CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
+      GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+      if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "incomplete NCCL library"; return false; }
+      return true;
+   }
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+struct LaunchGroup { int wave, dt, fin, ring; bool extras; int64_t offset; int count; };
+
+}  // namespace
+
+struct pampa_sn_handle {
+   std::string err;
+   pampa_sn_options opts;
+   Plan plan;
+   int device = 0;
+   cudaStream_t stream = nullptr;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   std::vector<void*> allocs;
+   int64_t device_bytes = 0;
+   int64_t launches = 0;
+
+   int G = 0, M = 0, Gown = 0, nmat = 0;
+   std::vector<int32_t> gloc;
+   std::vector<double> h_beta;
+
+   // device data
+   int32_t *d_slot_of_xy = nullptr, *d_mats = nullptr, *d_gloc = nullptr;
+   double *d_area = nullptr, *d_dz = nullptr, *d_inv_dz = nullptr;
+   double *d_sig_t = nullptr, *d_sig_s = nullptr, *d_chi = nullptr, *d_nusf = nullptr, *d_kapsf = nullptr;
+   double *d_phi = nullptr, *d_phi_new = nullptr, *d_q = nullptr, *d_psi = nullptr;
+   double *d_bnd[2] = {nullptr, nullptr}, *d_bndz[2] = {nullptr, nullptr};
+   int bnd_cur = 0;
+   int64_t bnd_count = 0, bndz_count = 0;
+   double *d_partials = nullptr;
+   int nblocks_reduce = 0;
+   ReduceScalars* d_sc = nullptr;
+   ClassDev* d_classes = nullptr;
+   ChunkDev* d_chunks = nullptr;
+   Task* d_tasks = nullptr;
+   std::vector<LaunchGroup> groups;
+   std::vector<int32_t*> d_pos_of;       // per class
+   int32_t** d_class_pos_of = nullptr;
+   // LS
+   int nls = 0; int64_t ls_nnz = 0;
+   int32_t *d_ls_ptr = nullptr, *d_ls_nbr = nullptr, *d_dir_chunk = nullptr, *d_dir_d = nullptr;
+   double *d_ls_coef = nullptr, *d_ls_dD = nullptr, *d_ls_rhs = nullptr;
+   std::vector<int> dir_chunk, dir_d;
+   bool extras = false;
+
+   // iteration state
+   ReduceScalars sc{};
+   double scale = 1.0;         // normalisation of the last solve: fields = scale * device values
+   double keff = 1.0;
+   bool solved = false;
+   double last_sweep_ms = 0, last_source_ms = 0, last_reduce_ms = 0;
+   std::vector<double> h_temperature, h_delayed;
+   NcclComm comm = nullptr;
+
+   SweepGlobals globals() const {
+      SweepGlobals gp{};
+      gp.classes = d_classes; gp.chunks = d_chunks; gp.gloc = d_gloc; gp.q = d_q;
+      gp.phi_new = d_phi_new; gp.mats = d_mats; gp.sigma_t = d_sig_t; gp.inv_dz = d_inv_dz;
+      gp.bnd_old = d_bnd[bnd_cur]; gp.bnd_new = d_bnd[1 - bnd_cur];
+      gp.bndz_old = d_bndz[bnd_cur]; gp.bndz_new = d_bndz[1 - bnd_cur];
+      gp.ls_dD = d_ls_dD; gp.ls_rhs = d_ls_rhs;
+      gp.Sb = plan.Sb; gp.G = G; gp.Gown = Gown; gp.M = M; gp.nz = plan.nz; gp.Kc = plan.Kc;
+      gp.has_z = plan.has_z; gp.nrf = plan.num_rfaces; gp.nls = nls;
+      gp.bcz_minus_refl = bcz_refl[0]; gp.bcz_plus_refl = bcz_refl[1];
+      gp.store_psi = 1;
+      return gp;
+   }
+   int bcz_refl[2] = {0, 0};
+};
+
+#define SN_FAIL(h, msg) do { (h)->err = (msg); return 1; } while (0)
+#define SN_CUDA(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+   (h)->err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call; return 1; } } while (0)
+
+namespace {
+
+template <typename T>
+int dev_alloc(pampa_sn_handle* h, T** p, int64_t count) {
+   *p = nullptr;
+   if (count <= 0) return 0;
+   void* v = nullptr;
+   cudaError_t e = cudaMalloc(&v, (size_t)count * sizeof(T));
+   if (e != cudaSuccess) {
+      h->err = std::string("CUDA error: ") + cudaGetErrorString(e) + " allocating " +
+               std::to_string((size_t)count * sizeof(T)) + " bytes";
+      return 1;
+   }
+   h->allocs.push_back(v);
+   h->device_bytes += count * (int64_t)sizeof(T);
+   *p = (T*)v;
+   return 0;
+}
+
+template <typename T>
+int dev_upload(pampa_sn_handle* h, T** p, const T* src, int64_t count) {
+   if (dev_alloc(h, p, count)) return 1;
+   if (count > 0) SN_CUDA(h, cudaMemcpy(*p, src, (size_t)count * sizeof(T), cudaMemcpyHostToDevice));
+   return 0;
+}
+
+template <typename T>
+int dev_upload(pampa_sn_handle* h, T** p, const std::vector<T>& v) {
+   return dev_upload(h, p, v.data(), (int64_t)v.size());
+}
+
+int dt_template(int nd) {
+   const int opts[] = {1, 2, 3, 4, 5, 6, 8, 10};
+   for (int o : opts) if (nd <= o) return o;
+   return 10;
+}
+
+int upload_xs(pampa_sn_handle* h, const pampa_sn_xs* xs, bool first) {
+   const int G = xs->num_groups, nm = xs->num_materials;
+   if (!first && (G != h->G || nm != h->nmat)) SN_FAIL(h, "cross-section table shape changed");
+   const int64_t n = (int64_t)nm * G;
+   if (first) {
+      if (dev_alloc(h, &h->d_sig_t, n) || dev_alloc(h, &h->d_sig_s, n * G) || dev_alloc(h, &h->d_chi, n) ||
+          dev_alloc(h, &h->d_nusf, n) || dev_alloc(h, &h->d_kapsf, n)) return 1;
+   }
+   SN_CUDA(h, cudaMemcpy(h->d_sig_t, xs->sigma_total, n * sizeof(double), cudaMemcpyHostToDevice));
+   SN_CUDA(h, cudaMemcpy(h->d_sig_s, xs->sigma_scattering, n * G * sizeof(double), cudaMemcpyHostToDevice));
+   SN_CUDA(h, cudaMemcpy(h->d_chi, xs->chi_effective, n * sizeof(double), cudaMemcpyHostToDevice));
+   SN_CUDA(h, cudaMemcpy(h->d_nusf, xs->nu_sigma_fission, n * sizeof(double), cudaMemcpyHostToDevice));
+   SN_CUDA(h, cudaMemcpy(h->d_kapsf, xs->kappa_sigma_fission, n * sizeof(double), cudaMemcpyHostToDevice));
+   h->h_beta.assign(nm, 0.0);
+   if (xs->beta_total) h->h_beta.assign(xs->beta_total, xs->beta_total + nm);
+   return 0;
+}
+
+int sync_scalars(pampa_sn_handle* h) {
+   SN_CUDA(h, cudaMemcpyAsync(&h->sc, h->d_sc, sizeof(ReduceScalars), cudaMemcpyDeviceToHost, h->stream));
+   SN_CUDA(h, cudaStreamSynchronize(h->stream));
+   return 0;
+}
+
+int do_source(pampa_sn_handle* h) {
+   launch_source(h->d_phi, h->d_q, h->d_mats, h->d_sig_s, h->d_chi, h->d_nusf, h->d_sc, h->G,
+                 h->plan.nz, h->plan.Sb, h->stream);
+   h->launches++;
+   return 0;
+}
+
+int do_sweep(pampa_sn_handle* h) {
+   SweepGlobals gp = h->globals();
+   if (h->nls > 0) {
+      launch_ls_rhs(gp, h->d_ls_ptr, h->d_ls_nbr, h->d_ls_coef, h->ls_nnz, h->d_dir_chunk, h->d_dir_d,
+                    (const int32_t* const*)h->d_class_pos_of, h->stream);
+      h->launches++;
+   }
+   for (const LaunchGroup& lg : h->groups) {
+      launch_sweep(gp, h->d_tasks + lg.offset, lg.count, h->plan.P, lg.dt, lg.fin, lg.ring, lg.extras,
+                   h->stream);
+      h->launches++;
+   }
+   h->bnd_cur = 1 - h->bnd_cur;      // what this sweep wrote is what the next one reads
+   return 0;
+}
+
+int do_exchange(pampa_sn_handle* h) {
+   if (!h->comm) return 0;
+   const int64_t n = (int64_t)h->G * h->plan.nz * h->plan.Sb;
+   int r = g_nccl.AllReduce(h->d_phi_new, h->d_phi_new, (size_t)n, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+   if (r != 0) SN_FAIL(h, std::string("NCCL error in the flux-moment allreduce: ") +
+                          (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+   // mirrored-direction boundary fluxes may live on another rank
+   double* bufs[2] = {h->d_bnd[h->bnd_cur], h->d_bndz[h->bnd_cur]};
+   int64_t cnt[2] = {h->bnd_count, h->bndz_count};
+   for (int b = 0; b < 2; b++)
+      if (bufs[b] && cnt[b] > 0) {
+         r = g_nccl.AllReduce(bufs[b], bufs[b], (size_t)cnt[b], NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+         if (r != 0) SN_FAIL(h, "NCCL error in the boundary-flux allreduce");
+      }
+   return 0;
+}
+
+int do_reduce(pampa_sn_handle* h, int update_k) {
+   launch_reduce(h->d_phi, h->d_phi_new, h->d_mats, h->d_nusf, h->d_kapsf, h->d_area, h->d_dz,
+                 h->plan.has_z, h->G, h->plan.nz, h->plan.Sb, h->d_partials, h->nblocks_reduce, h->d_sc,
+                 update_k, h->stream);
+   h->launches += 2;
+   return 0;
+}
+
+int check_async(pampa_sn_handle* h, const char* what) {
+   cudaError_t e = cudaGetLastError();
+   if (e != cudaSuccess) SN_FAIL(h, std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+   return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void pampa_sn_default_options(pampa_sn_options* o) {
+   std::memset(o, 0, sizeof(*o));
+   o->store_psi = 1;
+   o->num_ranks = 1;
+}
+
+const char* pampa_sn_last_error(const pampa_sn_handle* h) {
+   return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+int pampa_sn_plan_check(const pampa_sn_mesh* mesh, const pampa_sn_quadrature* quad, int32_t num_groups,
+                        const pampa_sn_options* opts, pampa_sn_info* info) {
+   try {
+      pampa_sn_options o;
+      if (opts) o = *opts; else pampa_sn_default_options(&o);
+      Plan pl;
+      build_plan(PlanInput{mesh, quad, num_groups, o}, pl);
+      // invariants: every xy cell appears exactly once per class; sources point upwind
+      for (auto& cp : pl.classes) {
+         std::vector<int> seen(pl.Sb, 0);
+         for (int64_t s = 0; s < cp.S; s++) {
+            if ((cp.cell_of[s] >= 0) != (cp.lvl[s] != LVL_EMPTY)) throw std::runtime_error("slot/level mismatch");
+            if (cp.cell_of[s] >= 0) seen[cp.cell_of[s]]++;
+         }
+         for (int c = 0; c < pl.nxy; c++) if (seen[pl.slot_of_xy[c]] != 1) throw std::runtime_error("cell coverage");
+         for (int f = 0; f < FIN_MAX; f++)
+            for (int64_t s = 0; s < cp.S; s++) {
+               int32_t code = cp.in_src[(size_t)f * cp.S + s];
+               if (code < 0) continue;
+               int kind = code >> SRC_KIND_SHIFT, pay = code & SRC_PAYLOAD;
+               int64_t p = s / pl.P;
+               if (kind == SRC_LOCAL) {
+                  int64_t u = p * pl.P + pay;
+                  int diff = (int)cp.lvl[s] - (int)cp.lvl[u];
+                  if (cp.lvl[u] == LVL_EMPTY || diff < 1 || diff >= cp.ring) throw std::runtime_error("local source level");
+               } else if (kind == SRC_GLOBAL) {
+                  int64_t up = pay / pl.P;
+                  if (cp.lvl[pay] == LVL_EMPTY) throw std::runtime_error("global source hole");
+                  if (up != p && cp.patch_level[up] >= cp.patch_level[p]) throw std::runtime_error("patch order");
+               }
+            }
+      }
+      if (info) {
+         std::memset(info, 0, sizeof(*info));
+         info->num_cells = (int64_t)pl.nxy * pl.nz; info->num_groups = pl.G; info->num_directions = pl.M;
+         info->updates_per_sweep = pl.owned_updates;
+         info->sweep_launches = (int64_t)pl.waves.size();
+         for (auto& w : pl.waves) info->sweep_tasks += (int64_t)w.size();
+         info->num_classes = (int64_t)pl.classes.size(); info->num_chunks = (int64_t)pl.chunks.size();
+         info->tile_classes = pl.tile_classes;
+      }
+   } catch (const std::exception& e) {
+      g_create_error = e.what();
+      return 1;
+   }
+   return 0;
+}
+
+int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pampa_sn_xs* xs,
+                    const pampa_sn_quadrature* quad, const pampa_sn_ls* ls, const pampa_sn_options* opts) {
+   *out = nullptr;
+   std::unique_ptr<pampa_sn_handle> hp(new pampa_sn_handle());
+   pampa_sn_handle* h = hp.get();
+   auto fail = [&](int) { g_create_error = h->err; pampa_sn_destroy(hp.release()); return 1; };
+   if (opts) h->opts = *opts; else pampa_sn_default_options(&h->opts);
+   if (!mesh || !xs || !quad) { h->err = "null input"; return fail(1); }
+   if (h->opts.num_ranks < 1 || h->opts.rank < 0 || h->opts.rank >= h->opts.num_ranks) { h->err = "wrong rank"; return fail(1); }
+   if (h->opts.store_psi != 1) { h->err = "store_psi = 0 is not implemented"; return fail(1); }
+   if (h->opts.patch_cells > 256) { h->err = "patch_cells must be <= 256"; return fail(1); }
+   h->G = xs->num_groups; h->M = quad->num_directions; h->nmat = xs->num_materials;
+   for (int64_t i = 0; i < (int64_t)mesh->num_layers * mesh->num_xy_cells; i++)
+      if (mesh->materials[i] < 0 || mesh->materials[i] >= xs->num_materials) { h->err = "wrong material index"; return fail(1); }
+   if (ls && ls->num_cells > 0 && (mesh->has_z_faces || mesh->num_layers != 1)) {
+      h->err = "least-squares boundary interpolation is only supported on 1-D and 2-D meshes"; return fail(1);
+   }
+
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if (e != cudaSuccess || ndev == 0) {
+      h->err = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this layer has no CPU fallback";
+      return fail(1);
+   }
+   h->device = h->opts.device;
+   if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "unable to select the CUDA device"; return fail(1); }
+
+   try {
+      build_plan(PlanInput{mesh, quad, h->G, h->opts}, h->plan);
+   } catch (const std::exception& ex) { h->err = ex.what(); return fail(1); }
+   Plan& pl = h->plan;
+   if (pl.P > 256) { h->err = "patch size must be <= 256"; return fail(1); }
+
+   auto body = [&]() -> int {
+      SN_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+      SN_CUDA(h, cudaEventCreate(&h->ev0));
+      SN_CUDA(h, cudaEventCreate(&h->ev1));
+      SN_CUDA(h, configure_sweep_kernels());
+
+      const int nr = h->opts.num_ranks, rank = h->opts.rank;
+      h->gloc.assign(h->G, -1); h->Gown = 0;
+      for (int g = 0; g < h->G; g++)
+         if (h->opts.shard_mode != 1 || g % nr == rank) h->gloc[g] = h->Gown++;
+      std::vector<char> chunk_owned(pl.chunks.size(), 1);
+      if (h->opts.shard_mode != 1)
+         for (size_t c = 0; c < pl.chunks.size(); c++) chunk_owned[c] = ((int)(c % nr) == rank);
+
+      // mesh arrays in the padded slot numbering
+      const int64_t Sb = pl.Sb; const int nz = pl.nz;
+      std::vector<int32_t> mats((size_t)nz * Sb, -1);
+      std::vector<double> area(Sb, 0.0), dz(nz, 1.0), idz(nz, 0.0);
+      for (int c = 0; c < pl.nxy; c++) area[pl.slot_of_xy[c]] = mesh->xy_area[c];
+      for (int k = 0; k < nz; k++) {
+         if (pl.has_z) { dz[k] = mesh->dz[k]; idz[k] = 1.0 / mesh->dz[k]; }
+         for (int c = 0; c < pl.nxy; c++) mats[(size_t)k * Sb + pl.slot_of_xy[c]] = mesh->materials[(size_t)k * pl.nxy + c];
+      }
+      if (dev_upload(h, &h->d_slot_of_xy, pl.slot_of_xy) || dev_upload(h, &h->d_mats, mats) ||
+          dev_upload(h, &h->d_area, area) || dev_upload(h, &h->d_dz, dz) || dev_upload(h, &h->d_inv_dz, idz) ||
+          dev_upload(h, &h->d_gloc, h->gloc)) return 1;
+      if (upload_xs(h, xs, true)) return 1;
+      if (pl.has_z) {
+         h->bcz_refl[0] = mesh->bc_types[mesh->bc_minus_z] == PAMPA_SN_BC_REFLECTIVE;
+         h->bcz_refl[1] = mesh->bc_types[mesh->bc_plus_z] == PAMPA_SN_BC_REFLECTIVE;
+      }
+
+      // flux arrays
+      const int64_t nphi = (int64_t)h->G * nz * Sb;
+      if (dev_alloc(h, &h->d_phi, nphi) || dev_alloc(h, &h->d_phi_new, nphi) || dev_alloc(h, &h->d_q, nphi)) return 1;
+      int64_t psi_doubles = 0;
+      std::vector<int64_t> psi_off(pl.chunks.size(), -1);
+      for (size_t c = 0; c < pl.chunks.size(); c++)
+         if (chunk_owned[c]) {
+            psi_off[c] = psi_doubles;
+            psi_doubles += (int64_t)pl.chunks[c].nd * h->Gown * nz * pl.classes[pl.chunks[c].cls].S;
+         }
+      if (dev_alloc(h, &h->d_psi, psi_doubles)) return 1;
+      SN_CUDA(h, cudaMemsetAsync(h->d_psi, 0, (size_t)psi_doubles * sizeof(double), h->stream));
+
+      // reflective boundary buffers
+      h->extras = false;
+      if (pl.num_rfaces > 0) {
+         h->bnd_count = (int64_t)h->M * h->G * nz * pl.num_rfaces;
+         for (int b = 0; b < 2; b++) {
+            if (dev_alloc(h, &h->d_bnd[b], h->bnd_count)) return 1;
+            SN_CUDA(h, cudaMemsetAsync(h->d_bnd[b], 0, (size_t)h->bnd_count * sizeof(double), h->stream));
+         }
+         h->extras = true;
+      }
+      if (h->bcz_refl[0] || h->bcz_refl[1]) {
+         h->bndz_count = 2LL * h->M * h->G * Sb;
+         for (int b = 0; b < 2; b++) {
+            if (dev_alloc(h, &h->d_bndz[b], h->bndz_count)) return 1;
+            SN_CUDA(h, cudaMemsetAsync(h->d_bndz[b], 0, (size_t)h->bndz_count * sizeof(double), h->stream));
+         }
+         h->extras = true;
+      }
+
+      // LS correction tables
+      std::vector<std::vector<int32_t>> ls_of(pl.classes.size());
+      if (ls && ls->num_cells > 0) {
+         h->nls = ls->num_cells; h->ls_nnz = ls->ptr[ls->num_cells];
+         std::vector<int32_t> nbr_slot(h->ls_nnz);
+         for (int64_t a = 0; a < h->ls_nnz; a++) nbr_slot[a] = pl.slot_of_xy[ls->nbr[a]];
+         std::vector<double> coef((size_t)h->M * h->ls_nnz), dD((size_t)h->M * h->nls, 0.0);
+         for (int m = 0; m < h->M; m++)
+            for (int b = 0; b < h->nls; b++)
+               for (int a = ls->ptr[b]; a < ls->ptr[b + 1]; a++) {
+                  double w = quad->directions[3*m] * ls->nvec[3*a] + quad->directions[3*m+1] * ls->nvec[3*a+1] +
+                             quad->directions[3*m+2] * ls->nvec[3*a+2];
+                  double c = w > 0.0 ? ls->omega[a] * w : 0.0;
+                  coef[(size_t)m * h->ls_nnz + a] = c;
+                  dD[(size_t)m * h->nls + b] -= c;
+               }
+         std::vector<int32_t> ptr(ls->ptr, ls->ptr + h->nls + 1);
+         if (dev_upload(h, &h->d_ls_ptr, ptr) || dev_upload(h, &h->d_ls_nbr, nbr_slot) ||
+             dev_upload(h, &h->d_ls_coef, coef) || dev_upload(h, &h->d_ls_dD, dD) ||
+             dev_alloc(h, &h->d_ls_rhs, (int64_t)h->M * h->G * h->nls)) return 1;
+         SN_CUDA(h, cudaMemsetAsync(h->d_ls_rhs, 0, (size_t)h->M * h->G * h->nls * sizeof(double), h->stream));
+         for (size_t ci = 0; ci < pl.classes.size(); ci++) {
+            ls_of[ci].assign(pl.classes[ci].S, -1);
+            for (int b = 0; b < h->nls; b++) ls_of[ci][pl.classes[ci].pos_of[pl.slot_of_xy[ls->cell[b]]]] = b;
+         }
+         h->extras = true;
+      }
+
+      // classes
+      std::vector<ClassDev> cdev(pl.classes.size());
+      h->d_pos_of.assign(pl.classes.size(), nullptr);
+      for (size_t ci = 0; ci < pl.classes.size(); ci++) {
+         const ClassPlan& cp = pl.classes[ci];
+         ClassDev& cd = cdev[ci];
+         cd.S = cp.S; cd.zdir = cp.zdir; cd.ring = cp.ring; cd.tiles = cp.tiles ? 1 : 0; cd.pad = 0;
+         int32_t *d_cell_of, *d_patch_nlev, *d_in_src, *d_rout, *d_ls_of = nullptr;
+         uint16_t* d_lvl; Vec2 *d_out_vec, *d_in_vec;
+         if (dev_upload(h, &d_cell_of, cp.cell_of) || dev_upload(h, &d_lvl, cp.lvl) ||
+             dev_upload(h, &d_patch_nlev, cp.patch_nlev) || dev_upload(h, &d_out_vec, cp.out_vec) ||
+             dev_upload(h, &d_in_src, cp.in_src) || dev_upload(h, &d_in_vec, cp.in_vec) ||
+             dev_upload(h, &d_rout, cp.rout) || dev_upload(h, &h->d_pos_of[ci], cp.pos_of)) return 1;
+         if (h->nls > 0 && dev_upload(h, &d_ls_of, ls_of[ci])) return 1;
+         cd.cell_of = d_cell_of; cd.lvl = d_lvl; cd.patch_nlev = d_patch_nlev;
+         cd.out_vec = (const double2*)d_out_vec; cd.in_src = d_in_src; cd.in_vec = (const double2*)d_in_vec;
+         cd.rout = d_rout; cd.ls_of = d_ls_of;
+      }
+      if (dev_upload(h, &h->d_classes, cdev)) return 1;
+      if (dev_upload(h, &h->d_class_pos_of, h->d_pos_of.data(), (int64_t)h->d_pos_of.size())) return 1;
+
+      // chunks
+      std::vector<ChunkDev> chdev(pl.chunks.size());
+      h->dir_chunk.assign(h->M, -1); h->dir_d.assign(h->M, -1);
+      for (size_t c = 0; c < pl.chunks.size(); c++) {
+         const Chunk& ch = pl.chunks[c];
+         ChunkDev& cd = chdev[c];
+         std::memset(&cd, 0, sizeof(cd));
+         cd.cls = ch.cls; cd.nd = ch.nd;
+         for (int d = 0; d < DT_MAX; d++) {
+            const int m = d < ch.nd ? ch.m[d] : -1;
+            cd.m[d] = m;
+            if (m >= 0) {
+               cd.mux[d] = quad->directions[3*m]; cd.muy[d] = quad->directions[3*m+1];
+               cd.muz_abs[d] = std::fabs(quad->directions[3*m+2]); cd.w[d] = quad->weights[m];
+               for (int ax = 0; ax < 3; ax++) cd.mrefl[d][ax] = quad->reflected[3*m+ax];
+               if (chunk_owned[c]) { h->dir_chunk[m] = (int)c; h->dir_d[m] = d; }
+            }
+         }
+         cd.psi = chunk_owned[c] ? h->d_psi + psi_off[c] : nullptr;
+      }
+      if (dev_upload(h, &h->d_chunks, chdev)) return 1;
+      {
+         std::vector<int32_t> a(h->dir_chunk.begin(), h->dir_chunk.end()), b(h->dir_d.begin(), h->dir_d.end());
+         if (dev_upload(h, &h->d_dir_chunk, a) || dev_upload(h, &h->d_dir_d, b)) return 1;
+      }
+
+      // launch schedule: per wave, tasks grouped by kernel variant
+      std::vector<Task> all;
+      h->groups.clear();
+      for (size_t w = 0; w < pl.waves.size(); w++) {
+         std::vector<Task> tasks = pl.waves[w];
+         auto variant = [&](const Task& t) {
+            const Chunk& ch = pl.chunks[t.chunk]; const ClassPlan& cp = pl.classes[ch.cls];
+            return std::make_tuple(dt_template(ch.nd), cp.fin <= 2 ? 2 : FIN_MAX, cp.ring);
+         };
+         std::stable_sort(tasks.begin(), tasks.end(), [&](const Task& a, const Task& b) { return variant(a) < variant(b); });
+         size_t i = 0;
+         while (i < tasks.size()) {
+            size_t j = i;
+            while (j < tasks.size() && variant(tasks[j]) == variant(tasks[i])) j++;
+            auto v = variant(tasks[i]);
+            h->groups.push_back(LaunchGroup{(int)w, std::get<0>(v), std::get<1>(v), std::get<2>(v), h->extras,
+                                            (int64_t)all.size() + (int64_t)i, (int)(j - i)});
+            i = j;
+         }
+         all.insert(all.end(), tasks.begin(), tasks.end());
+      }
+      if (dev_upload(h, &h->d_tasks, all)) return 1;
+
+      // reduction scratch and iteration state
+      h->nblocks_reduce = (int)std::min<int64_t>(((int64_t)nz * Sb + 255) / 256, 148 * 8);
+      if (dev_alloc(h, &h->d_partials, 5LL * h->nblocks_reduce) || dev_alloc(h, &h->d_sc, 1)) return 1;
+      ReduceScalars sc0{}; sc0.keff = 1.0;
+      SN_CUDA(h, cudaMemcpyAsync(h->d_sc, &sc0, sizeof(sc0), cudaMemcpyHostToDevice, h->stream));
+      SN_CUDA(h, cudaMemsetAsync(h->d_phi, 0, (size_t)nphi * sizeof(double), h->stream));
+      launch_fill_phi(h->d_phi_new, h->d_mats, 1.0, h->G, (int64_t)nz * Sb, h->stream);
+      if (do_reduce(h, 0)) return 1;
+      if (sync_scalars(h)) return 1;
+      return check_async(h, "initialisation");
+   };
+   if (body()) return fail(1);
+   if (h->opts.verbose)
+      std::printf("pampa_sn: %d xy cells x %d layers, %d groups, %d directions, %zu classes (%d tiled), %zu chunks, "
+                  "%zu sweep launches, %.1f MB on device %d\n", pl.nxy, pl.nz, h->G, h->M, pl.classes.size(),
+                  pl.tile_classes, pl.chunks.size(), h->groups.size(), h->device_bytes / 1.0e6, h->device);
+   *out = hp.release();
+   return 0;
+}
+
+int pampa_sn_destroy(pampa_sn_handle* h) {
+   if (!h) return 0;
+   cudaSetDevice(h->device);
+   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+   if (h->stream) cudaStreamSynchronize(h->stream);
+   for (void* p : h->allocs) cudaFree(p);
+   if (h->ev0) cudaEventDestroy(h->ev0);
+   if (h->ev1) cudaEventDestroy(h->ev1);
+   if (h->stream) cudaStreamDestroy(h->stream);
+   delete h;
+   return 0;
+}
+
+int pampa_sn_update_xs(pampa_sn_handle* h, const pampa_sn_xs* xs) {
+   SN_CUDA(h, cudaSetDevice(h->device));
+   SN_CUDA(h, cudaStreamSynchronize(h->stream));
+   return upload_xs(h, xs, false);
+}
+
+int pampa_sn_source(pampa_sn_handle* h, double keff) {
+   SN_CUDA(h, cudaSetDevice(h->device));
+   SN_CUDA(h, cudaMemcpyAsync(&h->d_sc->keff, &keff, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+   SN_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+   if (do_source(h)) return 1;
+   SN_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+   SN_CUDA(h, cudaStreamSynchronize(h->stream));
+   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->last_source_ms = ms;
+   return check_async(h, "the source kernel");
+}
+
+int pampa_sn_sweep(pampa_sn_handle* h) {
+   SN_CUDA(h, cudaSetDevice(h->device));
+   SN_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+   if (do_sweep(h)) return 1;
+   SN_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+   SN_CUDA(h, cudaStreamSynchronize(h->stream));
+   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->last_sweep_ms = ms;
+   return check_async(h, "the sweep kernel");
+}
+
+int pampa_sn_reduce(pampa_sn_handle* h, double* production, double* power, double* dphi_rel) {
+   SN_CUDA(h, cudaSetDevice(h->device));
+   if (do_exchange(h)) return 1;
+   SN_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+   if (do_reduce(h, 0)) return 1;
+   SN_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+   if (sync_scalars(h)) return 1;
+   float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->last_reduce_ms = ms;
+   if (production) *production = h->sc.production;
+   if (power) *power = h->sc.power;
+   if (dphi_rel) *dphi_rel = h->sc.phi2 > 0 ? std::sqrt(h->sc.dphi2 / h->sc.phi2) : 0.0;
+   return check_async(h, "the reduction kernel");
+}
+
+int pampa_sn_iterate(pampa_sn_handle* h, int32_t iterations, double* keff) {
+   SN_CUDA(h, cudaSetDevice(h->device));
+   for (int it = 0; it < iterations; it++) {
+      if (do_source(h) || do_sweep(h) || do_exchange(h) || do_reduce(h, 1)) return 1;
+   }
+   if (sync_scalars(h)) return 1;
+   h->keff = h->sc.keff;
+   if (keff) *keff = h->sc.keff;
+   return check_async(h, "the source iteration");
+}
+
+int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_t max_it, double power,
+                        double* keff, int32_t* iterations) {
+   SN_CUDA(h, cudaSetDevice(h->device));
+   int it = 0;
+   bool converged = false;
+   while (it < max_it) {
+      if (do_source(h) || do_sweep(h) || do_exchange(h) || do_reduce(h, 1)) return 1;
+      it++;
+      if (sync_scalars(h)) return 1;
+      const double dphi = h->sc.phi2 > 0 ? std::sqrt(h->sc.dphi2 / h->sc.phi2) : 0.0;
+      if (!(h->sc.keff == h->sc.keff)) SN_FAIL(h, "the power iteration diverged (NaN)");
+      if (it > 1 && std::fabs(h->sc.dk) < tol_k && dphi < tol_phi) { converged = true; break; }
+   }
+   if (check_async(h, "the k-eff iteration")) return 1;
+   h->keff = h->sc.keff;
+   if (keff) *keff = h->sc.keff;
+   if (iterations) *iterations = it;
+   if (h->sc.power == 0.0) SN_FAIL(h, "zero fission power: no fissile material in the mesh");
+   h->scale = power / h->sc.power;
+   h->solved = true;
+   if (h->sc.min_phi * h->scale < 0.0) SN_FAIL(h, "negative values in the scalar-flux solution");
+   if (!converged) SN_FAIL(h, "the power iteration did not converge in " + std::to_string(max_it) + " iterations");
+   return 0;
+}
+
+int64_t pampa_sn_field_size(const pampa_sn_handle* h, const char* name) {
+   const int64_t N = (int64_t)h->plan.nxy * h->plan.nz;
+   const std::string s(name);
+   if (s == "scalar-flux" || s == "flux-moments") return N * h->G;
+   if (s == "angular-flux") return N * h->G * h->M;
+   if (s == "power" || s == "production-rate" || s == "temperature" || s == "delayed-source") return N;
+   return -1;
+}
+
+int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
+   SN_CUDA(h, cudaSetDevice(h->device));
+   const std::string s(name);
+   const Plan& pl = h->plan;
+   const int64_t N = (int64_t)pl.nxy * pl.nz;
+   const int64_t count = pampa_sn_field_size(h, name);
+   if (count < 0) SN_FAIL(h, "unable to find field '" + s + "'");
+   if (s == "temperature" || s == "delayed-source") {
+      std::vector<double>& v = s == "temperature" ? h->h_temperature : h->h_delayed;
+      if (s == "delayed-source" && h->solved) {
+         // S_i = beta * P_i (reference src/NeutronicSolver.cxx:103)
+         std::vector<double> P(N);
+         if (pampa_sn_get(h, "production-rate", P.data())) return 1;
+         std::vector<int32_t> mats((size_t)pl.nz * pl.Sb);
+         SN_CUDA(h, cudaMemcpy(mats.data(), h->d_mats, mats.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+         for (int64_t i = 0; i < N; i++) {
+            int k = (int)(i / pl.nxy), c = (int)(i % pl.nxy);
+            out[i] = h->h_beta[mats[(size_t)k * pl.Sb + pl.slot_of_xy[c]]] * P[i];
+         }
+         return 0;
+      }
+      for (int64_t i = 0; i < N; i++) out[i] = (int64_t)v.size() == N ? v[i] : 0.0;
+      return 0;
+   }
+   double* d_out = nullptr;
+   SN_CUDA(h, cudaMalloc(&d_out, (size_t)count * sizeof(double)));
+   int rc = 0;
+   if (s == "scalar-flux") {
+      launch_export_phi(h->d_phi, h->d_slot_of_xy, 4.0 * M_PI * h->scale, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
+   } else if (s == "flux-moments") {      // raw device moments sum_m w_m psi, no normalisation
+      launch_export_phi(h->d_phi, h->d_slot_of_xy, 1.0, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
+   } else if (s == "power") {
+      launch_export_cell(h->d_phi, h->d_slot_of_xy, h->d_mats, h->d_kapsf, h->d_area, h->d_dz, pl.has_z,
+                         4.0 * M_PI * h->scale, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
+   } else if (s == "production-rate") {
+      launch_export_cell(h->d_phi, h->d_slot_of_xy, h->d_mats, h->d_nusf, h->d_area, h->d_dz, pl.has_z,
+                         4.0 * M_PI * h->scale / h->keff, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
+   } else {   // angular-flux
+      cudaMemsetAsync(d_out, 0, (size_t)count * sizeof(double), h->stream);
+      double* d_min = nullptr;
+      cudaMalloc(&d_min, sizeof(double));
+      cudaMemsetAsync(d_min, 0, sizeof(double), h->stream);
+      for (int m = 0; m < h->M; m++) {
+         const int c = h->dir_chunk[m];
+         if (c < 0) continue;
+         const Chunk& ch = pl.chunks[c];
+         const ClassPlan& cp = pl.classes[ch.cls];
+         ChunkDev cd;
+         cudaMemcpyAsync(&cd, h->d_chunks + c, sizeof(ChunkDev), cudaMemcpyDeviceToHost, h->stream);
+         cudaStreamSynchronize(h->stream);
+         launch_export_psi(cd.psi, h->d_pos_of[ch.cls], h->d_slot_of_xy, h->dir_d[m], m, h->Gown, h->d_gloc,
+                           h->scale, h->G, h->M, pl.nz, pl.nxy, cp.S, d_out, d_min, h->stream);
+      }
+      double mn = 0.0;
+      cudaMemcpyAsync(&mn, d_min, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+      cudaStreamSynchronize(h->stream);
+      cudaFree(d_min);
+      if (mn < 0.0) { h->err = "negative values in the angular-flux solution"; rc = 1; }
+   }
+   cudaError_t e = cudaStreamSynchronize(h->stream);
+   if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost);
+   cudaFree(d_out);
+   if (e != cudaSuccess) SN_FAIL(h, std::string("CUDA error exporting field: ") + cudaGetErrorString(e));
+   return rc;
+}
+
+int pampa_sn_set(pampa_sn_handle* h, const char* name, const double* in) {
+   const std::string s(name);
+   const int64_t N = (int64_t)h->plan.nxy * h->plan.nz;
+   if (s == "temperature") { h->h_temperature.assign(in, in + N); return 0; }
+   if (s == "delayed-source") { h->h_delayed.assign(in, in + N); return 0; }
+   if (s == "flux-moments") {      // iteration state / initial guess, layout [i][g]
+      SN_CUDA(h, cudaSetDevice(h->device));
+      const int64_t count = N * h->G;
+      double* d_in = nullptr;
+      SN_CUDA(h, cudaMalloc(&d_in, (size_t)count * sizeof(double)));
+      cudaMemcpy(d_in, in, (size_t)count * sizeof(double), cudaMemcpyHostToDevice);
+      cudaMemsetAsync(h->d_phi, 0, (size_t)h->G * h->plan.nz * h->plan.Sb * sizeof(double), h->stream);
+      launch_import_phi(h->d_phi_new, h->d_slot_of_xy, h->G, h->plan.nz, h->plan.nxy, h->plan.Sb, d_in, h->stream);
+      do_reduce(h, 0);
+      int rc = sync_scalars(h);
+      cudaFree(d_in);
+      return rc ? 1 : check_async(h, "field import");
+   }
+   SN_FAIL(h, "unable to find field '" + s + "'");
+}
+
+int pampa_sn_comm_unique_id(void* id, int32_t id_bytes) {
+   if (id_bytes != (int32_t)sizeof(NcclUniqueId)) { g_create_error = "NCCL unique id must be 128 bytes"; return 1; }
+   if (!g_nccl.load(g_create_error)) return 1;
+   return g_nccl.GetUniqueId((NcclUniqueId*)id) == 0 ? 0 : 1;
+}
+
+int pampa_sn_comm_init(pampa_sn_handle* h, const void* id, int32_t id_bytes) {
+   if (id_bytes != (int32_t)sizeof(NcclUniqueId)) SN_FAIL(h, "NCCL unique id must be 128 bytes");
+   if (!g_nccl.load(h->err)) return 1;
+   SN_CUDA(h, cudaSetDevice(h->device));
+   NcclUniqueId uid;
+   std::memcpy(&uid, id, sizeof(uid));
+   int r = g_nccl.CommInitRank(&h->comm, h->opts.num_ranks, uid, h->opts.rank);
+   if (r != 0) SN_FAIL(h, std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+   return 0;
+}
+
+void* pampa_sn_device_ptr(pampa_sn_handle* h, const char* name, int64_t* count) {
+   const std::string s(name);
+   const int64_t nphi = (int64_t)h->G * h->plan.nz * h->plan.Sb;
+   if (s == "phi") { if (count) *count = nphi; return h->d_phi; }
+   if (s == "phi-new") { if (count) *count = nphi; return h->d_phi_new; }
+   if (s == "q") { if (count) *count = nphi; return h->d_q; }
+   if (count) *count = 0;
+   return nullptr;
+}
+
+int pampa_sn_get_info(pampa_sn_handle* h, pampa_sn_info* info) {
+   std::memset(info, 0, sizeof(*info));
+   const Plan& pl = h->plan;
+   info->num_cells = (int64_t)pl.nxy * pl.nz; info->num_groups = h->G; info->num_directions = h->M;
+   info->updates_per_sweep = pl.owned_updates;
+   info->sweep_launches = (int64_t)h->groups.size();
+   for (auto& g : h->groups) info->sweep_tasks += g.count;
+   info->num_classes = (int64_t)pl.classes.size(); info->num_chunks = (int64_t)pl.chunks.size();
+   info->tile_classes = pl.tile_classes;
+   info->device_bytes = h->device_bytes;
+   info->last_sweep_ms = h->last_sweep_ms; info->last_source_ms = h->last_source_ms;
+   info->last_reduce_ms = h->last_reduce_ms;
+   info->kernel_launches = h->launches;
+   return 0;
+}
+
+}  // extern "C"

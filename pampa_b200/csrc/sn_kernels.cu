@@ -1,0 +1,534 @@
+// sn_kernels.cu -- sm_100a kernels of the SN transport layer.
+//
+//  (1) sn_sweep_kernel    upwind transport sweep  psi = T^-1 q   (replaces the LU solve inside
+//                         EPSSolve, reference src/petsc.cxx:428-433, for the operator assembled
+//                         by src/SNSolver.cxx:396-397, :459-599 with delta = 1)
+//  (2) sn_source_kernel   q = (S + F/k) phi                       (src/SNSolver.cxx:417-439)
+//  (3) sn_reduce_kernel   production / power integrals, flux change norms, k update
+//                         (src/SNSolver.cxx:272-299, src/NeutronicSolver.cxx:81-116)
+//
+// Sweep mapping: one CTA per task = (chunk of <= DT directions with the same upwind pattern,
+// one energy group, one patch of <= P xy cells, one chunk of z layers).  Thread <-> xy cell.
+// A thread marches through the layers of its column; the z-upwind flux stays in registers, the
+// in-patch lateral upwind fluxes come from a shared-memory ring written by the neighbouring
+// threads one pipeline step earlier, and only patch-boundary fluxes are re-read from HBM/L2.
+// All arithmetic is fp64.  HBM traffic per cell-angle-group update: 8 B psi store + q and phi
+// shared by the DT directions of the chunk + patch-boundary reads.
+#include "sn_kernels.cuh"
+
+namespace pampa_sn {
+
+__device__ __forceinline__ double ldcg_f64(const double* p) { return __ldcg(p); }
+
+template <int DT, int FIN, bool EXTRAS>
+__global__ void __launch_bounds__(256)
+sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
+   extern __shared__ double smem[];
+   const Task tk = tasks[blockIdx.x];
+   const ChunkDev* __restrict__ ch = gp.chunks + tk.chunk;
+   const ClassDev* __restrict__ cl = gp.classes + ch->cls;
+   const int P = blockDim.x, t = threadIdx.x;
+   const int64_t S = cl->S;
+   const int64_t Sb = gp.Sb;
+   const int64_t slot = (int64_t)tk.patch * P + t;
+   const int g = tk.group;
+   const int gl = gp.gloc[g];
+   const int nd = ch->nd;
+   const int nz = gp.nz;
+   const int zdir = cl->zdir;
+   const int RD = cl->ring;
+   const int lv = cl->lvl[slot];
+   const bool valid = (lv != LVL_EMPTY);
+   const int cell = valid ? (cl->tiles ? (int)slot : cl->cell_of[slot]) : 0;
+   const int kp0 = tk.zc * gp.Kc;
+   const int kcnt = min(gp.Kc, nz - kp0);
+   const int nsteps = cl->patch_nlev[tk.patch] + kcnt - 1;
+
+   double* ring = smem;                       // [RD][DT][P]
+   double* s_muz = smem + (size_t)RD * DT * P;   // [DT]
+   double* s_w = s_muz + DT;                  // [DT]
+   if (t < DT) {
+      s_muz[t] = (t < nd && gp.has_z) ? ch->muz_abs[t] : 0.0;
+      s_w[t] = t < nd ? ch->w[t] : 0.0;
+   }
+
+   // streaming coefficients of this cell for the DT directions (per unit volume)
+   double a[FIN][DT], so[DT];
+   int src[FIN];
+   {
+      const double2 ov = valid ? cl->out_vec[slot] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int d = 0; d < DT; d++) {
+         const double mx = d < nd ? ch->mux[d] : 0.0, my = d < nd ? ch->muy[d] : 0.0;
+         so[d] = mx * ov.x + my * ov.y;
+      }
+#pragma unroll
+      for (int s = 0; s < FIN; s++) {
+         src[s] = valid ? cl->in_src[(size_t)s * S + slot] : SRC_NONE;
+         const double2 iv = valid ? cl->in_vec[(size_t)s * S + slot] : make_double2(0.0, 0.0);
+#pragma unroll
+         for (int d = 0; d < DT; d++) {
+            const double mx = d < nd ? ch->mux[d] : 0.0, my = d < nd ? ch->muy[d] : 0.0;
+            a[s][d] = -(mx * iv.x + my * iv.y);
+         }
+      }
+   }
+   int rout[ROUT_MAX];
+   int lsb = -1;
+   if (EXTRAS) {
+#pragma unroll
+      for (int r = 0; r < ROUT_MAX; r++) rout[r] = valid ? cl->rout[(size_t)r * S + slot] : -1;
+      if (cl->ls_of != nullptr && valid) lsb = cl->ls_of[slot];
+   }
+
+   const int64_t dstride = (int64_t)gp.Gown * nz * S;
+   double* __restrict__ psi_g = ch->psi + (int64_t)gl * nz * S + slot;
+   const double* __restrict__ q_g = gp.q + (int64_t)g * nz * Sb + cell;
+   double* __restrict__ phi_g = gp.phi_new + (int64_t)g * nz * Sb + cell;
+   const int32_t* __restrict__ mats_c = gp.mats + cell;
+   const double* __restrict__ sigt_g = gp.sigma_t + g;
+
+   // z-upwind start values
+   double psiz[DT];
+#pragma unroll
+   for (int d = 0; d < DT; d++) psiz[d] = 0.0;
+   if (gp.has_z && valid) {
+      if (kp0 > 0) {
+         const int kprev = zdir > 0 ? kp0 - 1 : nz - kp0;
+#pragma unroll
+         for (int d = 0; d < DT; d++)
+            if (d < nd) psiz[d] = ldcg_f64(psi_g + d * dstride + (int64_t)kprev * S);
+      } else if (EXTRAS) {
+         const int face = zdir > 0 ? 0 : 1;
+         const bool refl = face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl;
+         if (refl) {
+#pragma unroll
+            for (int d = 0; d < DT; d++)
+               if (d < nd)
+                  psiz[d] = gp.bndz_old[(((int64_t)face * gp.M + ch->mrefl[d][2]) * gp.G + g) * Sb + cell];
+         }
+      }
+   }
+   __syncthreads();
+
+   int rs = 0;
+   for (int step = 0; step < nsteps; step++) {
+      const int kl = step - lv;
+      if (valid && kl >= 0 && kl < kcnt) {
+         const int kp = kp0 + kl;
+         const int k = zdir >= 0 ? kp : nz - 1 - kp;
+         const int64_t koff = (int64_t)k * Sb;
+         const int mat = mats_c[koff];
+         const double st = sigt_g[mat * gp.G];
+         const double qv = q_g[koff];
+         const double idz = gp.has_z ? gp.inv_dz[k] : 0.0;
+         double acc[DT], den[DT];
+#pragma unroll
+         for (int d = 0; d < DT; d++) {
+            const double az = s_muz[d] * idz;
+            acc[d] = fma(az, psiz[d], qv);
+            den[d] = st + so[d] + az;
+         }
+         if (EXTRAS) {
+            if (lsb >= 0) {
+#pragma unroll
+               for (int d = 0; d < DT; d++)
+                  if (d < nd) {
+                     const int m = ch->m[d];
+                     den[d] += gp.ls_dD[(int64_t)m * gp.nls + lsb];
+                     acc[d] += gp.ls_rhs[((int64_t)m * gp.G + g) * gp.nls + lsb];
+                  }
+            }
+         }
+#pragma unroll
+         for (int s = 0; s < FIN; s++) {
+            const int code = src[s];
+            if (code >= 0) {
+               const int kind = code >> SRC_KIND_SHIFT;
+               const int pay = code & SRC_PAYLOAD;
+               if (kind == SRC_LOCAL) {
+                  const double* r = ring + (size_t)rs * DT * P + pay;
+#pragma unroll
+                  for (int d = 0; d < DT; d++) acc[d] = fma(a[s][d], r[d * P], acc[d]);
+               } else if (kind == SRC_GLOBAL) {
+                  const double* pg = ch->psi + (int64_t)gl * nz * S + (int64_t)k * S + pay;
+#pragma unroll
+                  for (int d = 0; d < DT; d++)
+                     if (d < nd) acc[d] = fma(a[s][d], ldcg_f64(pg + d * dstride), acc[d]);
+               } else if (EXTRAS) {
+                  const int axis = pay >> SRC_AXIS_SHIFT;
+                  const int rf = pay & ((1 << SRC_AXIS_SHIFT) - 1);
+#pragma unroll
+                  for (int d = 0; d < DT; d++)
+                     if (d < nd) {
+                        const int mr = ch->mrefl[d][axis];
+                        acc[d] = fma(a[s][d],
+                                     gp.bnd_old[(((int64_t)mr * gp.G + g) * nz + k) * gp.nrf + rf], acc[d]);
+                     }
+               }
+            }
+         }
+         double ph = 0.0;
+         double* rw = ring + (size_t)rs * DT * P + t;
+#pragma unroll
+         for (int d = 0; d < DT; d++) {
+            const double v = acc[d] / den[d];
+            psiz[d] = v;
+            rw[d * P] = v;
+            ph = fma(s_w[d], v, ph);
+         }
+         if (gp.store_psi) {
+#pragma unroll
+            for (int d = 0; d < DT; d++)
+               if (d < nd) psi_g[d * dstride + (int64_t)k * S] = psiz[d];
+         }
+         atomicAdd(phi_g + koff, ph);
+         if (EXTRAS) {
+#pragma unroll
+            for (int r = 0; r < ROUT_MAX; r++)
+               if (rout[r] >= 0) {
+#pragma unroll
+                  for (int d = 0; d < DT; d++)
+                     if (d < nd)
+                        gp.bnd_new[(((int64_t)ch->m[d] * gp.G + g) * nz + k) * gp.nrf + rout[r]] = psiz[d];
+               }
+            if (gp.has_z && kp == nz - 1) {
+               const int face = zdir > 0 ? 1 : 0;
+               const bool refl = face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl;
+               if (refl) {
+#pragma unroll
+                  for (int d = 0; d < DT; d++)
+                     if (d < nd)
+                        gp.bndz_new[(((int64_t)face * gp.M + ch->m[d]) * gp.G + g) * Sb + cell] = psiz[d];
+               }
+            }
+         }
+         rs = (rs + 1 == RD) ? 0 : rs + 1;
+      }
+      __syncthreads();
+   }
+}
+
+template <int DT, int FIN>
+static void launch_sweep_fin(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int P,
+                             size_t smem, bool extras, cudaStream_t st) {
+   if (extras) sn_sweep_kernel<DT, FIN, true><<<ntasks, P, smem, st>>>(gp, d_tasks);
+   else        sn_sweep_kernel<DT, FIN, false><<<ntasks, P, smem, st>>>(gp, d_tasks);
+}
+
+template <int DT>
+static void launch_sweep_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int P, int fin,
+                            int ring, bool extras, cudaStream_t st) {
+   const size_t smem = ((size_t)ring * DT * P + 2 * DT) * sizeof(double);
+   if (fin <= 2) launch_sweep_fin<DT, 2>(gp, d_tasks, ntasks, P, smem, extras, st);
+   else          launch_sweep_fin<DT, FIN_MAX>(gp, d_tasks, ntasks, P, smem, extras, st);
+}
+
+void launch_sweep(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int P, int dt, int fin,
+                  int ring, bool extras, cudaStream_t st) {
+   if (ntasks <= 0) return;
+   if (dt <= 1)      launch_sweep_dt<1>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
+   else if (dt <= 2) launch_sweep_dt<2>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
+   else if (dt <= 3) launch_sweep_dt<3>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
+   else if (dt <= 4) launch_sweep_dt<4>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
+   else if (dt <= 5) launch_sweep_dt<5>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
+   else if (dt <= 6) launch_sweep_dt<6>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
+   else if (dt <= 8) launch_sweep_dt<8>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
+   else              launch_sweep_dt<10>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
+}
+
+template <int DT, int FIN, bool EX>
+static cudaError_t cfg_one() {
+   return cudaFuncSetAttribute(sn_sweep_kernel<DT, FIN, EX>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+}
+template <int DT>
+static cudaError_t cfg_dt() {
+   cudaError_t e;
+   if ((e = cfg_one<DT, 2, false>()) != cudaSuccess) return e;
+   if ((e = cfg_one<DT, 2, true>()) != cudaSuccess) return e;
+   if ((e = cfg_one<DT, FIN_MAX, false>()) != cudaSuccess) return e;
+   return cfg_one<DT, FIN_MAX, true>();
+}
+cudaError_t configure_sweep_kernels() {
+   cudaError_t e;
+   if ((e = cfg_dt<1>()) != cudaSuccess) return e;
+   if ((e = cfg_dt<2>()) != cudaSuccess) return e;
+   if ((e = cfg_dt<3>()) != cudaSuccess) return e;
+   if ((e = cfg_dt<4>()) != cudaSuccess) return e;
+   if ((e = cfg_dt<5>()) != cudaSuccess) return e;
+   if ((e = cfg_dt<6>()) != cudaSuccess) return e;
+   if ((e = cfg_dt<8>()) != cudaSuccess) return e;
+   return cfg_dt<10>();
+}
+
+// ------------------------------------------------------------------------------------ source
+// q[g] = sum_g2 (sigma_s(g2->g) + chi_g nu-sigma-f_g2 / k) phi[g2]; one thread per (layer, slot).
+__global__ void __launch_bounds__(256)
+sn_source_kernel(const double* __restrict__ phi, double* __restrict__ q,
+                 const int32_t* __restrict__ mats, const double* __restrict__ sig_s,
+                 const double* __restrict__ chi, const double* __restrict__ nusf,
+                 const ReduceScalars* __restrict__ sc, int G, int64_t n) {
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= n) return;
+   const int mat = mats[idx];
+   if (mat < 0) return;
+   const double ik = 1.0 / sc->keff;
+   double fis = 0.0;
+   for (int g2 = 0; g2 < G; g2++) fis = fma(nusf[mat * G + g2], phi[(int64_t)g2 * n + idx], fis);
+   fis *= ik;
+   const double* ss = sig_s + (size_t)mat * G * G;
+   for (int g = 0; g < G; g++) {
+      double acc = chi[mat * G + g] * fis;
+      for (int g2 = 0; g2 < G; g2++) acc = fma(ss[g2 * G + g], phi[(int64_t)g2 * n + idx], acc);
+      q[(int64_t)g * n + idx] = acc;
+   }
+}
+
+void launch_source(const double* phi, double* q, const int32_t* mats, const double* sig_s,
+                   const double* chi, const double* nusf, const ReduceScalars* sc, int G, int nz,
+                   int64_t Sb, cudaStream_t st) {
+   const int64_t n = (int64_t)nz * Sb;
+   const int nb = (int)((n + 255) / 256);
+   sn_source_kernel<<<nb, 256, 0, st>>>(phi, q, mats, sig_s, chi, nusf, sc, G, n);
+}
+
+// ------------------------------------------------------------------------------------ reduce
+// Per-block partials of {production, power, ||dphi||^2, ||phi_new||^2, min phi}; also rotates
+// phi <- phi_new and clears phi_new for the next sweep's accumulation.
+__global__ void __launch_bounds__(256)
+sn_reduce_kernel(double* __restrict__ phi, double* __restrict__ phi_new,
+                 const int32_t* __restrict__ mats, const double* __restrict__ nusf,
+                 const double* __restrict__ kapsf, const double* __restrict__ area,
+                 const double* __restrict__ dz, int has_z, int G, int nz, int64_t Sb,
+                 double* __restrict__ partials) {
+   const int64_t n = (int64_t)nz * Sb;
+   double prod = 0.0, pow_ = 0.0, d2 = 0.0, p2 = 0.0, mn = 1.0e300;
+   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+        idx += (int64_t)gridDim.x * blockDim.x) {
+      const int mat = mats[idx];
+      if (mat < 0) continue;
+      const int k = (int)(idx / Sb);
+      const double vol = area[idx - (int64_t)k * Sb] * (has_z ? dz[k] : 1.0);
+      for (int g = 0; g < G; g++) {
+         const int64_t a = (int64_t)g * n + idx;
+         const double pn = phi_new[a], po = phi[a];
+         phi[a] = pn;
+         phi_new[a] = 0.0;
+         prod = fma(vol * nusf[mat * G + g], pn, prod);
+         pow_ = fma(vol * kapsf[mat * G + g], pn, pow_);
+         d2 = fma(pn - po, pn - po, d2);
+         p2 = fma(pn, pn, p2);
+         mn = fmin(mn, pn);
+      }
+   }
+   __shared__ double sh[5][256];
+   sh[0][threadIdx.x] = prod; sh[1][threadIdx.x] = pow_; sh[2][threadIdx.x] = d2;
+   sh[3][threadIdx.x] = p2; sh[4][threadIdx.x] = mn;
+   __syncthreads();
+   for (int off = 128; off > 0; off >>= 1) {
+      if ((int)threadIdx.x < off) {
+         for (int j = 0; j < 4; j++) sh[j][threadIdx.x] += sh[j][threadIdx.x + off];
+         sh[4][threadIdx.x] = fmin(sh[4][threadIdx.x], sh[4][threadIdx.x + off]);
+      }
+      __syncthreads();
+   }
+   if (threadIdx.x == 0)
+      for (int j = 0; j < 5; j++) partials[(size_t)j * gridDim.x + blockIdx.x] = sh[j][0];
+}
+
+// Deterministic final sum + power-iteration update k <- k * P_new / P_old.
+__global__ void sn_reduce_final_kernel(const double* __restrict__ partials, int nblocks,
+                                       ReduceScalars* sc, int update_k) {
+   __shared__ double sh[5][256];
+   double v[5] = {0, 0, 0, 0, 1.0e300};
+   for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+      for (int j = 0; j < 4; j++) v[j] += partials[(size_t)j * nblocks + b];
+      v[4] = fmin(v[4], partials[(size_t)4 * nblocks + b]);
+   }
+   for (int j = 0; j < 5; j++) sh[j][threadIdx.x] = v[j];
+   __syncthreads();
+   for (int off = 128; off > 0; off >>= 1) {
+      if ((int)threadIdx.x < off) {
+         for (int j = 0; j < 4; j++) sh[j][threadIdx.x] += sh[j][threadIdx.x + off];
+         sh[4][threadIdx.x] = fmin(sh[4][threadIdx.x], sh[4][threadIdx.x + off]);
+      }
+      __syncthreads();
+   }
+   if (threadIdx.x == 0) {
+      const double pnew = sh[0][0];
+      if (update_k && sc->production > 0.0) {
+         const double knew = sc->keff * pnew / sc->production;
+         sc->dk = knew - sc->keff;
+         sc->keff = knew;
+      }
+      sc->production = pnew;
+      sc->power = sh[1][0];
+      sc->dphi2 = sh[2][0];
+      sc->phi2 = sh[3][0];
+      sc->min_phi = sh[4][0];
+   }
+}
+
+void launch_reduce(double* phi, double* phi_new, const int32_t* mats, const double* nusf,
+                   const double* kapsf, const double* area, const double* dz, int has_z, int G,
+                   int nz, int64_t Sb, double* partials, int nblocks, ReduceScalars* sc,
+                   int update_k, cudaStream_t st) {
+   sn_reduce_kernel<<<nblocks, 256, 0, st>>>(phi, phi_new, mats, nusf, kapsf, area, dz, has_z, G,
+                                             nz, Sb, partials);
+   sn_reduce_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, sc, update_k);
+}
+
+// ------------------------------------------------------------------------------------ LS term
+// rhs[m][g][b] = - sum_e coef[m][e] psi_{m,g}(nbr_e), from the angular flux of the previous
+// sweep (lagged), reference src/SNSolver.cxx:485-516.
+__global__ void sn_ls_rhs_kernel(const SweepGlobals gp, const int32_t* __restrict__ ls_ptr,
+                                 const int32_t* __restrict__ ls_nbr_slot,
+                                 const double* __restrict__ ls_coef, int64_t nnz,
+                                 const int32_t* __restrict__ dir_chunk,
+                                 const int32_t* __restrict__ dir_d,
+                                 const int32_t* const* __restrict__ class_pos_of, double* rhs) {
+   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int64_t total = (int64_t)gp.M * gp.G * gp.nls;
+   if (tid >= total) return;
+   const int b = (int)(tid % gp.nls);
+   const int g = (int)((tid / gp.nls) % gp.G);
+   const int m = (int)(tid / ((int64_t)gp.nls * gp.G));
+   const int gl = gp.gloc[g];
+   const int c = dir_chunk[m];
+   double acc = 0.0;
+   if (gl >= 0 && c >= 0) {
+      const ChunkDev* ch = gp.chunks + c;
+      const ClassDev* cl = gp.classes + ch->cls;
+      const int32_t* pos = class_pos_of[ch->cls];
+      const double* psi = ch->psi + ((int64_t)dir_d[m] * gp.Gown + gl) * gp.nz * cl->S;
+      for (int e = ls_ptr[b]; e < ls_ptr[b + 1]; e++)
+         acc -= ls_coef[(int64_t)m * nnz + e] * psi[pos[ls_nbr_slot[e]]];
+   }
+   rhs[tid] = acc;
+}
+
+void launch_ls_rhs(const SweepGlobals& gp, const int32_t* ls_ptr, const int32_t* ls_nbr_slot,
+                   const double* ls_coef, int64_t nnz, const int32_t* dir_chunk,
+                   const int32_t* dir_d, const int32_t* const* class_pos_of, cudaStream_t st) {
+   const int64_t total = (int64_t)gp.M * gp.G * gp.nls;
+   if (total <= 0) return;
+   sn_ls_rhs_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(
+      gp, ls_ptr, ls_nbr_slot, ls_coef, nnz, dir_chunk, dir_d, class_pos_of,
+      const_cast<double*>(gp.ls_rhs));
+}
+
+// ------------------------------------------------------------------------------------ fields
+__global__ void sn_export_phi_kernel(const double* __restrict__ phi,
+                                     const int32_t* __restrict__ slot_of_xy, double scale, int G,
+                                     int nz, int nxy, int64_t Sb, double* __restrict__ out) {
+   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int64_t total = (int64_t)nz * nxy * G;
+   if (tid >= total) return;
+   const int g = (int)(tid % G);
+   const int64_t i = tid / G;
+   const int k = (int)(i / nxy), c = (int)(i % nxy);
+   out[tid] = scale * phi[((int64_t)g * nz + k) * Sb + slot_of_xy[c]];
+}
+void launch_export_phi(const double* phi, const int32_t* slot_of_xy, double scale, int G, int nz,
+                       int nxy, int64_t Sb, double* out, cudaStream_t st) {
+   const int64_t total = (int64_t)nz * nxy * G;
+   sn_export_phi_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(phi, slot_of_xy, scale, G, nz,
+                                                                    nxy, Sb, out);
+}
+
+// out[i] = scale * V_i * sum_g xs_g[mat][g] * phi[g][i]   (power, production-rate)
+__global__ void sn_export_cell_kernel(const double* __restrict__ phi,
+                                      const int32_t* __restrict__ slot_of_xy,
+                                      const int32_t* __restrict__ mats,
+                                      const double* __restrict__ xs_g,
+                                      const double* __restrict__ area,
+                                      const double* __restrict__ dz, int has_z, double scale, int G,
+                                      int nz, int nxy, int64_t Sb, double* __restrict__ out) {
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= (int64_t)nz * nxy) return;
+   const int k = (int)(i / nxy), c = (int)(i % nxy);
+   const int s = slot_of_xy[c];
+   const int64_t idx = (int64_t)k * Sb + s;
+   const int mat = mats[idx];
+   const double vol = area[s] * (has_z ? dz[k] : 1.0);
+   double acc = 0.0;
+   for (int g = 0; g < G; g++) acc = fma(xs_g[mat * G + g], phi[(int64_t)g * nz * Sb + idx], acc);
+   out[i] = scale * vol * acc;
+}
+void launch_export_cell(const double* phi, const int32_t* slot_of_xy, const int32_t* mats,
+                        const double* xs_g, const double* area, const double* dz, int has_z,
+                        double scale, int G, int nz, int nxy, int64_t Sb, double* out,
+                        cudaStream_t st) {
+   const int64_t total = (int64_t)nz * nxy;
+   sn_export_cell_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(
+      phi, slot_of_xy, mats, xs_g, area, dz, has_z, scale, G, nz, nxy, Sb, out);
+}
+
+// angular flux of one direction m into the reference layout out[(i*G + g)*M + m]
+__global__ void sn_export_psi_kernel(const double* __restrict__ psi_block,
+                                     const int32_t* __restrict__ pos_of,
+                                     const int32_t* __restrict__ slot_of_xy, int d, int m, int Gown,
+                                     const int32_t* __restrict__ gloc, double scale, int G, int M,
+                                     int nz, int nxy, int64_t S, double* __restrict__ out,
+                                     double* __restrict__ minval) {
+   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int64_t total = (int64_t)nz * nxy * G;
+   if (tid >= total) return;
+   const int g = (int)(tid % G);
+   const int64_t i = tid / G;
+   const int k = (int)(i / nxy), c = (int)(i % nxy);
+   const int gl = gloc[g];
+   if (gl < 0) return;
+   const double v = scale * psi_block[(((int64_t)d * Gown + gl) * nz + k) * S + pos_of[slot_of_xy[c]]];
+   out[tid * M + m] = v;
+   if (v < 0.0) *minval = v;     // benign race: any negative value flags the error
+}
+void launch_export_psi(const double* psi_block, const int32_t* pos_of, const int32_t* slot_of_xy,
+                       int d, int m, int Gown, const int32_t* gloc, double scale, int G, int M,
+                       int nz, int nxy, int64_t S, double* out, double* minval, cudaStream_t st) {
+   const int64_t total = (int64_t)nz * nxy * G;
+   sn_export_psi_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(
+      psi_block, pos_of, slot_of_xy, d, m, Gown, gloc, scale, G, M, nz, nxy, S, out, minval);
+}
+
+__global__ void sn_import_phi_kernel(double* __restrict__ phi, const int32_t* __restrict__ slot_of_xy,
+                                     int G, int nz, int nxy, int64_t Sb, const double* __restrict__ in) {
+   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int64_t total = (int64_t)nz * nxy * G;
+   if (tid >= total) return;
+   const int g = (int)(tid % G);
+   const int64_t i = tid / G;
+   const int k = (int)(i / nxy), c = (int)(i % nxy);
+   phi[((int64_t)g * nz + k) * Sb + slot_of_xy[c]] = in[tid];
+}
+void launch_import_phi(double* phi, const int32_t* slot_of_xy, int G, int nz, int nxy, int64_t Sb,
+                       const double* in, cudaStream_t st) {
+   const int64_t total = (int64_t)nz * nxy * G;
+   sn_import_phi_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(phi, slot_of_xy, G, nz, nxy, Sb, in);
+}
+
+__global__ void sn_fill_kernel(double* p, double v, int64_t n) {
+   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+        i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+void launch_fill(double* p, double v, int64_t n, cudaStream_t st) {
+   if (n <= 0) return;
+   int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+   sn_fill_kernel<<<nb, 256, 0, st>>>(p, v, n);
+}
+
+// phi = v on physical cells, 0 in the padding holes
+__global__ void sn_fill_phi_kernel(double* phi, const int32_t* mats, double v, int G, int64_t n) {
+   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+        i += (int64_t)gridDim.x * blockDim.x) {
+      const double x = mats[i] >= 0 ? v : 0.0;
+      for (int g = 0; g < G; g++) phi[(int64_t)g * n + i] = x;
+   }
+}
+void launch_fill_phi(double* phi, const int32_t* mats, double v, int G, int64_t n, cudaStream_t st) {
+   int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+   sn_fill_phi_kernel<<<nb, 256, 0, st>>>(phi, mats, v, G, n);
+}
+
+}  // namespace pampa_sn

@@ -1,0 +1,103 @@
+// sn_kernels.cuh -- device-side structures and kernel launchers of the SN transport layer.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "sn_plan.hpp"
+
+namespace pampa_sn {
+
+// Per ordering class, device pointers into the uploaded plan.
+struct ClassDev {
+   int64_t S;                 // slots of this class (npatch * P)
+   int32_t zdir;              // +1 / -1 / 0
+   int32_t ring;              // smem ring depth
+   int32_t tiles;             // 1: class slot == base slot
+   int32_t pad;
+   const int32_t* cell_of;    // [S] base slot or -1
+   const uint16_t* lvl;       // [S]
+   const int32_t* patch_nlev; // [npatch]
+   const double2* out_vec;    // [S]
+   const int32_t* in_src;     // [FIN_MAX][S]
+   const double2* in_vec;     // [FIN_MAX][S]
+   const int32_t* rout;       // [ROUT_MAX][S]
+   const int32_t* ls_of;      // [S] index into the LS cell list or -1 (nullptr: no LS)
+};
+
+// Per chunk of directions swept together by one CTA.
+struct ChunkDev {
+   int32_t cls;
+   int32_t nd;
+   int32_t m[DT_MAX];         // quadrature index
+   int32_t mrefl[DT_MAX][3];  // mirrored direction about x, y, z
+   double mux[DT_MAX], muy[DT_MAX], muz_abs[DT_MAX], w[DT_MAX];
+   double* psi;               // [nd][Gown][nz][S]
+};
+
+struct SweepGlobals {
+   const ClassDev* classes;
+   const ChunkDev* chunks;
+   const int32_t* gloc;       // [G] local index of an owned group or -1
+   const double* q;           // [G][nz][Sb]
+   double* phi_new;           // [G][nz][Sb] accumulated with atomics
+   const int32_t* mats;       // [nz][Sb] (-1 in holes)
+   const double* sigma_t;     // [mat][G]
+   const double* inv_dz;      // [nz]
+   // reflective boundary buffers (old: read, new: written)
+   const double* bnd_old;     // [M][G][nz][nrf]
+   double* bnd_new;
+   const double* bndz_old;    // [2][M][G][Sb]  (0: -z face, 1: +z face)
+   double* bndz_new;
+   // least-squares lagged correction (2-D / 1-D meshes only)
+   const double* ls_dD;       // [M][nls]
+   const double* ls_rhs;      // [M][G][nls]
+   int64_t Sb;
+   int32_t G, Gown, M, nz, Kc, has_z, nrf, nls;
+   int32_t bcz_minus_refl, bcz_plus_refl;   // 1 if that z boundary is reflective
+   int32_t store_psi;
+};
+
+struct ReduceScalars {        // device-resident iteration state
+   double keff;
+   double production;         // sum V nu-sigma-f phi of the current phi
+   double power;              // sum V kappa-sigma-f phi
+   double dphi2, phi2;        // ||phi_new - phi||^2, ||phi_new||^2 of the last reduce
+   double dk;                 // keff change of the last reduce
+   double min_phi;            // min over cells/groups of phi
+   double pad;
+};
+
+void launch_sweep(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int P, int dt, int fin,
+                  int ring, bool extras, cudaStream_t st);
+cudaError_t configure_sweep_kernels();
+
+void launch_source(const double* phi, double* q, const int32_t* mats, const double* sig_s,
+                   const double* chi, const double* nusf, const ReduceScalars* sc, int G, int nz,
+                   int64_t Sb, cudaStream_t st);
+
+void launch_reduce(double* phi, double* phi_new, const int32_t* mats, const double* nusf,
+                   const double* kapsf, const double* area, const double* dz, int has_z, int G,
+                   int nz, int64_t Sb, double* partials, int nblocks, ReduceScalars* sc,
+                   int update_k, cudaStream_t st);
+
+void launch_ls_rhs(const SweepGlobals& gp, const int32_t* ls_ptr, const int32_t* ls_nbr_slot,
+                   const double* ls_coef, int64_t nnz, const int32_t* dir_chunk,
+                   const int32_t* dir_d, const int32_t* const* class_pos_of, cudaStream_t st);
+
+// field export (reference layouts)
+void launch_export_phi(const double* phi, const int32_t* slot_of_xy, double scale, int G, int nz,
+                       int nxy, int64_t Sb, double* out, cudaStream_t st);
+void launch_export_cell(const double* phi, const int32_t* slot_of_xy, const int32_t* mats,
+                        const double* xs_g, const double* area, const double* dz, int has_z,
+                        double scale, int G, int nz, int nxy, int64_t Sb, double* out,
+                        cudaStream_t st);
+void launch_export_psi(const double* psi_block, const int32_t* pos_of, const int32_t* slot_of_xy,
+                       int d, int m, int Gown, const int32_t* gloc, double scale, int G, int M,
+                       int nz, int nxy, int64_t S, double* out, double* minval, cudaStream_t st);
+void launch_import_phi(double* phi, const int32_t* slot_of_xy, int G, int nz, int nxy, int64_t Sb,
+                       const double* in, cudaStream_t st);
+void launch_fill(double* p, double v, int64_t n, cudaStream_t st);
+void launch_fill_phi(double* phi, const int32_t* mats, double v, int G, int64_t n, cudaStream_t st);
+
+}  // namespace pampa_sn

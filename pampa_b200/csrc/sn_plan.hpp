@@ -1,0 +1,446 @@
+// sn_plan.hpp -- host-side sweep planning for the B200 SN transport layer.
+//
+// Turns the extruded mesh + quadrature into what the sweep kernel consumes:
+//   * a padded "slot" numbering of the xy cells (patch-major: slot = patch*P + lane), shared by
+//     q, phi and the material map, so that a CTA's accesses are contiguous;
+//   * ordering classes: sets of directions with the same upwind face pattern (one per octant on
+//     Cartesian meshes; azimuthal sectors on hexagonal / triangular meshes);
+//   * per class, a partition of the xy cells into patches of <= P cells whose patch graph is
+//     acyclic: the shared 2-D tiles when they are acyclic for the class, otherwise chunks of the
+//     class's own topological (level, lateral) order;
+//   * per slot, the local pipeline level and the upwind sources (in-patch lane, other-patch
+//     slot, reflective boundary face), with the face vectors that give the streaming
+//     coefficients of Appendix A of SURVEY.md (reference: src/SNSolver.cxx:574-597);
+//   * the launch schedule: tasks (chunk of directions, group, patch, z chunk) grouped by
+//     wavefront number = patch level + z chunk.
+//
+// Nothing here touches the GPU; tests exercise it through pampa_sn_plan_check().
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <queue>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pampa_sn.h"
+
+namespace pampa_sn {
+
+constexpr int FIN_MAX = 4;         // incoming lateral faces per cell the kernel is instantiated for
+constexpr int ROUT_MAX = 2;        // outgoing reflective lateral faces per cell
+constexpr int DT_MAX = 10;         // directions per sweep chunk (register-resident chains)
+constexpr int RING_MAX = 4;        // smem ring depth for in-patch upwind values
+constexpr uint16_t LVL_EMPTY = 0xFFFF;
+
+// upwind source codes
+constexpr int32_t SRC_NONE = -1;
+constexpr int32_t SRC_KIND_SHIFT = 28;
+constexpr int32_t SRC_GLOBAL = 0, SRC_LOCAL = 1, SRC_REFL = 2;
+constexpr int32_t SRC_PAYLOAD = 0x0FFFFFFF;
+constexpr int32_t SRC_AXIS_SHIFT = 26;
+
+struct Vec2 { double x, y; };
+
+struct ClassPlan {
+   int zdir = 0;                        // +1: sweep k upward, -1: downward, 0: no z faces
+   std::vector<int> dirs;               // quadrature directions of this class
+   bool tiles = false;                  // true: shares the base tile partition
+   int npatch = 0;
+   int64_t S = 0;                       // slots = npatch * P
+   int fin = 0;                         // max incoming lateral faces
+   int ring = 2;                        // smem ring depth
+   std::vector<int32_t> cell_of;        // [S] base slot (or -1)
+   std::vector<int32_t> pos_of;         // [Sb] base slot -> class slot (or -1)
+   std::vector<uint16_t> lvl;           // [S] local level, LVL_EMPTY for holes
+   std::vector<int32_t> patch_nlev;     // [npatch]
+   std::vector<int32_t> patch_level;    // [npatch] level in the patch graph
+   std::vector<Vec2> out_vec;           // [S] sum over outgoing faces of cf*f/area
+   std::vector<int32_t> in_src;         // [FIN_MAX][S]
+   std::vector<Vec2> in_vec;            // [FIN_MAX][S] cf*f/area of the incoming face
+   std::vector<int32_t> rout;           // [ROUT_MAX][S] reflective face id written by this slot
+};
+
+struct Chunk {
+   int cls = 0;
+   int nd = 0;
+   int m[DT_MAX];                       // quadrature direction indices
+   int64_t psi_offset = 0;              // offset (doubles) of this chunk's psi block
+};
+
+struct Task { int32_t chunk, group, patch, zc; };
+
+struct Plan {
+   int P = 256;
+   int nxy = 0, nz = 1, has_z = 0;
+   int G = 0, M = 0;
+   int npatch_b = 0;
+   int64_t Sb = 0;                      // base slots
+   std::vector<int32_t> slot_of_xy;     // [nxy] xy cell -> base slot
+   std::vector<int32_t> xy_of_slot;     // [Sb] base slot -> xy cell or -1
+   std::vector<ClassPlan> classes;
+   std::vector<int> class_of_dir;       // [M]
+   std::vector<Chunk> chunks;
+   int Kc = 1, nzc = 1;                 // layers per task, z chunks
+   std::vector<std::vector<Task>> waves;  // launch schedule (owned tasks only)
+   int64_t psi_doubles = 0;
+   int num_rfaces = 0;                  // lateral reflective faces (xy cell, face) pairs
+   std::vector<int32_t> rface_axis;     // [num_rfaces]
+   int64_t owned_updates = 0;
+   int tile_classes = 0;
+};
+
+namespace detail {
+
+inline void kd_split(std::vector<int>& ids, int lo, int hi, const double* cx, const double* cy,
+                     int P, std::vector<std::pair<int, int>>& leaves) {
+   if (hi - lo <= P) { leaves.push_back({lo, hi}); return; }
+   double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+   for (int a = lo; a < hi; a++) {
+      x0 = std::min(x0, cx[ids[a]]); x1 = std::max(x1, cx[ids[a]]);
+      y0 = std::min(y0, cy[ids[a]]); y1 = std::max(y1, cy[ids[a]]);
+   }
+   const bool by_x = (x1 - x0) >= (y1 - y0);
+   // split into the smallest number of <= P leaves: left part gets a multiple of P when possible
+   int n = hi - lo;
+   int nleaf = (n + P - 1) / P;
+   int mid = lo + (nleaf / 2) * ((n + nleaf - 1) / nleaf);
+   if (mid <= lo || mid >= hi) mid = lo + n / 2;
+   auto key = [&](int c) { return by_x ? cx[c] : cy[c]; };
+   std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi,
+                    [&](int a, int b) { return key(a) < key(b) || (key(a) == key(b) && a < b); });
+   kd_split(ids, lo, mid, cx, cy, P, leaves);
+   kd_split(ids, mid, hi, cx, cy, P, leaves);
+}
+
+// longest-path levels of a DAG given as upwind adjacency; returns false on a cycle
+inline bool dag_levels(int n, const std::vector<std::vector<int>>& up, std::vector<int>& level) {
+   std::vector<int> indeg(n, 0);
+   std::vector<std::vector<int>> down(n);
+   for (int v = 0; v < n; v++)
+      for (int u : up[v]) { down[u].push_back(v); indeg[v]++; }
+   level.assign(n, 0);
+   std::vector<int> stack;
+   for (int v = 0; v < n; v++) if (indeg[v] == 0) stack.push_back(v);
+   int done = 0;
+   while (!stack.empty()) {
+      int u = stack.back(); stack.pop_back(); done++;
+      for (int v : down[u]) {
+         level[v] = std::max(level[v], level[u] + 1);
+         if (--indeg[v] == 0) stack.push_back(v);
+      }
+   }
+   return done == n;
+}
+
+}  // namespace detail
+
+struct PlanInput {
+   const pampa_sn_mesh* mesh;
+   const pampa_sn_quadrature* quad;
+   int G;
+   pampa_sn_options opts;
+};
+
+inline void build_plan(const PlanInput& in, Plan& pl) {
+   const pampa_sn_mesh& ms = *in.mesh;
+   const pampa_sn_quadrature& qd = *in.quad;
+   const int nxy = ms.num_xy_cells, F = ms.max_xy_faces;
+   if (nxy <= 0 || ms.num_layers <= 0 || F <= 0) throw std::runtime_error("empty mesh");
+   pl.nxy = nxy; pl.nz = ms.num_layers; pl.has_z = ms.has_z_faces ? 1 : 0;
+   pl.G = in.G; pl.M = qd.num_directions;
+   int P = in.opts.patch_cells > 0 ? in.opts.patch_cells : 256;
+   int ti = in.opts.tile_i > 0 ? in.opts.tile_i : 16;
+   int tj = in.opts.tile_j > 0 ? in.opts.tile_j : 16;
+   if (ms.xy_ij) {
+      // thin meshes (1-D slabs, narrow strips): stretch the tile along i instead of wasting lanes
+      int jext = 0;
+      for (int c = 0; c < nxy; c++) jext = std::max(jext, ms.xy_ij[2*c+1] + 1);
+      while (tj > 1 && tj / 2 >= jext) { tj /= 2; ti *= 2; }
+      P = ti * tj;
+   }
+   if (P % 32 != 0 || P > 1024) throw std::runtime_error("patch size must be a multiple of 32, <= 1024");
+   pl.P = P;
+
+   auto bc_type = [&](int nb) -> int {
+      int b = -nb;
+      if (b < 1 || b > ms.num_bcs) return PAMPA_SN_BC_NONE;
+      return ms.bc_types[b];
+   };
+
+   // ---- base partition (class independent) -------------------------------------------------
+   pl.slot_of_xy.assign(nxy, -1);
+   if (ms.xy_ij) {
+      int imax = 0, jmax = 0;
+      for (int c = 0; c < nxy; c++) { imax = std::max(imax, ms.xy_ij[2*c]); jmax = std::max(jmax, ms.xy_ij[2*c+1]); }
+      int ntx = imax / ti + 1, nty = jmax / tj + 1;
+      std::vector<int> tile_id(ntx * nty, -1);
+      int np = 0;
+      for (int c = 0; c < nxy; c++) {           // number the non-empty tiles in first-touch order
+         int t = (ms.xy_ij[2*c+1] / tj) * ntx + ms.xy_ij[2*c] / ti;
+         if (tile_id[t] < 0) tile_id[t] = 0;
+      }
+      for (int t = 0; t < ntx * nty; t++) if (tile_id[t] == 0) tile_id[t] = np++;
+      for (int c = 0; c < nxy; c++) {
+         int i = ms.xy_ij[2*c], j = ms.xy_ij[2*c+1];
+         int t = (j / tj) * ntx + i / ti;
+         pl.slot_of_xy[c] = tile_id[t] * P + (j % tj) * ti + (i % ti);
+      }
+      pl.npatch_b = np;
+   } else {
+      std::vector<int> ids(nxy);
+      std::iota(ids.begin(), ids.end(), 0);
+      std::vector<std::pair<int, int>> leaves;
+      detail::kd_split(ids, 0, nxy, ms.xy_cx, ms.xy_cy, P, leaves);
+      int np = 0;
+      for (auto& lf : leaves) {
+         std::sort(ids.begin() + lf.first, ids.begin() + lf.second);
+         for (int a = lf.first; a < lf.second; a++) pl.slot_of_xy[ids[a]] = np * P + (a - lf.first);
+         np++;
+      }
+      pl.npatch_b = np;
+   }
+   pl.Sb = (int64_t)pl.npatch_b * P;
+   pl.xy_of_slot.assign(pl.Sb, -1);
+   for (int c = 0; c < nxy; c++) {
+      if (pl.xy_of_slot[pl.slot_of_xy[c]] != -1) throw std::runtime_error("duplicate structured (i,j) in xy_ij");
+      pl.xy_of_slot[pl.slot_of_xy[c]] = c;
+   }
+
+   // ---- reflective lateral faces -----------------------------------------------------------
+   std::vector<int32_t> rface_id((size_t)nxy * F, -1);
+   pl.num_rfaces = 0; pl.rface_axis.clear();
+   for (int c = 0; c < nxy; c++)
+      for (int f = 0; f < ms.xy_num_faces[c]; f++) {
+         int nb = ms.xy_neighbor[(size_t)c * F + f];
+         if (nb >= 0) continue;
+         int t = bc_type(nb);
+         if (t == PAMPA_SN_BC_REFLECTIVE) {
+            double fx = ms.xy_face_fx[(size_t)c * F + f], fy = ms.xy_face_fy[(size_t)c * F + f];
+            double len = std::sqrt(fx * fx + fy * fy);
+            int axis = -1;                         // intended per-cell test of SNSolver.cxx:539-543
+            if (std::fabs(fx / len) > 1.0 - 1.0e-6) axis = 0;
+            if (std::fabs(fy / len) > 1.0 - 1.0e-6) axis = 1;
+            if (axis < 0) throw std::runtime_error("reflected direction not found");
+            rface_id[(size_t)c * F + f] = pl.num_rfaces++;
+            pl.rface_axis.push_back(axis);
+         } else if (t != PAMPA_SN_BC_VACUUM) {
+            throw std::runtime_error("boundary condition not implemented");
+         }
+      }
+   if (pl.has_z) {
+      for (int b : {ms.bc_minus_z, ms.bc_plus_z}) {
+         int t = (b >= 1 && b <= ms.num_bcs) ? ms.bc_types[b] : PAMPA_SN_BC_NONE;
+         if (t != PAMPA_SN_BC_VACUUM && t != PAMPA_SN_BC_REFLECTIVE)
+            throw std::runtime_error("boundary condition not implemented");
+      }
+   }
+
+   // ---- ordering classes -------------------------------------------------------------------
+   const double eps = 1.0e-14;
+   std::map<std::vector<uint8_t>, int> class_key;
+   pl.class_of_dir.assign(pl.M, -1);
+   pl.classes.clear();
+   std::vector<std::vector<uint8_t>> class_flags;   // incoming flag per (xy cell, face)
+   for (int m = 0; m < pl.M; m++) {
+      const double ox = qd.directions[3*m], oy = qd.directions[3*m+1], oz = qd.directions[3*m+2];
+      std::vector<uint8_t> key((size_t)nxy * F + 1, 0);
+      for (int c = 0; c < nxy; c++)
+         for (int f = 0; f < ms.xy_num_faces[c]; f++) {
+            size_t a = (size_t)c * F + f;
+            double w = ox * ms.xy_face_fx[a] + oy * ms.xy_face_fy[a];
+            key[a] = (w > eps) ? 1 : (w < -eps ? 2 : 0);
+         }
+      key[(size_t)nxy * F] = pl.has_z ? (oz > 0 ? 1 : 2) : 0;
+      auto it = class_key.find(key);
+      int ci;
+      if (it == class_key.end()) {
+         ci = (int)pl.classes.size();
+         class_key.emplace(key, ci);
+         ClassPlan cp; cp.zdir = pl.has_z ? (oz > 0 ? 1 : -1) : 0;
+         pl.classes.push_back(cp);
+         class_flags.push_back(key);
+      } else ci = it->second;
+      pl.classes[ci].dirs.push_back(m);
+      pl.class_of_dir[m] = ci;
+   }
+   class_key.clear();
+
+   // ---- per-class patches, levels, sources ---------------------------------------------------
+   pl.tile_classes = 0;
+   for (size_t ci = 0; ci < pl.classes.size(); ci++) {
+      ClassPlan& cp = pl.classes[ci];
+      const std::vector<uint8_t>& flg = class_flags[ci];
+      // xy upwind graph
+      std::vector<std::vector<int>> up(nxy);
+      int fin = 0;
+      for (int c = 0; c < nxy; c++) {
+         int cnt = 0;
+         for (int f = 0; f < ms.xy_num_faces[c]; f++) {
+            size_t a = (size_t)c * F + f;
+            if (flg[a] != 2) continue;
+            int nb = ms.xy_neighbor[a];
+            if (nb >= 0) { up[c].push_back(nb); cnt++; }
+            else if (bc_type(nb) == PAMPA_SN_BC_REFLECTIVE) cnt++;
+         }
+         fin = std::max(fin, cnt);
+      }
+      if (fin > FIN_MAX) throw std::runtime_error("cell with more than 4 incoming lateral faces");
+      cp.fin = fin;
+      std::vector<int> glevel;
+      if (!detail::dag_levels(nxy, up, glevel)) throw std::runtime_error("cyclic upwind dependency in the xy mesh");
+
+      // candidate 1: base tiles
+      std::vector<int32_t> patch_of(nxy), lane_of(nxy);
+      auto try_partition = [&](int np) -> bool {
+         // patch graph
+         std::vector<std::vector<int>> pup(np);
+         for (int c = 0; c < nxy; c++)
+            for (int u : up[c]) if (patch_of[u] != patch_of[c]) pup[patch_of[c]].push_back(patch_of[u]);
+         for (auto& v : pup) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+         std::vector<int> plevel;
+         if (!detail::dag_levels(np, pup, plevel)) return false;
+         cp.npatch = np; cp.S = (int64_t)np * P;
+         cp.patch_level.assign(plevel.begin(), plevel.end());
+         return true;
+      };
+      for (int c = 0; c < nxy; c++) { patch_of[c] = pl.slot_of_xy[c] / P; lane_of[c] = pl.slot_of_xy[c] % P; }
+      cp.tiles = try_partition(pl.npatch_b);
+      if (cp.tiles) pl.tile_classes++;
+      else {
+         // candidate 2: chunks of the (level, lateral) order -- acyclic by construction
+         double ox = 0, oy = 0;
+         for (int m : cp.dirs) { ox += qd.directions[3*m]; oy += qd.directions[3*m+1]; }
+         std::vector<int> ord(nxy);
+         std::iota(ord.begin(), ord.end(), 0);
+         std::vector<double> lat(nxy);
+         for (int c = 0; c < nxy; c++) lat[c] = -oy * ms.xy_cx[c] + ox * ms.xy_cy[c];
+         std::sort(ord.begin(), ord.end(), [&](int a, int b) {
+            if (glevel[a] != glevel[b]) return glevel[a] < glevel[b];
+            if (lat[a] != lat[b]) return lat[a] < lat[b];
+            return a < b; });
+         for (int a = 0; a < nxy; a++) { patch_of[ord[a]] = a / P; lane_of[ord[a]] = a % P; }
+         if (!try_partition((nxy + P - 1) / P)) throw std::runtime_error("internal: level-chunk partition is cyclic");
+      }
+      // slot tables
+      const int64_t S = cp.S;
+      cp.cell_of.assign(S, -1); cp.pos_of.assign(pl.Sb, -1);
+      for (int c = 0; c < nxy; c++) {
+         int64_t s = (int64_t)patch_of[c] * P + lane_of[c];
+         cp.cell_of[s] = pl.slot_of_xy[c];
+         cp.pos_of[pl.slot_of_xy[c]] = (int32_t)s;
+      }
+      // local levels: longest path over in-patch edges
+      {
+         std::vector<std::vector<int>> lup(nxy);
+         for (int c = 0; c < nxy; c++)
+            for (int u : up[c]) if (patch_of[u] == patch_of[c]) lup[c].push_back(u);
+         std::vector<int> ll;
+         detail::dag_levels(nxy, lup, ll);
+         cp.lvl.assign(S, LVL_EMPTY);
+         cp.patch_nlev.assign(cp.npatch, 1);
+         int maxdiff = 1;
+         for (int c = 0; c < nxy; c++) {
+            if (ll[c] >= LVL_EMPTY) throw std::runtime_error("patch pipeline too deep");
+            cp.lvl[(int64_t)patch_of[c] * P + lane_of[c]] = (uint16_t)ll[c];
+            cp.patch_nlev[patch_of[c]] = std::max(cp.patch_nlev[patch_of[c]], ll[c] + 1);
+            for (int u : lup[c]) maxdiff = std::max(maxdiff, ll[c] - ll[u]);
+         }
+         cp.ring = std::min(RING_MAX, maxdiff + 1);
+         // sources and vectors
+         cp.out_vec.assign(S, Vec2{0, 0});
+         cp.in_src.assign((size_t)FIN_MAX * S, SRC_NONE);
+         cp.in_vec.assign((size_t)FIN_MAX * S, Vec2{0, 0});
+         cp.rout.assign((size_t)ROUT_MAX * S, -1);
+         for (int c = 0; c < nxy; c++) {
+            const int64_t s = (int64_t)patch_of[c] * P + lane_of[c];
+            int nin = 0, nro = 0;
+            const double ia = 1.0 / ms.xy_area[c];
+            for (int f = 0; f < ms.xy_num_faces[c]; f++) {
+               size_t a = (size_t)c * F + f;
+               const double vx = ms.xy_face_cf[a] * ms.xy_face_fx[a] * ia;
+               const double vy = ms.xy_face_cf[a] * ms.xy_face_fy[a] * ia;
+               const int nb = ms.xy_neighbor[a];
+               if (flg[a] == 1) {
+                  cp.out_vec[s].x += vx; cp.out_vec[s].y += vy;
+                  if (nb < 0 && rface_id[a] >= 0) {
+                     if (nro >= ROUT_MAX) throw std::runtime_error("cell with more than 2 outgoing reflective faces");
+                     cp.rout[(size_t)nro * S + s] = rface_id[a]; nro++;
+                  }
+               } else if (flg[a] == 2) {
+                  int32_t code = SRC_NONE;
+                  if (nb >= 0) {
+                     if (patch_of[nb] == patch_of[c] && ll[c] - ll[nb] < cp.ring)
+                        code = (SRC_LOCAL << SRC_KIND_SHIFT) | lane_of[nb];
+                     else
+                        code = (SRC_GLOBAL << SRC_KIND_SHIFT) | (int32_t)((int64_t)patch_of[nb] * P + lane_of[nb]);
+                  } else if (rface_id[a] >= 0) {
+                     code = (SRC_REFL << SRC_KIND_SHIFT) | (pl.rface_axis[rface_id[a]] << SRC_AXIS_SHIFT) | rface_id[a];
+                  }
+                  if (code != SRC_NONE) {
+                     cp.in_src[(size_t)nin * S + s] = code;
+                     cp.in_vec[(size_t)nin * S + s] = Vec2{vx, vy};
+                     nin++;
+                  }
+               }
+            }
+         }
+      }
+   }
+   class_flags.clear();
+
+   // ---- chunks of directions ---------------------------------------------------------------
+   pl.chunks.clear();
+   pl.psi_doubles = 0;
+   for (size_t ci = 0; ci < pl.classes.size(); ci++) {
+      const ClassPlan& cp = pl.classes[ci];
+      int n = (int)cp.dirs.size();
+      int nch = (n + DT_MAX - 1) / DT_MAX;
+      int per = (n + nch - 1) / nch;
+      for (int a = 0; a < n; a += per) {
+         Chunk ch; ch.cls = (int)ci; ch.nd = std::min(per, n - a);
+         for (int d = 0; d < DT_MAX; d++) ch.m[d] = d < ch.nd ? cp.dirs[a + d] : -1;
+         pl.chunks.push_back(ch);
+      }
+   }
+
+   // ---- z chunks and the launch schedule ---------------------------------------------------
+   int Kc = pl.nz;
+   if (in.opts.z_chunk > 0) Kc = std::min(pl.nz, in.opts.z_chunk);
+   else if (pl.has_z && pl.tile_classes < (int)pl.classes.size()) Kc = std::min(pl.nz, 32);
+   pl.Kc = Kc; pl.nzc = (pl.nz + Kc - 1) / Kc;
+
+   const int rank = in.opts.rank, nr = std::max(1, in.opts.num_ranks);
+   int maxw = 0;
+   for (auto& cp : pl.classes)
+      for (int p = 0; p < cp.npatch; p++) maxw = std::max(maxw, cp.patch_level[p] + pl.nzc);
+   pl.waves.assign(maxw, {});
+   pl.owned_updates = 0;
+   for (size_t ch = 0; ch < pl.chunks.size(); ch++) {
+      const Chunk& c = pl.chunks[ch];
+      const ClassPlan& cp = pl.classes[c.cls];
+      for (int g = 0; g < pl.G; g++) {
+         bool mine = in.opts.shard_mode == 1 ? (g % nr == rank) : ((int)(ch % nr) == rank);
+         if (!mine) continue;
+         pl.owned_updates += (int64_t)c.nd * nxy * pl.nz;
+         for (int p = 0; p < cp.npatch; p++)
+            for (int zc = 0; zc < pl.nzc; zc++)
+               pl.waves[cp.patch_level[p] + zc].push_back(Task{(int32_t)ch, g, p, zc});
+      }
+   }
+   // drop empty waves (ranks that own nothing at some wavefront number)
+   pl.waves.erase(std::remove_if(pl.waves.begin(), pl.waves.end(),
+                                 [](const std::vector<Task>& w) { return w.empty(); }), pl.waves.end());
+   // psi storage: per chunk [nd][G][nz][S_class]
+   for (auto& c : pl.chunks) {
+      c.psi_offset = pl.psi_doubles;
+      pl.psi_doubles += (int64_t)c.nd * pl.G * pl.nz * pl.classes[c.cls].S;
+   }
+}
+
+}  // namespace pampa_sn

@@ -1,0 +1,168 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle.
+
+Tolerances are the ones BASELINE.json's north_star states: k-eff within 1 pcm (1e-5), scalar flux
+within 1e-5 relative L2 and 1e-4 max-relative per cell and group.  The solves are converged much
+tighter than that (1e-10 / 1e-9), so the observed differences are ~1e-8."""
+import math
+
+import numpy as np
+import pytest
+
+import util
+from oracle import pampa_oracle as orc
+from pampa_b200 import problem as pb
+from pampa_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+TOL_K, TOL_L2, TOL_MAX = 1.0e-5, 1.0e-5, 1.0e-4
+
+
+def _solve(em, xs, quad, ls=None, **opts):
+    dev = pb.SNDevice(em, xs, quad, ls, **opts)
+    k, it = dev.solve_keff(tol_k=1e-11, tol_phi=1e-9, max_it=20000)
+    return dev, k, it
+
+
+def _check_solution(dev, k, sol_keff, sol_phi, sol_power):
+    phi = dev.get("scalar-flux").reshape(sol_phi.shape)
+    q = dev.get("power")
+    assert abs(k - sol_keff) < TOL_K, (k, sol_keff)
+    assert util.rel_l2(phi, sol_phi) < TOL_L2
+    assert util.max_rel(phi, sol_phi) < TOL_MAX
+    assert abs(q.sum() - sol_power.sum()) < 1e-9 * abs(sol_power.sum())
+    assert util.rel_l2(q, sol_power) < TOL_L2
+
+
+@pytest.mark.parametrize("name", ["slabs_s2", "slabs_s4", "pwr_cartesian_s2", "pwr_unstructured_s2",
+                                  "pwr_cartesian_s2_lsoff", "pwr_cartesian_s8_lsoff"])
+def test_reference_cases(name):
+    """The SN cases the reference ships (test/check_ref.txt:32,53,234,415) and two variants."""
+    em, xs, quad, ls, z = util.load_golden(name)
+    dev, k, it = _solve(em, xs, quad, ls)
+    gold = float(z["golden_keff"])
+    if not math.isnan(gold):
+        assert "%.6f" % k == "%.6f" % gold          # what check.sh diffs
+    _check_solution(dev, k, float(z["keff"]), z["phi"], z["power"])
+    P = dev.get("production-rate")
+    assert util.rel_l2(P, z["production"]) < TOL_L2
+    if "psi" in z:
+        psi = dev.get("angular-flux").reshape(z["psi"].shape)
+        assert util.rel_l2(psi, z["psi"]) < TOL_L2
+    dev.close()
+
+
+def _oracle_cart(dx, dy, dz, mats, bcs, xs, quad, G):
+    names = ["-x", "+x"] + (["-y", "+y"] if dy is not None else []) + (["-z", "+z"] if dz is not None else [])
+    obcs = [0] + [{pb.BC_VACUUM: orc.VACUUM, pb.BC_REFLECTIVE: orc.REFLECTIVE}[(bcs or {}).get(n, pb.BC_VACUUM)]
+                  for n in names]
+    mesh = orc.build_cartesian_mesh(dx, dy, dz, np.asarray(mats).reshape(-1), names, obcs)
+    op = orc.build_operator(mesh, util.xs_to_oracle(xs), G, 0, 1.0, "off", obcs, quad=util.quad_to_oracle(quad))
+    return mesh, op
+
+
+def test_single_sweep_cartesian_3d():
+    """Kernel-1 unit parity: one sweep with a frozen source equals T^-1 q of the oracle."""
+    rng = np.random.default_rng(7)
+    nx, ny, nz, G = 21, 18, 11, 3
+    dx, dy, dz = rng.uniform(0.5, 1.5, nx), rng.uniform(0.5, 1.5, ny), rng.uniform(0.5, 1.5, nz)
+    mats = rng.integers(0, 2, size=(nz, ny, nx))
+    xs = syn.synthetic_xs(G, seed=3)
+    quad = syn.level_symmetric(4)
+    em = syn.cartesian_mesh(dx, dy, dz, mats)
+    mesh, op = _oracle_cart(dx, dy, dz, mats, None, xs, quad, G)
+    import scipy.sparse.linalg as spla
+    N, M = op.N, op.M
+    phi0 = rng.uniform(0.5, 1.5, size=(N, G))
+    keff = 0.9
+    qd = np.einsum("nfg,nf->ng", op.sig_s, phi0) + op.chi * np.sum(op.nusf * phi0, axis=1)[:, None] / keff
+    b = np.repeat((qd * op.vol[:, None]).reshape(N * G), M)
+    psi = spla.splu(op.T.tocsc()).solve(b).reshape(N, G, M)
+    for opts in ({}, {"z_chunk": 4}, {"tile_i": 8, "tile_j": 4}):
+        dev = pb.SNDevice(em, xs, quad, **opts)
+        dev.set("flux-moments", phi0.reshape(-1))
+        dev.source(keff)
+        dev.sweep()
+        dev.reduce()
+        got_psi = dev.get("angular-flux").reshape(N, G, M)
+        got_phi = dev.get("flux-moments").reshape(N, G)
+        assert util.rel_l2(got_psi, psi) < 1e-12
+        assert util.max_rel(got_phi, psi @ op.w) < 1e-11
+        dev.close()
+
+
+def test_keff_cartesian_3d_reflective():
+    """3-D Cartesian core with void corner cells, reflective -x/-y/-z and vacuum +x/+y/+z, S4."""
+    nx, ny, nz, G = 12, 12, 8, 2
+    mats = np.zeros((nz, ny, nx), dtype=int)
+    mats[:, :, 8:] = 1; mats[:, 8:, :] = 1; mats[6:] = 1
+    mats[:, 10:, 10:] = -1
+    xs = syn.synthetic_xs(G, seed=11)
+    xs.nu_sigma_fission[0] *= 4.0; xs.kappa_sigma_fission[0] *= 4.0
+    quad = syn.level_symmetric(4)
+    bcs = {"-x": pb.BC_REFLECTIVE, "-y": pb.BC_REFLECTIVE, "-z": pb.BC_REFLECTIVE}
+    h = np.full(nx, 2.0)
+    em = syn.cartesian_mesh(h, h, np.full(nz, 2.5), mats, bcs)
+    mesh, op = _oracle_cart(h, h, np.full(nz, 2.5), mats, bcs, xs, quad, G)
+    sol = orc.solve_matrix_free(op)
+    dev, k, it = _solve(em, xs, quad)
+    _check_solution(dev, k, sol.keff, sol.phi, sol.power)
+    psi = dev.get("angular-flux").reshape(sol.psi.shape)
+    assert util.rel_l2(psi, sol.psi) < TOL_L2
+    dev.close()
+
+
+def _hex_problem(nrings, nz, G, order, seed):
+    mesh_d, xs, (points, cells) = syn.hex_core(nrings, nz, pitch=2.0, dz=3.0, num_groups=G, seed=seed)
+    xs.nu_sigma_fission[0] *= 4.0; xs.kappa_sigma_fission[0] *= 4.0
+    quad = syn.level_symmetric(order)
+    bnames = ["-z", "+z", "exterior"]
+    obcs = [0, orc.VACUUM, orc.VACUUM, orc.VACUUM]
+    omesh = orc.build_unstructured_mesh(points, cells, np.full(nz, 3.0), mesh_d.materials, bnames, ["exterior"],
+                                        [[]], 2, obcs, 3)
+    # the reference numbers the default boundary by its xy ordinal (quirk C.8): ordinal 2 -> index 3 here
+    op = orc.build_operator(omesh, util.xs_to_oracle(xs), G, 0, 1.0, "off", obcs, quad=util.quad_to_oracle(quad))
+    return mesh_d, xs, quad, op
+
+
+def test_single_sweep_hex_3d():
+    """Hexagonal prisms: several ordering classes per octant, level-chunk patches."""
+    rng = np.random.default_rng(5)
+    em, xs, quad, op = _hex_problem(6, 5, 2, 8, seed=2)
+    import scipy.sparse.linalg as spla
+    N, G, M = op.N, op.G, op.M
+    phi0 = rng.uniform(0.5, 1.5, size=(N, G))
+    qd = np.einsum("nfg,nf->ng", op.sig_s, phi0) + op.chi * np.sum(op.nusf * phi0, axis=1)[:, None]
+    b = np.repeat((qd * op.vol[:, None]).reshape(N * G), M)
+    psi = spla.splu(op.T.tocsc()).solve(b).reshape(N, G, M)
+    for opts in ({}, {"patch_cells": 32}, {"patch_cells": 64, "z_chunk": 2}):
+        dev = pb.SNDevice(em, xs, quad, **opts)
+        dev.set("flux-moments", phi0.reshape(-1))
+        dev.source(1.0)
+        dev.sweep()
+        dev.reduce()
+        got_psi = dev.get("angular-flux").reshape(N, G, M)
+        assert util.rel_l2(got_psi, psi) < 1e-12
+        dev.close()
+
+
+def test_keff_hex_3d():
+    em, xs, quad, op = _hex_problem(5, 6, 2, 4, seed=4)
+    sol = orc.solve_matrix_free(op)
+    dev, k, it = _solve(em, xs, quad, patch_cells=64)
+    _check_solution(dev, k, sol.keff, sol.phi, sol.power)
+    dev.close()
+
+
+def test_errors_are_loud():
+    """Wrong inputs fail with the reference's messages instead of computing something else."""
+    em, xs, quad, ls, z = util.load_golden("slabs_s2")
+    em.bc_types = [0, pb.BC_VACUUM, 0]
+    with pytest.raises(pb.SNError, match="boundary condition not implemented"):
+        pb.SNDevice(em, xs, quad)
+    em.bc_types = [0, pb.BC_VACUUM, pb.BC_VACUUM]
+    xs.nu_sigma_fission[:] = 0.0; xs.kappa_sigma_fission[:] = 0.0
+    dev = pb.SNDevice(em, xs, quad)
+    with pytest.raises(pb.SNError):
+        dev.solve_keff(max_it=5)
+    dev.close()
