@@ -86,7 +86,11 @@ struct pampa_sn_handle {
 
    // iteration state
    ReduceScalars sc{};
-   double scale = 1.0;         // normalisation of the last solve: fields = scale * device values
+   // Normalisation of the last solve: fields = scale * device values.  The reference forms
+   // phi = 4 pi sum_m w_m psi and then rescales phi and psi separately to the requested power
+   // (src/NeutronicSolver.cxx:46-78, src/SNSolver.cxx:302-341), so the 4 pi cancels and both
+   // end up as scale * (device value), scale = power / sum_i V_i sum_g kappa-sigma-f phi~.
+   double scale = 1.0;
    double keff = 1.0;
    bool solved = false;
    double last_sweep_ms = 0, last_source_ms = 0, last_reduce_ms = 0;
@@ -632,15 +636,15 @@ int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
    SN_CUDA(h, cudaMalloc(&d_out, (size_t)count * sizeof(double)));
    int rc = 0;
    if (s == "scalar-flux") {
-      launch_export_phi(h->d_phi, h->d_slot_of_xy, 4.0 * M_PI * h->scale, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
+      launch_export_phi(h->d_phi, h->d_slot_of_xy, h->scale, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
    } else if (s == "flux-moments") {      // raw device moments sum_m w_m psi, no normalisation
       launch_export_phi(h->d_phi, h->d_slot_of_xy, 1.0, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
    } else if (s == "power") {
       launch_export_cell(h->d_phi, h->d_slot_of_xy, h->d_mats, h->d_kapsf, h->d_area, h->d_dz, pl.has_z,
-                         4.0 * M_PI * h->scale, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
+                         h->scale, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
    } else if (s == "production-rate") {
       launch_export_cell(h->d_phi, h->d_slot_of_xy, h->d_mats, h->d_nusf, h->d_area, h->d_dz, pl.has_z,
-                         4.0 * M_PI * h->scale / h->keff, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
+                         h->scale / h->keff, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
    } else {   // angular-flux
       cudaMemsetAsync(d_out, 0, (size_t)count * sizeof(double), h->stream);
       double* d_min = nullptr;
