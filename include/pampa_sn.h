@@ -104,6 +104,7 @@ typedef struct {
    int32_t rank, num_ranks;      /* angle/group sharding; (0,1) for one GPU */
    int32_t shard_mode;           /* 0: shard sweep chunks (angle sets), 1: shard energy groups */
    int32_t verbose;
+   int32_t dt_max;               /* directions swept together per CTA, 1..10 (0: default) */
 } pampa_sn_options;
 
 void pampa_sn_default_options(pampa_sn_options* opts);

@@ -148,11 +148,7 @@ int dev_upload(pampa_sn_handle* h, T** p, const std::vector<T>& v) {
    return dev_upload(h, p, v.data(), (int64_t)v.size());
 }
 
-int dt_template(int nd) {
-   const int opts[] = {1, 2, 3, 4, 5, 6, 8, 10};
-   for (int o : opts) if (nd <= o) return o;
-   return 10;
-}
+int dt_template(int nd) { return nd; }      // one instantiation per chunk size 1..DT_MAX
 
 int upload_xs(pampa_sn_handle* h, const pampa_sn_xs* xs, bool first) {
    const int G = xs->num_groups, nm = xs->num_materials;
@@ -193,8 +189,7 @@ int do_sweep(pampa_sn_handle* h) {
       h->launches++;
    }
    for (const LaunchGroup& lg : h->groups) {
-      launch_sweep(gp, h->d_tasks + lg.offset, lg.count, h->plan.P, lg.dt, lg.fin, lg.ring, lg.extras,
-                   h->stream);
+      launch_sweep(gp, h->d_tasks + lg.offset, lg.count, lg.dt, lg.fin, lg.ring, lg.extras, h->stream);
       h->launches++;
    }
    h->bnd_cur = 1 - h->bnd_cur;      // what this sweep wrote is what the next one reads
@@ -304,7 +299,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
    if (!mesh || !xs || !quad) { h->err = "null input"; return fail(1); }
    if (h->opts.num_ranks < 1 || h->opts.rank < 0 || h->opts.rank >= h->opts.num_ranks) { h->err = "wrong rank"; return fail(1); }
    if (h->opts.store_psi != 1) { h->err = "store_psi = 0 is not implemented"; return fail(1); }
-   if (h->opts.patch_cells > 256) { h->err = "patch_cells must be <= 256"; return fail(1); }
+   if (h->opts.patch_cells > PS) { h->err = "patch_cells must be <= 256"; return fail(1); }
    h->G = xs->num_groups; h->M = quad->num_directions; h->nmat = xs->num_materials;
    for (int64_t i = 0; i < (int64_t)mesh->num_layers * mesh->num_xy_cells; i++)
       if (mesh->materials[i] < 0 || mesh->materials[i] >= xs->num_materials) { h->err = "wrong material index"; return fail(1); }
@@ -325,7 +320,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       build_plan(PlanInput{mesh, quad, h->G, h->opts}, h->plan);
    } catch (const std::exception& ex) { h->err = ex.what(); return fail(1); }
    Plan& pl = h->plan;
-   if (pl.P > 256) { h->err = "patch size must be <= 256"; return fail(1); }
+   if (pl.P != PS) { h->err = "internal: patch stride must be 256"; return fail(1); }
 
    auto body = [&]() -> int {
       SN_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -425,7 +420,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       for (size_t ci = 0; ci < pl.classes.size(); ci++) {
          const ClassPlan& cp = pl.classes[ci];
          ClassDev& cd = cdev[ci];
-         cd.S = cp.S; cd.zdir = cp.zdir; cd.ring = cp.ring; cd.tiles = cp.tiles ? 1 : 0; cd.pad = 0;
+         cd.S = cp.S; cd.zdir = cp.zdir; cd.ring = cp.ring; cd.tiles = cp.tiles ? 1 : 0; cd.npatch = cp.npatch;
          int32_t *d_cell_of, *d_patch_nlev, *d_in_src, *d_rout, *d_ls_of = nullptr;
          uint16_t* d_lvl; Vec2 *d_out_vec, *d_in_vec;
          if (dev_upload(h, &d_cell_of, cp.cell_of) || dev_upload(h, &d_lvl, cp.lvl) ||
@@ -658,8 +653,8 @@ int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
          ChunkDev cd;
          cudaMemcpyAsync(&cd, h->d_chunks + c, sizeof(ChunkDev), cudaMemcpyDeviceToHost, h->stream);
          cudaStreamSynchronize(h->stream);
-         launch_export_psi(cd.psi, h->d_pos_of[ch.cls], h->d_slot_of_xy, h->dir_d[m], m, h->Gown, h->d_gloc,
-                           h->scale, h->G, h->M, pl.nz, pl.nxy, cp.S, d_out, d_min, h->stream);
+         launch_export_psi(cd.psi, h->d_pos_of[ch.cls], h->d_slot_of_xy, h->dir_d[m], ch.nd, m, h->d_gloc,
+                           h->scale, h->G, h->M, pl.nz, pl.nxy, cp.npatch, d_out, d_min, h->stream);
       }
       double mn = 0.0;
       cudaMemcpyAsync(&mn, d_min, sizeof(double), cudaMemcpyDeviceToHost, h->stream);

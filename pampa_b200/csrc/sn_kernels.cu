@@ -20,21 +20,25 @@ namespace pampa_sn {
 
 __device__ __forceinline__ double ldcg_f64(const double* p) { return __ldcg(p); }
 
+// One CTA = one sweep task.  PS (= 256) threads, thread <-> xy cell of the patch.
+//
+// psi layout of a chunk: [owned group][layer][patch][direction][lane] -- the DT x 256 values a CTA
+// produces in one pipeline step are one contiguous block, every store / patch-boundary load is
+// a fixed immediate offset (d * 2 KB) from one running pointer.
 template <int DT, int FIN, bool EXTRAS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PS, 2)
 sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    extern __shared__ double smem[];
    const Task tk = tasks[blockIdx.x];
    const ChunkDev* __restrict__ ch = gp.chunks + tk.chunk;
    const ClassDev* __restrict__ cl = gp.classes + ch->cls;
-   const int P = blockDim.x, t = threadIdx.x;
-   const int64_t S = cl->S;
+   const int t = threadIdx.x;
    const int64_t Sb = gp.Sb;
-   const int64_t slot = (int64_t)tk.patch * P + t;
+   const int64_t slot = (int64_t)tk.patch * PS + t;
    const int g = tk.group;
    const int gl = gp.gloc[g];
-   const int nd = ch->nd;
    const int nz = gp.nz;
+   const int npatch = cl->npatch;
    const int zdir = cl->zdir;
    const int RD = cl->ring;
    const int lv = cl->lvl[slot];
@@ -44,49 +48,51 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    const int kcnt = min(gp.Kc, nz - kp0);
    const int nsteps = cl->patch_nlev[tk.patch] + kcnt - 1;
 
-   double* ring = smem;                       // [RD][DT][P]
-   double* s_muz = smem + (size_t)RD * DT * P;   // [DT]
-   double* s_w = s_muz + DT;                  // [DT]
+   double* ring = smem;                              // [RD][DT][PS]
+   double* s_mux = smem + (size_t)RD * DT * PS;      // [DT] each
+   double* s_muy = s_mux + DT;
+   double* s_muz = s_muy + DT;
+   double* s_w = s_muz + DT;
    if (t < DT) {
-      s_muz[t] = (t < nd && gp.has_z) ? ch->muz_abs[t] : 0.0;
-      s_w[t] = t < nd ? ch->w[t] : 0.0;
+      s_mux[t] = ch->mux[t];
+      s_muy[t] = ch->muy[t];
+      s_muz[t] = gp.has_z ? ch->muz_abs[t] : 0.0;
+      s_w[t] = ch->w[t];
    }
+   __syncthreads();
 
    // streaming coefficients of this cell for the DT directions (per unit volume)
-   double a[FIN][DT], so[DT];
+   double a[FIN][DT];
    int src[FIN];
-   {
-      const double2 ov = valid ? cl->out_vec[slot] : make_double2(0.0, 0.0);
+   const double* gsrc[FIN];                          // running pointers of patch-boundary sources
+   const double2 ov = valid ? cl->out_vec[slot] : make_double2(0.0, 0.0);
+   const int kfirst = zdir >= 0 ? kp0 : nz - 1 - kp0;
+   const int64_t kstride_psi = (int64_t)(zdir >= 0 ? 1 : -1) * npatch * (DT * PS);
+   double* psi_w = ch->psi + ((((int64_t)gl * nz + kfirst) * npatch + tk.patch) * DT) * PS + t;
 #pragma unroll
-      for (int d = 0; d < DT; d++) {
-         const double mx = d < nd ? ch->mux[d] : 0.0, my = d < nd ? ch->muy[d] : 0.0;
-         so[d] = mx * ov.x + my * ov.y;
-      }
+   for (int s = 0; s < FIN; s++) {
+      src[s] = valid ? cl->in_src[(size_t)s * cl->S + slot] : SRC_NONE;
+      const double2 iv = valid ? cl->in_vec[(size_t)s * cl->S + slot] : make_double2(0.0, 0.0);
 #pragma unroll
-      for (int s = 0; s < FIN; s++) {
-         src[s] = valid ? cl->in_src[(size_t)s * S + slot] : SRC_NONE;
-         const double2 iv = valid ? cl->in_vec[(size_t)s * S + slot] : make_double2(0.0, 0.0);
-#pragma unroll
-         for (int d = 0; d < DT; d++) {
-            const double mx = d < nd ? ch->mux[d] : 0.0, my = d < nd ? ch->muy[d] : 0.0;
-            a[s][d] = -(mx * iv.x + my * iv.y);
-         }
-      }
+      for (int d = 0; d < DT; d++) a[s][d] = -(s_mux[d] * iv.x + s_muy[d] * iv.y);
+      const int pay = src[s] & SRC_PAYLOAD;
+      gsrc[s] = ch->psi + ((((int64_t)gl * nz + kfirst) * npatch + (pay >> 8)) * DT) * PS + (pay & (PS - 1));
    }
    int rout[ROUT_MAX];
    int lsb = -1;
    if (EXTRAS) {
 #pragma unroll
-      for (int r = 0; r < ROUT_MAX; r++) rout[r] = valid ? cl->rout[(size_t)r * S + slot] : -1;
+      for (int r = 0; r < ROUT_MAX; r++) rout[r] = valid ? cl->rout[(size_t)r * cl->S + slot] : -1;
       if (cl->ls_of != nullptr && valid) lsb = cl->ls_of[slot];
    }
 
-   const int64_t dstride = (int64_t)gp.Gown * nz * S;
-   double* __restrict__ psi_g = ch->psi + (int64_t)gl * nz * S + slot;
    const double* __restrict__ q_g = gp.q + (int64_t)g * nz * Sb + cell;
    double* __restrict__ phi_g = gp.phi_new + (int64_t)g * nz * Sb + cell;
    const int32_t* __restrict__ mats_c = gp.mats + cell;
    const double* __restrict__ sigt_g = gp.sigma_t + g;
+   const int64_t kstride_b = (zdir >= 0 ? 1 : -1) * Sb;
+   int64_t koff = (int64_t)kfirst * Sb;
+   int k = kfirst;
 
    // z-upwind start values
    double psiz[DT];
@@ -94,50 +100,70 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    for (int d = 0; d < DT; d++) psiz[d] = 0.0;
    if (gp.has_z && valid) {
       if (kp0 > 0) {
-         const int kprev = zdir > 0 ? kp0 - 1 : nz - kp0;
+         const double* pz = psi_w - kstride_psi;
 #pragma unroll
-         for (int d = 0; d < DT; d++)
-            if (d < nd) psiz[d] = ldcg_f64(psi_g + d * dstride + (int64_t)kprev * S);
+         for (int d = 0; d < DT; d++) psiz[d] = ldcg_f64(pz + d * PS);
       } else if (EXTRAS) {
          const int face = zdir > 0 ? 0 : 1;
          const bool refl = face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl;
          if (refl) {
 #pragma unroll
             for (int d = 0; d < DT; d++)
-               if (d < nd)
-                  psiz[d] = gp.bndz_old[(((int64_t)face * gp.M + ch->mrefl[d][2]) * gp.G + g) * Sb + cell];
+               psiz[d] = gp.bndz_old[(((int64_t)face * gp.M + ch->mrefl[d][2]) * gp.G + g) * Sb + cell];
          }
       }
    }
-   __syncthreads();
 
-   int rs = 0;
+   // software prefetch of the per-layer inputs (material, source) one step ahead
+   int mat_c = 0;
+   double q_c = 0.0;
+   if (valid) { mat_c = mats_c[koff]; q_c = q_g[koff]; }
+   int mat_prev = -1;
+   double idz_prev = -1.0;
+   double inv[DT];
+#pragma unroll
+   for (int d = 0; d < DT; d++) inv[d] = 0.0;
+
+   int rs_off = 0;                                   // ring slot offset (doubles) of my current layer
    for (int step = 0; step < nsteps; step++) {
       const int kl = step - lv;
       if (valid && kl >= 0 && kl < kcnt) {
-         const int kp = kp0 + kl;
-         const int k = zdir >= 0 ? kp : nz - 1 - kp;
-         const int64_t koff = (int64_t)k * Sb;
-         const int mat = mats_c[koff];
-         const double st = sigt_g[mat * gp.G];
-         const double qv = q_g[koff];
-         const double idz = gp.has_z ? gp.inv_dz[k] : 0.0;
-         double acc[DT], den[DT];
+         // patch-boundary upwind values first: their latency overlaps the in-patch work
+         double upg[DT];
+         int sg = -1;
 #pragma unroll
-         for (int d = 0; d < DT; d++) {
-            const double az = s_muz[d] * idz;
-            acc[d] = fma(az, psiz[d], qv);
-            den[d] = st + so[d] + az;
+         for (int s = 0; s < FIN; s++)
+            if (sg < 0 && src[s] >= 0 && (src[s] >> SRC_KIND_SHIFT) == SRC_GLOBAL) sg = s;
+         if (sg >= 0) {
+#pragma unroll
+            for (int s = 0; s < FIN; s++)
+               if (s == sg) {
+#pragma unroll
+                  for (int d = 0; d < DT; d++) upg[d] = ldcg_f64(gsrc[s] + d * PS);
+               }
          }
+         const int mat = mat_c;
+         const double qv = q_c;
+         if (kl + 1 < kcnt) { mat_c = mats_c[koff + kstride_b]; q_c = q_g[koff + kstride_b]; }
+         const double idz = gp.has_z ? gp.inv_dz[k] : 0.0;
+         if (mat != mat_prev || idz != idz_prev) {
+            const double st = __ldg(sigt_g + mat * gp.G);
+#pragma unroll
+            for (int d = 0; d < DT; d++) {
+               double den = st + (s_mux[d] * ov.x + s_muy[d] * ov.y) + s_muz[d] * idz;
+               if (EXTRAS) { if (lsb >= 0) den += gp.ls_dD[(int64_t)ch->m[d] * gp.nls + lsb]; }
+               inv[d] = 1.0 / den;
+            }
+            mat_prev = mat; idz_prev = idz;
+         }
+         double acc[DT];
+#pragma unroll
+         for (int d = 0; d < DT; d++) acc[d] = fma(s_muz[d] * idz, psiz[d], qv);
          if (EXTRAS) {
             if (lsb >= 0) {
 #pragma unroll
                for (int d = 0; d < DT; d++)
-                  if (d < nd) {
-                     const int m = ch->m[d];
-                     den[d] += gp.ls_dD[(int64_t)m * gp.nls + lsb];
-                     acc[d] += gp.ls_rhs[((int64_t)m * gp.G + g) * gp.nls + lsb];
-                  }
+                  acc[d] += gp.ls_rhs[((int64_t)ch->m[d] * gp.G + g) * gp.nls + lsb];
             }
          }
 #pragma unroll
@@ -145,42 +171,44 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
             const int code = src[s];
             if (code >= 0) {
                const int kind = code >> SRC_KIND_SHIFT;
-               const int pay = code & SRC_PAYLOAD;
                if (kind == SRC_LOCAL) {
-                  const double* r = ring + (size_t)rs * DT * P + pay;
+                  const double* r = ring + rs_off + (code & SRC_PAYLOAD);
 #pragma unroll
-                  for (int d = 0; d < DT; d++) acc[d] = fma(a[s][d], r[d * P], acc[d]);
+                  for (int d = 0; d < DT; d++) acc[d] = fma(a[s][d], r[d * PS], acc[d]);
                } else if (kind == SRC_GLOBAL) {
-                  const double* pg = ch->psi + (int64_t)gl * nz * S + (int64_t)k * S + pay;
+                  if (s != sg) {
 #pragma unroll
-                  for (int d = 0; d < DT; d++)
-                     if (d < nd) acc[d] = fma(a[s][d], ldcg_f64(pg + d * dstride), acc[d]);
+                     for (int d = 0; d < DT; d++) acc[d] = fma(a[s][d], ldcg_f64(gsrc[s] + d * PS), acc[d]);
+                  }
                } else if (EXTRAS) {
+                  const int pay = code & SRC_PAYLOAD;
                   const int axis = pay >> SRC_AXIS_SHIFT;
                   const int rf = pay & ((1 << SRC_AXIS_SHIFT) - 1);
 #pragma unroll
-                  for (int d = 0; d < DT; d++)
-                     if (d < nd) {
-                        const int mr = ch->mrefl[d][axis];
-                        acc[d] = fma(a[s][d],
-                                     gp.bnd_old[(((int64_t)mr * gp.G + g) * nz + k) * gp.nrf + rf], acc[d]);
-                     }
+                  for (int d = 0; d < DT; d++) {
+                     const int mr = ch->mrefl[d][axis];
+                     acc[d] = fma(a[s][d], gp.bnd_old[(((int64_t)mr * gp.G + g) * nz + k) * gp.nrf + rf], acc[d]);
+                  }
                }
             }
          }
+         if (sg >= 0) {
+#pragma unroll
+            for (int s = 0; s < FIN; s++)
+               if (s == sg) {
+#pragma unroll
+                  for (int d = 0; d < DT; d++) acc[d] = fma(a[s][d], upg[d], acc[d]);
+               }
+         }
          double ph = 0.0;
-         double* rw = ring + (size_t)rs * DT * P + t;
+         double* rw = ring + rs_off + t;
 #pragma unroll
          for (int d = 0; d < DT; d++) {
-            const double v = acc[d] / den[d];
+            const double v = acc[d] * inv[d];
             psiz[d] = v;
-            rw[d * P] = v;
+            rw[d * PS] = v;
+            psi_w[d * PS] = v;
             ph = fma(s_w[d], v, ph);
-         }
-         if (gp.store_psi) {
-#pragma unroll
-            for (int d = 0; d < DT; d++)
-               if (d < nd) psi_g[d * dstride + (int64_t)k * S] = psiz[d];
          }
          atomicAdd(phi_g + koff, ph);
          if (EXTRAS) {
@@ -189,52 +217,61 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
                if (rout[r] >= 0) {
 #pragma unroll
                   for (int d = 0; d < DT; d++)
-                     if (d < nd)
-                        gp.bnd_new[(((int64_t)ch->m[d] * gp.G + g) * nz + k) * gp.nrf + rout[r]] = psiz[d];
+                     gp.bnd_new[(((int64_t)ch->m[d] * gp.G + g) * nz + k) * gp.nrf + rout[r]] = psiz[d];
                }
-            if (gp.has_z && kp == nz - 1) {
+            if (gp.has_z && kp0 + kl == nz - 1) {
                const int face = zdir > 0 ? 1 : 0;
                const bool refl = face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl;
                if (refl) {
 #pragma unroll
                   for (int d = 0; d < DT; d++)
-                     if (d < nd)
-                        gp.bndz_new[(((int64_t)face * gp.M + ch->m[d]) * gp.G + g) * Sb + cell] = psiz[d];
+                     gp.bndz_new[(((int64_t)face * gp.M + ch->m[d]) * gp.G + g) * Sb + cell] = psiz[d];
                }
             }
          }
-         rs = (rs + 1 == RD) ? 0 : rs + 1;
+         // advance to my next layer
+         rs_off += DT * PS;
+         if (rs_off == RD * DT * PS) rs_off = 0;
+         psi_w += kstride_psi;
+#pragma unroll
+         for (int s = 0; s < FIN; s++) gsrc[s] += kstride_psi;
+         koff += kstride_b;
+         k += (zdir >= 0 ? 1 : -1);
       }
       __syncthreads();
    }
 }
 
 template <int DT, int FIN>
-static void launch_sweep_fin(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int P,
-                             size_t smem, bool extras, cudaStream_t st) {
-   if (extras) sn_sweep_kernel<DT, FIN, true><<<ntasks, P, smem, st>>>(gp, d_tasks);
-   else        sn_sweep_kernel<DT, FIN, false><<<ntasks, P, smem, st>>>(gp, d_tasks);
+static void launch_sweep_fin(const SweepGlobals& gp, const Task* d_tasks, int ntasks, size_t smem,
+                             bool extras, cudaStream_t st) {
+   if (extras) sn_sweep_kernel<DT, FIN, true><<<ntasks, PS, smem, st>>>(gp, d_tasks);
+   else        sn_sweep_kernel<DT, FIN, false><<<ntasks, PS, smem, st>>>(gp, d_tasks);
 }
 
 template <int DT>
-static void launch_sweep_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int P, int fin,
+static void launch_sweep_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int fin,
                             int ring, bool extras, cudaStream_t st) {
-   const size_t smem = ((size_t)ring * DT * P + 2 * DT) * sizeof(double);
-   if (fin <= 2) launch_sweep_fin<DT, 2>(gp, d_tasks, ntasks, P, smem, extras, st);
-   else          launch_sweep_fin<DT, FIN_MAX>(gp, d_tasks, ntasks, P, smem, extras, st);
+   const size_t smem = ((size_t)ring * DT * PS + 4 * DT) * sizeof(double);
+   if (fin <= 2) launch_sweep_fin<DT, 2>(gp, d_tasks, ntasks, smem, extras, st);
+   else          launch_sweep_fin<DT, FIN_MAX>(gp, d_tasks, ntasks, smem, extras, st);
 }
 
-void launch_sweep(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int P, int dt, int fin,
+void launch_sweep(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, int fin,
                   int ring, bool extras, cudaStream_t st) {
    if (ntasks <= 0) return;
-   if (dt <= 1)      launch_sweep_dt<1>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
-   else if (dt <= 2) launch_sweep_dt<2>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
-   else if (dt <= 3) launch_sweep_dt<3>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
-   else if (dt <= 4) launch_sweep_dt<4>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
-   else if (dt <= 5) launch_sweep_dt<5>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
-   else if (dt <= 6) launch_sweep_dt<6>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
-   else if (dt <= 8) launch_sweep_dt<8>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
-   else              launch_sweep_dt<10>(gp, d_tasks, ntasks, P, fin, ring, extras, st);
+   switch (dt) {
+      case 1: launch_sweep_dt<1>(gp, d_tasks, ntasks, fin, ring, extras, st); break;
+      case 2: launch_sweep_dt<2>(gp, d_tasks, ntasks, fin, ring, extras, st); break;
+      case 3: launch_sweep_dt<3>(gp, d_tasks, ntasks, fin, ring, extras, st); break;
+      case 4: launch_sweep_dt<4>(gp, d_tasks, ntasks, fin, ring, extras, st); break;
+      case 5: launch_sweep_dt<5>(gp, d_tasks, ntasks, fin, ring, extras, st); break;
+      case 6: launch_sweep_dt<6>(gp, d_tasks, ntasks, fin, ring, extras, st); break;
+      case 7: launch_sweep_dt<7>(gp, d_tasks, ntasks, fin, ring, extras, st); break;
+      case 8: launch_sweep_dt<8>(gp, d_tasks, ntasks, fin, ring, extras, st); break;
+      case 9: launch_sweep_dt<9>(gp, d_tasks, ntasks, fin, ring, extras, st); break;
+      default: launch_sweep_dt<10>(gp, d_tasks, ntasks, fin, ring, extras, st); break;
+   }
 }
 
 template <int DT, int FIN, bool EX>
@@ -258,7 +295,9 @@ cudaError_t configure_sweep_kernels() {
    if ((e = cfg_dt<4>()) != cudaSuccess) return e;
    if ((e = cfg_dt<5>()) != cudaSuccess) return e;
    if ((e = cfg_dt<6>()) != cudaSuccess) return e;
+   if ((e = cfg_dt<7>()) != cudaSuccess) return e;
    if ((e = cfg_dt<8>()) != cudaSuccess) return e;
+   if ((e = cfg_dt<9>()) != cudaSuccess) return e;
    return cfg_dt<10>();
 }
 
@@ -401,9 +440,10 @@ __global__ void sn_ls_rhs_kernel(const SweepGlobals gp, const int32_t* __restric
       const ChunkDev* ch = gp.chunks + c;
       const ClassDev* cl = gp.classes + ch->cls;
       const int32_t* pos = class_pos_of[ch->cls];
-      const double* psi = ch->psi + ((int64_t)dir_d[m] * gp.Gown + gl) * gp.nz * cl->S;
+      const int d = dir_d[m];
       for (int e = ls_ptr[b]; e < ls_ptr[b + 1]; e++)
-         acc -= ls_coef[(int64_t)m * nnz + e] * psi[pos[ls_nbr_slot[e]]];
+         acc -= ls_coef[(int64_t)m * nnz + e] *
+                ch->psi[psi_index(gl, 0, pos[ls_nbr_slot[e]], d, gp.nz, cl->npatch, ch->nd)];
    }
    rhs[tid] = acc;
 }
@@ -468,9 +508,9 @@ void launch_export_cell(const double* phi, const int32_t* slot_of_xy, const int3
 // angular flux of one direction m into the reference layout out[(i*G + g)*M + m]
 __global__ void sn_export_psi_kernel(const double* __restrict__ psi_block,
                                      const int32_t* __restrict__ pos_of,
-                                     const int32_t* __restrict__ slot_of_xy, int d, int m, int Gown,
+                                     const int32_t* __restrict__ slot_of_xy, int d, int nd, int m,
                                      const int32_t* __restrict__ gloc, double scale, int G, int M,
-                                     int nz, int nxy, int64_t S, double* __restrict__ out,
+                                     int nz, int nxy, int npatch, double* __restrict__ out,
                                      double* __restrict__ minval) {
    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    const int64_t total = (int64_t)nz * nxy * G;
@@ -480,16 +520,16 @@ __global__ void sn_export_psi_kernel(const double* __restrict__ psi_block,
    const int k = (int)(i / nxy), c = (int)(i % nxy);
    const int gl = gloc[g];
    if (gl < 0) return;
-   const double v = scale * psi_block[(((int64_t)d * Gown + gl) * nz + k) * S + pos_of[slot_of_xy[c]]];
+   const double v = scale * psi_block[psi_index(gl, k, pos_of[slot_of_xy[c]], d, nz, npatch, nd)];
    out[tid * M + m] = v;
    if (v < 0.0) *minval = v;     // benign race: any negative value flags the error
 }
 void launch_export_psi(const double* psi_block, const int32_t* pos_of, const int32_t* slot_of_xy,
-                       int d, int m, int Gown, const int32_t* gloc, double scale, int G, int M,
-                       int nz, int nxy, int64_t S, double* out, double* minval, cudaStream_t st) {
+                       int d, int nd, int m, const int32_t* gloc, double scale, int G, int M,
+                       int nz, int nxy, int npatch, double* out, double* minval, cudaStream_t st) {
    const int64_t total = (int64_t)nz * nxy * G;
    sn_export_psi_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(
-      psi_block, pos_of, slot_of_xy, d, m, Gown, gloc, scale, G, M, nz, nxy, S, out, minval);
+      psi_block, pos_of, slot_of_xy, d, nd, m, gloc, scale, G, M, nz, nxy, npatch, out, minval);
 }
 
 __global__ void sn_import_phi_kernel(double* __restrict__ phi, const int32_t* __restrict__ slot_of_xy,

@@ -9,12 +9,20 @@
 namespace pampa_sn {
 
 // Per ordering class, device pointers into the uploaded plan.
+constexpr int PS = 256;       // patch slots = sweep CTA size
+
+// psi of a chunk: [owned group][layer][patch][direction][lane]
+__host__ __device__ inline int64_t psi_index(int gl, int k, int64_t slot, int d, int nz, int npatch,
+                                             int nd) {
+   return ((((int64_t)gl * nz + k) * npatch + (slot >> 8)) * nd + d) * PS + (slot & (PS - 1));
+}
+
 struct ClassDev {
-   int64_t S;                 // slots of this class (npatch * P)
+   int64_t S;                 // slots of this class (npatch * PS)
    int32_t zdir;              // +1 / -1 / 0
    int32_t ring;              // smem ring depth
    int32_t tiles;             // 1: class slot == base slot
-   int32_t pad;
+   int32_t npatch;
    const int32_t* cell_of;    // [S] base slot or -1
    const uint16_t* lvl;       // [S]
    const int32_t* patch_nlev; // [npatch]
@@ -32,7 +40,7 @@ struct ChunkDev {
    int32_t m[DT_MAX];         // quadrature index
    int32_t mrefl[DT_MAX][3];  // mirrored direction about x, y, z
    double mux[DT_MAX], muy[DT_MAX], muz_abs[DT_MAX], w[DT_MAX];
-   double* psi;               // [nd][Gown][nz][S]
+   double* psi;               // [Gown][nz][npatch][nd][PS]
 };
 
 struct SweepGlobals {
@@ -68,7 +76,7 @@ struct ReduceScalars {        // device-resident iteration state
    double pad;
 };
 
-void launch_sweep(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int P, int dt, int fin,
+void launch_sweep(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, int fin,
                   int ring, bool extras, cudaStream_t st);
 cudaError_t configure_sweep_kernels();
 
@@ -93,8 +101,8 @@ void launch_export_cell(const double* phi, const int32_t* slot_of_xy, const int3
                         double scale, int G, int nz, int nxy, int64_t Sb, double* out,
                         cudaStream_t st);
 void launch_export_psi(const double* psi_block, const int32_t* pos_of, const int32_t* slot_of_xy,
-                       int d, int m, int Gown, const int32_t* gloc, double scale, int G, int M,
-                       int nz, int nxy, int64_t S, double* out, double* minval, cudaStream_t st);
+                       int d, int nd, int m, const int32_t* gloc, double scale, int G, int M,
+                       int nz, int nxy, int npatch, double* out, double* minval, cudaStream_t st);
 void launch_import_phi(double* phi, const int32_t* slot_of_xy, int G, int nz, int nxy, int64_t Sb,
                        const double* in, cudaStream_t st);
 void launch_fill(double* p, double v, int64_t n, cudaStream_t st);

@@ -154,17 +154,19 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
    if (nxy <= 0 || ms.num_layers <= 0 || F <= 0) throw std::runtime_error("empty mesh");
    pl.nxy = nxy; pl.nz = ms.num_layers; pl.has_z = ms.has_z_faces ? 1 : 0;
    pl.G = in.G; pl.M = qd.num_directions;
-   int P = in.opts.patch_cells > 0 ? in.opts.patch_cells : 256;
+   const int P = 256;                 // slot stride of a patch = sweep CTA size (fixed)
+   int cap = in.opts.patch_cells > 0 ? in.opts.patch_cells : P;   // cells per patch (<= P)
    int ti = in.opts.tile_i > 0 ? in.opts.tile_i : 16;
    int tj = in.opts.tile_j > 0 ? in.opts.tile_j : 16;
+   if (cap > P || cap < 1) throw std::runtime_error("patch_cells must be in 1..256");
    if (ms.xy_ij) {
       // thin meshes (1-D slabs, narrow strips): stretch the tile along i instead of wasting lanes
       int jext = 0;
       for (int c = 0; c < nxy; c++) jext = std::max(jext, ms.xy_ij[2*c+1] + 1);
       while (tj > 1 && tj / 2 >= jext) { tj /= 2; ti *= 2; }
-      P = ti * tj;
+      if (ti * tj > P) throw std::runtime_error("tile_i * tile_j must be <= 256");
+      cap = ti * tj;
    }
-   if (P % 32 != 0 || P > 1024) throw std::runtime_error("patch size must be a multiple of 32, <= 1024");
    pl.P = P;
 
    auto bc_type = [&](int nb) -> int {
@@ -189,14 +191,14 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
       for (int c = 0; c < nxy; c++) {
          int i = ms.xy_ij[2*c], j = ms.xy_ij[2*c+1];
          int t = (j / tj) * ntx + i / ti;
-         pl.slot_of_xy[c] = tile_id[t] * P + (j % tj) * ti + (i % ti);
+         pl.slot_of_xy[c] = tile_id[t] * P + (j % tj) * ti + (i % ti);   // ti*tj <= P lanes used
       }
       pl.npatch_b = np;
    } else {
       std::vector<int> ids(nxy);
       std::iota(ids.begin(), ids.end(), 0);
       std::vector<std::pair<int, int>> leaves;
-      detail::kd_split(ids, 0, nxy, ms.xy_cx, ms.xy_cy, P, leaves);
+      detail::kd_split(ids, 0, nxy, ms.xy_cx, ms.xy_cy, cap, leaves);
       int np = 0;
       for (auto& lf : leaves) {
          std::sort(ids.begin() + lf.first, ids.begin() + lf.second);
@@ -324,8 +326,8 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
             if (glevel[a] != glevel[b]) return glevel[a] < glevel[b];
             if (lat[a] != lat[b]) return lat[a] < lat[b];
             return a < b; });
-         for (int a = 0; a < nxy; a++) { patch_of[ord[a]] = a / P; lane_of[ord[a]] = a % P; }
-         if (!try_partition((nxy + P - 1) / P)) throw std::runtime_error("internal: level-chunk partition is cyclic");
+         for (int a = 0; a < nxy; a++) { patch_of[ord[a]] = a / cap; lane_of[ord[a]] = a % cap; }
+         if (!try_partition((nxy + cap - 1) / cap)) throw std::runtime_error("internal: level-chunk partition is cyclic");
       }
       // slot tables
       const int64_t S = cp.S;
@@ -400,7 +402,8 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
    for (size_t ci = 0; ci < pl.classes.size(); ci++) {
       const ClassPlan& cp = pl.classes[ci];
       int n = (int)cp.dirs.size();
-      int nch = (n + DT_MAX - 1) / DT_MAX;
+      const int dtm = (in.opts.dt_max >= 1 && in.opts.dt_max <= DT_MAX) ? in.opts.dt_max : DT_MAX;
+      int nch = (n + dtm - 1) / dtm;
       int per = (n + nch - 1) / nch;
       for (int a = 0; a < n; a += per) {
          Chunk ch; ch.cls = (int)ci; ch.nd = std::min(per, n - a);
