@@ -362,7 +362,8 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       for (size_t c = 0; c < pl.chunks.size(); c++)
          if (chunk_owned[c]) {
             psi_off[c] = psi_doubles;
-            psi_doubles += (int64_t)pl.chunks[c].nd * h->Gown * nz * pl.classes[pl.chunks[c].cls].S;
+            const ClassPlan& cpc = pl.classes[pl.chunks[c].cls];
+            psi_doubles += (int64_t)pl.chunks[c].nd * h->Gown * cpc.npatch * cpc.nsteps * PS;
          }
       if (dev_alloc(h, &h->d_psi, psi_doubles)) return 1;
       SN_CUDA(h, cudaMemsetAsync(h->d_psi, 0, (size_t)psi_doubles * sizeof(double), h->stream));
@@ -421,6 +422,21 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          const ClassPlan& cp = pl.classes[ci];
          ClassDev& cd = cdev[ci];
          cd.S = cp.S; cd.zdir = cp.zdir; cd.ring = cp.ring; cd.tiles = cp.tiles ? 1 : 0; cd.npatch = cp.npatch;
+         cd.nsteps = cp.nsteps; cd.pad = 0;
+         {  // material map in the class's (patch, pipeline step, lane) order
+            std::vector<int32_t> ms((size_t)cp.npatch * cp.nsteps * PS, -1);
+            for (int64_t sl = 0; sl < cp.S; sl++) {
+               if (cp.cell_of[sl] < 0) continue;
+               const int64_t p = sl / PS, lane = sl % PS;
+               for (int kp = 0; kp < nz; kp++) {
+                  const int k = cp.zdir >= 0 ? kp : nz - 1 - kp;
+                  ms[((size_t)p * cp.nsteps + kp + cp.lvl[sl]) * PS + lane] = mats[(size_t)k * Sb + cp.cell_of[sl]];
+               }
+            }
+            int32_t* d_ms;
+            if (dev_upload(h, &d_ms, ms)) return 1;
+            cd.mats_s = d_ms;
+         }
          int32_t *d_cell_of, *d_patch_nlev, *d_in_src, *d_rout, *d_ls_of = nullptr;
          uint16_t* d_lvl; Vec2 *d_out_vec, *d_in_vec;
          if (dev_upload(h, &d_cell_of, cp.cell_of) || dev_upload(h, &d_lvl, cp.lvl) ||
@@ -653,8 +669,8 @@ int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
          ChunkDev cd;
          cudaMemcpyAsync(&cd, h->d_chunks + c, sizeof(ChunkDev), cudaMemcpyDeviceToHost, h->stream);
          cudaStreamSynchronize(h->stream);
-         launch_export_psi(cd.psi, h->d_pos_of[ch.cls], h->d_slot_of_xy, h->dir_d[m], ch.nd, m, h->d_gloc,
-                           h->scale, h->G, h->M, pl.nz, pl.nxy, cp.npatch, d_out, d_min, h->stream);
+         launch_export_psi(cd.psi, h->d_classes + ch.cls, h->d_pos_of[ch.cls], h->d_slot_of_xy, h->dir_d[m],
+                           ch.nd, m, h->d_gloc, h->scale, h->G, h->M, pl.nz, pl.nxy, d_out, d_min, h->stream);
       }
       double mn = 0.0;
       cudaMemcpyAsync(&mn, d_min, sizeof(double), cudaMemcpyDeviceToHost, h->stream);

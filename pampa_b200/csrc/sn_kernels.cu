@@ -22,9 +22,9 @@ __device__ __forceinline__ double ldcg_f64(const double* p) { return __ldcg(p); 
 
 // One CTA = one sweep task.  PS (= 256) threads, thread <-> xy cell of the patch.
 //
-// psi layout of a chunk: [owned group][layer][patch][direction][lane] -- the DT x 256 values a CTA
-// produces in one pipeline step are one contiguous block, every store / patch-boundary load is
-// a fixed immediate offset (d * 2 KB) from one running pointer.
+// psi layout of a chunk: [owned group][patch][pipeline step][direction][lane] -- the DT x 256 values
+// a CTA produces in one pipeline step are one contiguous block, every store / patch-boundary load
+// is a fixed immediate offset (d * 2 KB) from one running pointer that advances by a constant.
 template <int DT, int FIN, bool EXTRAS>
 __global__ void __launch_bounds__(PS, 2)
 sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
@@ -53,6 +53,8 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    double* s_muy = s_mux + DT;
    double* s_muz = s_muy + DT;
    double* s_w = s_muz + DT;
+   double* s_idz = s_w + DT;                         // [nz]
+   for (int kk = t; kk < nz; kk += PS) s_idz[kk] = gp.has_z ? gp.inv_dz[kk] : 0.0;
    if (t < DT) {
       s_mux[t] = ch->mux[t];
       s_muy[t] = ch->muy[t];
@@ -67,8 +69,10 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    const double* gsrc[FIN];                          // running pointers of patch-boundary sources
    const double2 ov = valid ? cl->out_vec[slot] : make_double2(0.0, 0.0);
    const int kfirst = zdir >= 0 ? kp0 : nz - 1 - kp0;
-   const int64_t kstride_psi = (int64_t)(zdir >= 0 ? 1 : -1) * npatch * (DT * PS);
-   double* psi_w = ch->psi + ((((int64_t)gl * nz + kfirst) * npatch + tk.patch) * DT) * PS + t;
+   const int NS = cl->nsteps;
+   constexpr int kstride_psi = DT * PS;
+   double* psi_w = ch->psi + ((((int64_t)gl * npatch + tk.patch) * NS + kp0 + (valid ? lv : 0)) * DT) * PS + t;
+   const int32_t* mats_w = cl->mats_s + ((int64_t)tk.patch * NS + kp0 + (valid ? lv : 0)) * PS + t;
 #pragma unroll
    for (int s = 0; s < FIN; s++) {
       src[s] = valid ? cl->in_src[(size_t)s * cl->S + slot] : SRC_NONE;
@@ -76,7 +80,9 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
 #pragma unroll
       for (int d = 0; d < DT; d++) a[s][d] = -(s_mux[d] * iv.x + s_muy[d] * iv.y);
       const int pay = src[s] & SRC_PAYLOAD;
-      gsrc[s] = ch->psi + ((((int64_t)gl * nz + kfirst) * npatch + (pay >> 8)) * DT) * PS + (pay & (PS - 1));
+      gsrc[s] = ch->psi;
+      if (src[s] >= 0 && (src[s] >> SRC_KIND_SHIFT) == SRC_GLOBAL)
+         gsrc[s] += ((((int64_t)gl * npatch + (pay >> 8)) * NS + kp0 + cl->lvl[pay]) * DT) * PS + (pay & (PS - 1));
    }
    int rout[ROUT_MAX];
    int lsb = -1;
@@ -88,7 +94,6 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
 
    const double* __restrict__ q_g = gp.q + (int64_t)g * nz * Sb + cell;
    double* __restrict__ phi_g = gp.phi_new + (int64_t)g * nz * Sb + cell;
-   const int32_t* __restrict__ mats_c = gp.mats + cell;
    const double* __restrict__ sigt_g = gp.sigma_t + g;
    const int64_t kstride_b = (zdir >= 0 ? 1 : -1) * Sb;
    int64_t koff = (int64_t)kfirst * Sb;
@@ -117,7 +122,7 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    // software prefetch of the per-layer inputs (material, source) one step ahead
    int mat_c = 0;
    double q_c = 0.0;
-   if (valid) { mat_c = mats_c[koff]; q_c = q_g[koff]; }
+   if (valid) { mat_c = mats_w[0]; q_c = q_g[koff]; }
    int mat_prev = -1;
    double idz_prev = -1.0;
    double inv[DT];
@@ -144,8 +149,8 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
          }
          const int mat = mat_c;
          const double qv = q_c;
-         if (kl + 1 < kcnt) { mat_c = mats_c[koff + kstride_b]; q_c = q_g[koff + kstride_b]; }
-         const double idz = gp.has_z ? gp.inv_dz[k] : 0.0;
+         if (kl + 1 < kcnt) { mat_c = mats_w[PS]; q_c = q_g[koff + kstride_b]; }
+         const double idz = s_idz[k];
          if (mat != mat_prev || idz != idz_prev) {
             const double st = __ldg(sigt_g + mat * gp.G);
 #pragma unroll
@@ -233,6 +238,7 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
          rs_off += DT * PS;
          if (rs_off == RD * DT * PS) rs_off = 0;
          psi_w += kstride_psi;
+         mats_w += PS;
 #pragma unroll
          for (int s = 0; s < FIN; s++) gsrc[s] += kstride_psi;
          koff += kstride_b;
@@ -252,7 +258,7 @@ static void launch_sweep_fin(const SweepGlobals& gp, const Task* d_tasks, int nt
 template <int DT>
 static void launch_sweep_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int fin,
                             int ring, bool extras, cudaStream_t st) {
-   const size_t smem = ((size_t)ring * DT * PS + 4 * DT) * sizeof(double);
+   const size_t smem = ((size_t)ring * DT * PS + 4 * DT + gp.nz) * sizeof(double);
    if (fin <= 2) launch_sweep_fin<DT, 2>(gp, d_tasks, ntasks, smem, extras, st);
    else          launch_sweep_fin<DT, FIN_MAX>(gp, d_tasks, ntasks, smem, extras, st);
 }
@@ -442,8 +448,11 @@ __global__ void sn_ls_rhs_kernel(const SweepGlobals gp, const int32_t* __restric
       const int32_t* pos = class_pos_of[ch->cls];
       const int d = dir_d[m];
       for (int e = ls_ptr[b]; e < ls_ptr[b + 1]; e++)
-         acc -= ls_coef[(int64_t)m * nnz + e] *
-                ch->psi[psi_index(gl, 0, pos[ls_nbr_slot[e]], d, gp.nz, cl->npatch, ch->nd)];
+         {
+            const int sl = pos[ls_nbr_slot[e]];       // nz == 1: pipeline step = local level
+            acc -= ls_coef[(int64_t)m * nnz + e] *
+                   ch->psi[psi_index(gl, sl, cl->lvl[sl], d, cl->npatch, cl->nsteps, ch->nd)];
+         }
    }
    rhs[tid] = acc;
 }
@@ -507,10 +516,11 @@ void launch_export_cell(const double* phi, const int32_t* slot_of_xy, const int3
 
 // angular flux of one direction m into the reference layout out[(i*G + g)*M + m]
 __global__ void sn_export_psi_kernel(const double* __restrict__ psi_block,
+                                     const ClassDev* __restrict__ cl,
                                      const int32_t* __restrict__ pos_of,
                                      const int32_t* __restrict__ slot_of_xy, int d, int nd, int m,
                                      const int32_t* __restrict__ gloc, double scale, int G, int M,
-                                     int nz, int nxy, int npatch, double* __restrict__ out,
+                                     int nz, int nxy, double* __restrict__ out,
                                      double* __restrict__ minval) {
    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    const int64_t total = (int64_t)nz * nxy * G;
@@ -520,16 +530,19 @@ __global__ void sn_export_psi_kernel(const double* __restrict__ psi_block,
    const int k = (int)(i / nxy), c = (int)(i % nxy);
    const int gl = gloc[g];
    if (gl < 0) return;
-   const double v = scale * psi_block[psi_index(gl, k, pos_of[slot_of_xy[c]], d, nz, npatch, nd)];
+   const int sl = pos_of[slot_of_xy[c]];
+   const int kp = cl->zdir >= 0 ? k : nz - 1 - k;
+   const double v = scale * psi_block[psi_index(gl, sl, kp + cl->lvl[sl], d, cl->npatch, cl->nsteps, nd)];
    out[tid * M + m] = v;
    if (v < 0.0) *minval = v;     // benign race: any negative value flags the error
 }
-void launch_export_psi(const double* psi_block, const int32_t* pos_of, const int32_t* slot_of_xy,
-                       int d, int nd, int m, const int32_t* gloc, double scale, int G, int M,
-                       int nz, int nxy, int npatch, double* out, double* minval, cudaStream_t st) {
+void launch_export_psi(const double* psi_block, const ClassDev* cl, const int32_t* pos_of,
+                       const int32_t* slot_of_xy, int d, int nd, int m, const int32_t* gloc,
+                       double scale, int G, int M, int nz, int nxy, double* out, double* minval,
+                       cudaStream_t st) {
    const int64_t total = (int64_t)nz * nxy * G;
    sn_export_psi_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(
-      psi_block, pos_of, slot_of_xy, d, nd, m, gloc, scale, G, M, nz, nxy, npatch, out, minval);
+      psi_block, cl, pos_of, slot_of_xy, d, nd, m, gloc, scale, G, M, nz, nxy, out, minval);
 }
 
 __global__ void sn_import_phi_kernel(double* __restrict__ phi, const int32_t* __restrict__ slot_of_xy,

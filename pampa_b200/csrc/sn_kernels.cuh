@@ -11,10 +11,13 @@ namespace pampa_sn {
 // Per ordering class, device pointers into the uploaded plan.
 constexpr int PS = 256;       // patch slots = sweep CTA size
 
-// psi of a chunk: [owned group][layer][patch][direction][lane]
-__host__ __device__ inline int64_t psi_index(int gl, int k, int64_t slot, int d, int nz, int npatch,
-                                             int nd) {
-   return ((((int64_t)gl * nz + k) * npatch + (slot >> 8)) * nd + d) * PS + (slot & (PS - 1));
+// psi of a chunk: [owned group][patch][pipeline step][direction][lane].  The pipeline step of
+// (lane, layer) is kp + lvl(lane), kp = position of the layer in sweep order: the lanes of a CTA
+// work on different layers in the same step (wavefront skew), and storing by step instead of by
+// layer makes every CTA-step one contiguous, fully coalesced block of nd x 256 doubles.
+__host__ __device__ inline int64_t psi_index(int gl, int64_t slot, int step, int d, int npatch,
+                                             int nsteps, int nd) {
+   return ((((int64_t)gl * npatch + (slot >> 8)) * nsteps + step) * nd + d) * PS + (slot & (PS - 1));
 }
 
 struct ClassDev {
@@ -23,6 +26,9 @@ struct ClassDev {
    int32_t ring;              // smem ring depth
    int32_t tiles;             // 1: class slot == base slot
    int32_t npatch;
+   int32_t nsteps;            // pipeline steps stored per patch: max local levels + nz - 1
+   int32_t pad;
+   const int32_t* mats_s;     // [npatch][nsteps][PS] material of (lane, step), -1 outside
    const int32_t* cell_of;    // [S] base slot or -1
    const uint16_t* lvl;       // [S]
    const int32_t* patch_nlev; // [npatch]
@@ -40,7 +46,7 @@ struct ChunkDev {
    int32_t m[DT_MAX];         // quadrature index
    int32_t mrefl[DT_MAX][3];  // mirrored direction about x, y, z
    double mux[DT_MAX], muy[DT_MAX], muz_abs[DT_MAX], w[DT_MAX];
-   double* psi;               // [Gown][nz][npatch][nd][PS]
+   double* psi;               // [Gown][npatch][nsteps][nd][PS]
 };
 
 struct SweepGlobals {
@@ -100,9 +106,10 @@ void launch_export_cell(const double* phi, const int32_t* slot_of_xy, const int3
                         const double* xs_g, const double* area, const double* dz, int has_z,
                         double scale, int G, int nz, int nxy, int64_t Sb, double* out,
                         cudaStream_t st);
-void launch_export_psi(const double* psi_block, const int32_t* pos_of, const int32_t* slot_of_xy,
-                       int d, int nd, int m, const int32_t* gloc, double scale, int G, int M,
-                       int nz, int nxy, int npatch, double* out, double* minval, cudaStream_t st);
+void launch_export_psi(const double* psi_block, const ClassDev* cl, const int32_t* pos_of,
+                       const int32_t* slot_of_xy, int d, int nd, int m, const int32_t* gloc,
+                       double scale, int G, int M, int nz, int nxy, double* out, double* minval,
+                       cudaStream_t st);
 void launch_import_phi(double* phi, const int32_t* slot_of_xy, int G, int nz, int nxy, int64_t Sb,
                        const double* in, cudaStream_t st);
 void launch_fill(double* p, double v, int64_t n, cudaStream_t st);

@@ -55,6 +55,7 @@ struct ClassPlan {
    int64_t S = 0;                       // slots = npatch * P
    int fin = 0;                         // max incoming lateral faces
    int ring = 2;                        // smem ring depth
+   int nsteps = 1;                      // pipeline steps stored per patch: max local levels + nz - 1
    std::vector<int32_t> cell_of;        // [S] base slot (or -1)
    std::vector<int32_t> pos_of;         // [Sb] base slot -> class slot (or -1)
    std::vector<uint16_t> lvl;           // [S] local level, LVL_EMPTY for holes
@@ -354,6 +355,7 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
             for (int u : lup[c]) maxdiff = std::max(maxdiff, ll[c] - ll[u]);
          }
          cp.ring = std::min(RING_MAX, maxdiff + 1);
+         cp.nsteps = *std::max_element(cp.patch_nlev.begin(), cp.patch_nlev.end()) + pl.nz - 1;
          // sources and vectors
          cp.out_vec.assign(S, Vec2{0, 0});
          cp.in_src.assign((size_t)FIN_MAX * S, SRC_NONE);
