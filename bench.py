@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""Benchmark of the SN k-eigenvalue hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, host cores)
+
+Workload (BASELINE.json configs[3]): synthetic 3-D Cartesian core, 216 x 216 x 216 = 10 077 696
+cells, S8 (80 directions), 8 energy groups, vacuum boundaries, checkerboard of fuel / moderator
+assemblies, cross sections from seed 12345.  One "step" is one source
+iteration: scattering + fission source, transport sweep of every direction and group, flux-moment /
+k-eff reduction (and the NCCL allreduce of the flux moments when sharded over N GPUs).
+
+metric = cell*angle*group updates per second = cells * directions * groups * steps / time.
+The sweep is sharded over the ranks by angle set; the total work is fixed => scaling "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cell-angle-group updates/s per source iteration"
+UNIT = "updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, nargs=3, default=[216, 216, 216])
+    ap.add_argument("--groups", type=int, default=8)
+    ap.add_argument("--order", type=int, default=8)
+    ap.add_argument("--cpu-scale", type=int, default=2, help="CPU sample: mesh edge divided by this")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opts", default="{}", help="JSON of pampa_sn_options overrides")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "synthetic 3D extruded Cartesian core %dx%dx%d=%d cells, S%d, %d groups" % (
+        a.size[0], a.size[1], a.size[2], a.size[0] * a.size[1] * a.size[2], a.order, a.groups)
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.stop_flag, self.index = [], False, index
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.samples.append([t.strip() for t in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        self.thread.join(timeout=6)
+        sm = [int(s[0]) for s in self.samples if len(s) >= 6 and s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if len(s) >= 6 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v == "Active"})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_problem(a, scale):
+    from oracle import sweep_cpu
+    from pampa_b200 import synthetic as syn
+    n = [max(8, s // scale) for s in a.size]
+    mesh, xs = syn.checkerboard_core(n[0], n[1], n[2], num_groups=a.groups)
+    quad = syn.level_symmetric(a.order)
+    mats = mesh.materials.reshape(n[2], n[1], n[0])
+    cpu = sweep_cpu.SweepCPU(np.ones(n[0]), np.ones(n[1]), np.ones(n[2]), mats, xs.sigma_total,
+                             xs.sigma_scattering, xs.nu_sigma_fission, xs.chi_effective, quad.directions,
+                             quad.weights)
+    updates = n[0] * n[1] * n[2] * len(quad.weights) * a.groups
+    return cpu, updates, n
+
+
+def cpu_time_steps(a, scale, steps, warmup):
+    cpu, updates, n = cpu_problem(a, scale)
+    phi = np.ones(a.groups * n[0] * n[1] * n[2])
+    k = 1.0
+    for _ in range(warmup):
+        k = cpu.iterate(phi, k, 1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        k = cpu.iterate(phi, k, 1)
+    dt = time.perf_counter() - t0
+    sample = "%dx%dx%d sub-core of the same workload (1/%d of the cells), %d source iterations, fp64" % (
+        n[0], n[1], n[2], scale ** 3, steps)
+    return updates * steps / dt, dt / steps * 1e3, cpu.threads, sample
+
+
+def run_reference(a, rank):
+    """CPU arm: the oracle's C/OpenMP port of the same discrete operator on all host cores.  The
+    reference's own PETSc/SLEPc path cannot be built here and cannot form its monolithic matrix at
+    this size, so kind = "port"."""
+    if rank != 0:
+        return
+    # a bounded sample sized so that warmup + steps end within a few minutes
+    scale = max(a.cpu_scale, 2)
+    per_step_budget_s = 240.0 / max(1, a.steps + a.warmup)
+    while True:
+        n = [max(8, s // scale) for s in a.size]
+        est = n[0] * n[1] * n[2] * a.order * (a.order + 2) * a.groups / 1.5e8      # ~1.5e8 updates/s on 8 cores
+        if est <= per_step_budget_s or scale >= 16:
+            break
+        scale += 1
+    value, ms, threads, sample = cpu_time_steps(a, scale, a.steps, min(a.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "cpu_sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_b200(a, rank, world, local_rank):
+    import torch
+    from pampa_b200 import problem as pb, synthetic as syn
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    nx, ny, nz = a.size
+    mesh, xs = syn.checkerboard_core(nx, ny, nz, num_groups=a.groups)
+    quad = syn.level_symmetric(a.order)
+    M = len(quad.weights)
+    opts = dict(device=local_rank, rank=rank, num_ranks=world)
+    opts.update(json.loads(a.opts))
+    dev = pb.SNDevice(mesh, xs, quad, **opts)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(pb.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        dev.comm_init(bytes(uid.cpu().numpy().tobytes()))
+
+    info0 = dev.info()
+    U_total = mesh.num_cells * M * a.groups          # whole-job updates per step
+    U_own = info0["updates_per_sweep"]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dev.iterate(a.warmup)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = dev.info()["kernel_launches"]
+    k, total_ms, sweep_ms = dev.iterate_timed(a.steps)
+    barrier()
+    launches = dev.info()["kernel_launches"] - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([total_ms, sweep_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, sweep_ms = float(t[0]), float(t[1])
+
+    value = U_total * a.steps / (total_ms * 1e-3)
+
+    # roofline of the dominant kernel (the sweep), algorithmic bytes per update 16 + 16/M
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    b_alg = 16.0 + 16.0 / M
+    achieved = U_own * a.steps * b_alg / (sweep_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "sn_sweep_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_update": b_alg, "launches_per_step": info0["sweep_launches"],
+                "sweep_ms_per_step": sweep_ms / a.steps}
+
+    # end to end through the C ABI with host buffers: one solve-like call = upload of the cross
+    # sections and of the flux iterate, K source iterations, download of scalar flux and power
+    e2e = None
+    if not a.no_e2e:
+        n_phi = mesh.num_cells * a.groups
+        host_in = torch.empty(n_phi, dtype=torch.float64, pin_memory=True).numpy()
+        host_in[:] = 1.0
+        barrier()
+        t0 = time.perf_counter()
+        dev.update_xs(xs)
+        dev.set("flux-moments", host_in)
+        dev.iterate(a.steps)
+        phi_out = dev.get("scalar-flux")
+        pow_out = dev.get("power")
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        xs_bytes = sum(v.nbytes for v in (xs.sigma_total, xs.sigma_scattering, xs.nu_sigma_fission,
+                                          xs.kappa_sigma_fission, xs.chi_effective))
+        e2e = {"value": U_total * a.steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": (host_in.nbytes + xs_bytes) / a.steps,
+               "d2h_bytes_per_step": (phi_out.nbytes + pow_out.nbytes) / a.steps,
+               "call": "update_xs + set(flux-moments) + %d source iterations + get(scalar-flux, power)" % a.steps}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, ms, threads, sample = cpu_time_steps(a, max(a.cpu_scale, 2), 2, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(a), "parallelism": "angle-set sharding x%d" % world,
+                           "l2_policy": "working set (%.1f GB) far exceeds the 126 MB L2" % (info0["device_bytes"] / 1e9),
+                           "keff_after_steps": k, "options": json.loads(a.opts)},
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    dev.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+    if world == 1 and a.gpus > 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_b200(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -131,6 +131,11 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
 /* Run `iterations` source iterations with no convergence test (benchmark / warm-up). */
 int pampa_sn_iterate(pampa_sn_handle* h, int32_t iterations, double* keff);
 
+/* Same, timed on the device with CUDA events on the launching stream: total_ms spans the whole
+ * call, sweep_ms is the sum over iterations of the sweep-kernel launches alone. */
+int pampa_sn_iterate_timed(pampa_sn_handle* h, int32_t iterations, double* keff, double* total_ms,
+                           double* sweep_ms);
+
 /* Fields in the reference layouts (src/SNSolver.cxx:721-747):
  *   "scalar-flux" [i][g], "angular-flux" [i][g][m], "power" [i], "production-rate" [i],
  *   "delayed-source" [i]  (get);   "temperature" [i], "delayed-source" [i] (set, stored only);

@@ -64,6 +64,7 @@ SYMBOLS = {
     "pampa_sn_reduce": (C.c_int, [C.c_void_p, p_f64, p_f64, p_f64]),
     "pampa_sn_solve_keff": (C.c_int, [C.c_void_p, f64, f64, i32, f64, p_f64, p_i32]),
     "pampa_sn_iterate": (C.c_int, [C.c_void_p, i32, p_f64]),
+    "pampa_sn_iterate_timed": (C.c_int, [C.c_void_p, i32, p_f64, p_f64, p_f64]),
     "pampa_sn_get": (C.c_int, [C.c_void_p, C.c_char_p, p_f64]),
     "pampa_sn_set": (C.c_int, [C.c_void_p, C.c_char_p, p_f64]),
     "pampa_sn_field_size": (i64, [C.c_void_p, C.c_char_p]),

@@ -585,6 +585,38 @@ int pampa_sn_iterate(pampa_sn_handle* h, int32_t iterations, double* keff) {
    return check_async(h, "the source iteration");
 }
 
+int pampa_sn_iterate_timed(pampa_sn_handle* h, int32_t iterations, double* keff, double* total_ms,
+                           double* sweep_ms) {
+   SN_CUDA(h, cudaSetDevice(h->device));
+   std::vector<cudaEvent_t> ev(2 * (size_t)iterations + 2);
+   for (auto& e : ev) SN_CUDA(h, cudaEventCreate(&e));
+   int rc = 0;
+   SN_CUDA(h, cudaStreamSynchronize(h->stream));
+   cudaEventRecord(ev[0], h->stream);
+   for (int it = 0; it < iterations && !rc; it++) {
+      rc = do_source(h);
+      cudaEventRecord(ev[2 + 2 * it], h->stream);
+      if (!rc) rc = do_sweep(h);
+      cudaEventRecord(ev[3 + 2 * it], h->stream);
+      if (!rc) rc = do_exchange(h);
+      if (!rc) rc = do_reduce(h, 1);
+   }
+   cudaEventRecord(ev[1], h->stream);
+   if (!rc) rc = sync_scalars(h);
+   if (!rc) {
+      float ms = 0, sw = 0, t = 0;
+      cudaEventElapsedTime(&ms, ev[0], ev[1]);
+      for (int it = 0; it < iterations; it++) { cudaEventElapsedTime(&t, ev[2 + 2 * it], ev[3 + 2 * it]); sw += t; }
+      if (total_ms) *total_ms = ms;
+      if (sweep_ms) *sweep_ms = sw;
+      h->keff = h->sc.keff;
+      if (keff) *keff = h->sc.keff;
+   }
+   for (auto& e : ev) cudaEventDestroy(e);
+   if (rc) return 1;
+   return check_async(h, "the source iteration");
+}
+
 int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_t max_it, double power,
                         double* keff, int32_t* iterations) {
    SN_CUDA(h, cudaSetDevice(h->device));

@@ -233,6 +233,12 @@ class SNDevice:
         self._check(self.lib.pampa_sn_iterate(self.h, n, C.byref(k)))
         return k.value
 
+    def iterate_timed(self, n: int):
+        """n source iterations; returns (keff, total device ms, sweep-kernel device ms)."""
+        k, a, b = C.c_double(), C.c_double(), C.c_double()
+        self._check(self.lib.pampa_sn_iterate_timed(self.h, n, C.byref(k), C.byref(a), C.byref(b)))
+        return k.value, a.value, b.value
+
     def solve_keff(self, tol_k=1e-9, tol_phi=1e-8, max_it=20000, power=1.0):
         k, it = C.c_double(), C.c_int32()
         self._check(self.lib.pampa_sn_solve_keff(self.h, tol_k, tol_phi, max_it, power, C.byref(k), C.byref(it)))
