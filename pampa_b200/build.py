@@ -60,8 +60,21 @@ def build_host(force=False):
     return out
 
 
+def build_main(force=False):
+    """bin/pampa: the stand-alone driver (analogue of the reference's cxx main)."""
+    src = os.path.join(HOST, "main.cxx")
+    out = os.path.join(HERE, "bin", "pampa")
+    if not os.path.exists(src):
+        return None
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if force or _newer(out, [src, os.path.join(LIB, "libpampa.so")]):
+        _run(["g++", "-O2", "-std=c++17", src, "-o", out, "-L" + LIB, "-lpampa", "-lpampa_sn_b200",
+              "-Wl,-rpath,$ORIGIN/../lib"])
+    return out
+
+
 def build_all(force=False):
-    return [build_cuda(force), build_host(force)]
+    return [build_cuda(force), build_host(force), build_main(force)]
 
 
 if __name__ == "__main__":

@@ -33,10 +33,28 @@ CASES = {
 }
 
 
-def main():
+def hex_core_deck(groups):
+    """BASELINE config 3: the reference ships no SN input for hex-core, so this authors one on its
+    hex-cells mesh (test/hex-core/hex-cells-diffusion-3d/mesh.pmp: 163 hexagons x 16 layers) with the
+    materials of that directory's input.pmp:5-10, S8, vacuum on every boundary, LS off."""
+    base = os.path.join(REF, "hex-core")
+    mesh = orc.read_unstructured_mesh(os.path.join(base, "hex-cells-diffusion-3d", "mesh.pmp"))
+    names = ["fuel", "fuel", "fuel", "fuel", "reflector", "reflector"]
+    xs = [orc.read_material(os.path.join(base, "materials", "%s-%d-groups.pmp" % (n, groups))) for n in names]
+    bcs = [0] * (1 + len(mesh.boundaries))
+    for b in ("exterior", "-z", "+z"):
+        bcs[mesh.boundaries.index(b) + 1] = orc.VACUUM
+    return orc.Deck(mesh=mesh, xs=xs, G=groups, order=8, delta=1.0, ls=False, power=1.0, bcs=bcs)
+
+
+def main(only=None):
     ref_lines = open(os.path.join(REF, "check_ref.txt")).read().split("\n")
-    for name, (deck_path, line, gold, ls_mode, order) in CASES.items():
-        deck = orc.read_deck(os.path.join(REF, deck_path))
+    cases = dict(CASES)
+    cases["hex_core_s8_2g"] = ("hex-core", None, None, "off", None)
+    for name, (deck_path, line, gold, ls_mode, order) in cases.items():
+        if only and name not in only:
+            continue
+        deck = hex_core_deck(2) if deck_path == "hex-core" else orc.read_deck(os.path.join(REF, deck_path))
         if order is not None:
             deck.order = order
         op = orc.build_operator(deck.mesh, deck.xs, deck.G, deck.order, deck.delta, ls_mode, deck.bcs)
@@ -67,4 +85,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:] or None)
