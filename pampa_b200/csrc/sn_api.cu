@@ -188,6 +188,12 @@ int do_sweep(pampa_sn_handle* h) {
                     (const int32_t* const*)h->d_class_pos_of, h->stream);
       h->launches++;
    }
+   if (h->opts.num_ranks > 1) {
+      // sharded: the boundary buffers are summed over the ranks afterwards, so the entries this rank
+      // does not write must be zero rather than two sweeps old
+      if (gp.bnd_new) cudaMemsetAsync(gp.bnd_new, 0, (size_t)h->bnd_count * sizeof(double), h->stream);
+      if (gp.bndz_new) cudaMemsetAsync(gp.bndz_new, 0, (size_t)h->bndz_count * sizeof(double), h->stream);
+   }
    for (const LaunchGroup& lg : h->groups) {
       launch_sweep(gp, h->d_tasks + lg.offset, lg.count, lg.dt, lg.fin, lg.ring, lg.extras, h->stream);
       h->launches++;

@@ -35,7 +35,7 @@ def _check_solution(dev, k, sol_keff, sol_phi, sol_power):
 
 
 @pytest.mark.parametrize("name", ["slabs_s2", "slabs_s4", "pwr_cartesian_s2", "pwr_unstructured_s2",
-                                  "pwr_cartesian_s2_lsoff", "pwr_cartesian_s8_lsoff"])
+                                  "pwr_cartesian_s2_lsoff", "pwr_cartesian_s8_lsoff", "hex_core_s8_2g"])
 def test_reference_cases(name):
     """The SN cases the reference ships (test/check_ref.txt:32,53,234,415) and two variants."""
     em, xs, quad, ls, z = util.load_golden(name)
