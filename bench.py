@@ -203,10 +203,14 @@ def run_b200(a, rank, world, local_rank):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        # DRAM bytes per update from the committed ncu --set full capture, scaled to the average launch
+        per_update = json.load(open(tpath)).get("dram_bytes_per_update")
+        if per_update:
+            traffic = per_update * U_own / max(1, info0["sweep_launches"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "sn_sweep_kernel", "peak_source": peak_src,
                 "algorithmic_bytes_per_update": b_alg, "launches_per_step": info0["sweep_launches"],
+                "algorithmic_bytes_per_launch": b_alg * U_own / max(1, info0["sweep_launches"]),
                 "sweep_ms_per_step": sweep_ms / a.steps}
 
     # end to end through the C ABI with host buffers: one solve-like call = upload of the cross
