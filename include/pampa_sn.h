@@ -105,6 +105,7 @@ typedef struct {
    int32_t shard_mode;           /* 0: shard sweep chunks (angle sets), 1: shard energy groups */
    int32_t verbose;
    int32_t dt_max;               /* directions swept together per CTA, 1..10 (0: default) */
+   int32_t generic_only;         /* 1: never use the staged tile kernel (A/B testing) */
 } pampa_sn_options;
 
 void pampa_sn_default_options(pampa_sn_options* opts);

@@ -41,7 +41,7 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
 
-struct LaunchGroup { int wave, dt, fin, ring; bool extras; int64_t offset; int count; };
+struct LaunchGroup { int wave, kind, dt, fin, ring; bool extras; int64_t offset; int count; };
 
 }  // namespace
 
@@ -83,6 +83,10 @@ struct pampa_sn_handle {
    double *d_ls_coef = nullptr, *d_ls_dD = nullptr, *d_ls_rhs = nullptr;
    std::vector<int> dir_chunk, dir_d;
    bool extras = false;
+   // staged tile kernel
+   std::vector<char> class_fast;
+   int32_t *d_fast_classes = nullptr, *d_fast_chunks = nullptr;
+   int nfast_classes = 0, nfast_chunks = 0;
 
    // iteration state
    ReduceScalars sc{};
@@ -108,6 +112,7 @@ struct pampa_sn_handle {
       gp.has_z = plan.has_z; gp.nrf = plan.num_rfaces; gp.nls = nls;
       gp.bcz_minus_refl = bcz_refl[0]; gp.bcz_plus_refl = bcz_refl[1];
       gp.store_psi = 1;
+      gp.nmat = nmat;
       return gp;
    }
    int bcz_refl[2] = {0, 0};
@@ -194,8 +199,18 @@ int do_sweep(pampa_sn_handle* h) {
       if (gp.bnd_new) cudaMemsetAsync(gp.bnd_new, 0, (size_t)h->bnd_count * sizeof(double), h->stream);
       if (gp.bndz_new) cudaMemsetAsync(gp.bndz_new, 0, (size_t)h->bndz_count * sizeof(double), h->stream);
    }
+   if (h->nfast_classes > 0) {
+      launch_shear_q(gp, h->d_classes, h->d_fast_classes, h->nfast_classes, h->plan.npatch_b, h->stream);
+      h->launches++;
+   }
    for (const LaunchGroup& lg : h->groups) {
-      launch_sweep(gp, h->d_tasks + lg.offset, lg.count, lg.dt, lg.fin, lg.ring, lg.extras, h->stream);
+      if (lg.kind == 1) launch_sweep_tile(gp, h->d_tasks + lg.offset, lg.count, lg.dt, lg.extras, h->stream);
+      else launch_sweep(gp, h->d_tasks + lg.offset, lg.count, lg.dt, lg.fin, lg.ring, lg.extras, h->stream);
+      h->launches++;
+   }
+   if (h->nfast_chunks > 0) {
+      launch_unshear_phi(gp, h->d_chunks, h->d_classes, h->d_fast_chunks, h->nfast_chunks, h->plan.npatch_b,
+                         h->stream);
       h->launches++;
    }
    h->bnd_cur = 1 - h->bnd_cur;      // what this sweep wrote is what the next one reads
@@ -333,6 +348,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       SN_CUDA(h, cudaEventCreate(&h->ev0));
       SN_CUDA(h, cudaEventCreate(&h->ev1));
       SN_CUDA(h, configure_sweep_kernels());
+      SN_CUDA(h, configure_tile_kernels());
 
       const int nr = h->opts.num_ranks, rank = h->opts.rank;
       h->gloc.assign(h->G, -1); h->Gown = 0;
@@ -423,6 +439,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
 
       // classes
       std::vector<ClassDev> cdev(pl.classes.size());
+      h->class_fast.assign(pl.classes.size(), 0);
       h->d_pos_of.assign(pl.classes.size(), nullptr);
       for (size_t ci = 0; ci < pl.classes.size(); ci++) {
          const ClassPlan& cp = pl.classes[ci];
@@ -450,6 +467,22 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
              dev_upload(h, &d_in_src, cp.in_src) || dev_upload(h, &d_in_vec, cp.in_vec) ||
              dev_upload(h, &d_rout, cp.rout) || dev_upload(h, &h->d_pos_of[ci], cp.pos_of)) return 1;
          if (h->nls > 0 && dev_upload(h, &d_ls_of, ls_of[ci])) return 1;
+         uint16_t* d_hidx;
+         if (dev_upload(h, &d_hidx, cp.in_hidx)) return 1;
+         cd.in_hidx = d_hidx;
+         cd.q_sheared = nullptr;
+         h->class_fast[ci] = cp.fast && h->nls == 0 && h->nmat <= 4096 && !h->opts.generic_only;
+         if (h->class_fast[ci]) {
+            bool any_owned = false;
+            for (size_t c = 0; c < pl.chunks.size(); c++) any_owned |= (pl.chunks[c].cls == (int)ci && chunk_owned[c]);
+            if (!any_owned) h->class_fast[ci] = 0;
+         }
+         if (h->class_fast[ci]) {
+            double* d_qs;
+            if (dev_alloc(h, &d_qs, (int64_t)h->G * cp.npatch * cp.nsteps * PS)) return 1;
+            SN_CUDA(h, cudaMemsetAsync(d_qs, 0, (size_t)h->G * cp.npatch * cp.nsteps * PS * sizeof(double), h->stream));
+            cd.q_sheared = d_qs;
+         }
          cd.cell_of = d_cell_of; cd.lvl = d_lvl; cd.patch_nlev = d_patch_nlev;
          cd.out_vec = (const double2*)d_out_vec; cd.in_src = d_in_src; cd.in_vec = (const double2*)d_in_vec;
          cd.rout = d_rout; cd.ls_of = d_ls_of;
@@ -459,6 +492,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
 
       // chunks
       std::vector<ChunkDev> chdev(pl.chunks.size());
+      std::vector<int32_t> fast_chunks;
       h->dir_chunk.assign(h->M, -1); h->dir_d.assign(h->M, -1);
       for (size_t c = 0; c < pl.chunks.size(); c++) {
          const Chunk& ch = pl.chunks[c];
@@ -476,6 +510,18 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
             }
          }
          cd.psi = chunk_owned[c] ? h->d_psi + psi_off[c] : nullptr;
+         cd.phi_part = nullptr;
+         if (chunk_owned[c] && h->class_fast[ch.cls]) {
+            const ClassPlan& cpc = pl.classes[ch.cls];
+            if (dev_alloc(h, &cd.phi_part, (int64_t)h->Gown * cpc.npatch * cpc.nsteps * PS)) return 1;
+            fast_chunks.push_back((int32_t)c);
+         }
+      }
+      {
+         std::vector<int32_t> fast_classes;
+         for (size_t ci = 0; ci < pl.classes.size(); ci++) if (h->class_fast[ci]) fast_classes.push_back((int32_t)ci);
+         h->nfast_classes = (int)fast_classes.size(); h->nfast_chunks = (int)fast_chunks.size();
+         if (dev_upload(h, &h->d_fast_classes, fast_classes) || dev_upload(h, &h->d_fast_chunks, fast_chunks)) return 1;
       }
       if (dev_upload(h, &h->d_chunks, chdev)) return 1;
       {
@@ -490,7 +536,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          std::vector<Task> tasks = pl.waves[w];
          auto variant = [&](const Task& t) {
             const Chunk& ch = pl.chunks[t.chunk]; const ClassPlan& cp = pl.classes[ch.cls];
-            return std::make_tuple(dt_template(ch.nd), cp.fin <= 2 ? 2 : FIN_MAX, cp.ring);
+            return std::make_tuple(h->class_fast[ch.cls] ? 1 : 0, dt_template(ch.nd), cp.fin <= 2 ? 2 : FIN_MAX, cp.ring);
          };
          std::stable_sort(tasks.begin(), tasks.end(), [&](const Task& a, const Task& b) { return variant(a) < variant(b); });
          size_t i = 0;
@@ -498,7 +544,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
             size_t j = i;
             while (j < tasks.size() && variant(tasks[j]) == variant(tasks[i])) j++;
             auto v = variant(tasks[i]);
-            h->groups.push_back(LaunchGroup{(int)w, std::get<0>(v), std::get<1>(v), std::get<2>(v), h->extras,
+            h->groups.push_back(LaunchGroup{(int)w, std::get<0>(v), std::get<1>(v), std::get<2>(v), std::get<3>(v), h->extras,
                                             (int64_t)all.size() + (int64_t)i, (int)(j - i)});
             i = j;
          }

@@ -304,7 +304,366 @@ cudaError_t configure_sweep_kernels() {
    if ((e = cfg_dt<7>()) != cudaSuccess) return e;
    if ((e = cfg_dt<8>()) != cudaSuccess) return e;
    if ((e = cfg_dt<9>()) != cudaSuccess) return e;
-   return cfg_dt<10>();
+   if ((e = cfg_dt<10>()) != cudaSuccess) return e;
+   return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------ tile kernel
+// The fast path for classes swept on the shared 2-D tiles (Cartesian meshes): every lateral upwind
+// value is read from shared memory with the same instruction sequence on every lane --
+//   in-patch neighbour   -> the ring written by the neighbouring lane one step earlier,
+//   other patch / mirror -> a per-lane halo entry staged one step ahead with cp.async (no registers,
+//                           latency hidden behind the step's arithmetic),
+//   no source (vacuum)   -> zero coefficient --
+// the source q and the partial flux moments live in this class's step-major order (one contiguous
+// row of 256 doubles per CTA-step, written / read by sn_shear_q / sn_unshear_phi), and the divide is
+// an unconditional reciprocal (MUFU seed + 2 Newton steps).
+__device__ __forceinline__ double fast_rcp(double x) {
+   double r;
+   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+   double e = fma(-x, r, 1.0);
+   r = fma(r, e, r);
+   e = fma(-x, r, 1.0);
+   return fma(r, e, r);
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int DT, bool EXTRAS>
+__global__ void __launch_bounds__(PS, (DT <= 5 ? 2 : 1))
+sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
+   extern __shared__ double smem[];
+   constexpr int BUF = DT * PS;                       // one ring / halo buffer
+   const Task tk = tasks[blockIdx.x];
+   const ChunkDev* __restrict__ ch = gp.chunks + tk.chunk;
+   const ClassDev* __restrict__ cl = gp.classes + ch->cls;
+   const int t = threadIdx.x;
+   const int64_t S = cl->S;
+   const int64_t slot = (int64_t)tk.patch * PS + t;
+   const int g = tk.group;
+   const int gl = gp.gloc[g];
+   const int nz = gp.nz;
+   const int npatch = cl->npatch;
+   const int NS = cl->nsteps;
+   const int zdir = cl->zdir;
+   const int lv = cl->lvl[slot];
+   const bool valid = (lv != LVL_EMPTY);
+   const int lv0 = valid ? lv : 0;
+   const int kp0 = tk.zc * gp.Kc;
+   const int kcnt = min(gp.Kc, nz - kp0);
+   const int nsteps = cl->patch_nlev[tk.patch] + kcnt - 1;
+
+   // smem: ring[2][DT][PS] | halo[2][DT][PS] | mux,muy,muz,w [4][DT] | idz[nz] | sigma_t[nmat]
+   double* ring = smem;
+   double* halo = smem + 2 * BUF;
+   double* s_mux = smem + 4 * BUF;
+   double* s_muy = s_mux + DT;
+   double* s_muz = s_muy + DT;
+   double* s_w = s_muz + DT;
+   double* s_idz = s_w + DT;
+   double* s_sigt = s_idz + nz;
+   for (int a = t; a < 4 * BUF; a += PS) smem[a] = 0.0;
+   for (int kk = t; kk < nz; kk += PS) s_idz[kk] = gp.has_z ? gp.inv_dz[kk] : 0.0;
+   for (int m = t; m < gp.nmat; m += PS) s_sigt[m] = gp.sigma_t[m * gp.G + g];
+   if (t < DT) {
+      s_mux[t] = ch->mux[t];
+      s_muy[t] = ch->muy[t];
+      s_muz[t] = gp.has_z ? ch->muz_abs[t] : 0.0;
+      s_w[t] = ch->w[t];
+   }
+   __syncthreads();
+
+   // per-lane constants: coefficients, outgoing sum, the smem offset of each of the two sources
+   double a0[DT], a1[DT], so[DT];
+   int off0 = t, off1 = t;                            // default: own ring entry with a zero coefficient
+   int kind0 = -1, kind1 = -1, hx0 = 0, hx1 = 0;
+   const double* g0 = nullptr;                        // running global pointers of the staged sources
+   const double* g1 = nullptr;
+   {
+      const double2 ov = valid ? cl->out_vec[slot] : make_double2(0.0, 0.0);
+      const double2 v0 = valid ? cl->in_vec[slot] : make_double2(0.0, 0.0);
+      const double2 v1 = valid ? cl->in_vec[S + slot] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int d = 0; d < DT; d++) {
+         so[d] = s_mux[d] * ov.x + s_muy[d] * ov.y;
+         a0[d] = -(s_mux[d] * v0.x + s_muy[d] * v0.y);
+         a1[d] = -(s_mux[d] * v1.x + s_muy[d] * v1.y);
+      }
+      const int c0 = valid ? cl->in_src[slot] : SRC_NONE;
+      const int c1 = valid ? cl->in_src[S + slot] : SRC_NONE;
+      const double* psi_gl = ch->psi + (int64_t)gl * npatch * NS * BUF;
+      if (c0 >= 0) {
+         kind0 = c0 >> SRC_KIND_SHIFT;
+         const int pay = c0 & SRC_PAYLOAD;
+         if (kind0 == SRC_LOCAL) off0 = pay;
+         else {
+            hx0 = cl->in_hidx[slot]; off0 = 2 * BUF + hx0;
+            if (kind0 == SRC_GLOBAL)
+               g0 = psi_gl + (((int64_t)(pay >> 8) * NS + kp0 + cl->lvl[pay]) * DT) * PS + (pay & (PS - 1));
+         }
+      }
+      if (c1 >= 0) {
+         kind1 = c1 >> SRC_KIND_SHIFT;
+         const int pay = c1 & SRC_PAYLOAD;
+         if (kind1 == SRC_LOCAL) off1 = pay;
+         else {
+            hx1 = cl->in_hidx[S + slot]; off1 = 2 * BUF + hx1;
+            if (kind1 == SRC_GLOBAL)
+               g1 = psi_gl + (((int64_t)(pay >> 8) * NS + kp0 + cl->lvl[pay]) * DT) * PS + (pay & (PS - 1));
+         }
+      }
+   }
+   const bool staged = valid && (kind0 == SRC_GLOBAL || kind1 == SRC_GLOBAL || kind0 == SRC_REFL || kind1 == SRC_REFL);
+   int rout[ROUT_MAX];
+   if (EXTRAS) {
+#pragma unroll
+      for (int r = 0; r < ROUT_MAX; r++) rout[r] = valid ? cl->rout[(size_t)r * S + slot] : -1;
+   }
+
+   const int64_t row0 = ((int64_t)tk.patch * NS + kp0 + lv0) * PS + t;      // (patch, step, lane) offset
+   double* psi_w = ch->psi + (((int64_t)gl * npatch * NS) * DT) * PS + (row0 - t) * DT + t;
+   const int32_t* mats_w = cl->mats_s + row0;
+   const double* q_w = cl->q_sheared + (int64_t)g * npatch * NS * PS + row0;
+   double* ph_w = ch->phi_part + (int64_t)gl * npatch * NS * PS + row0;
+   const int cell = (int)slot;                         // tile classes: class slot == base slot
+   int k = zdir >= 0 ? kp0 : nz - 1 - kp0;
+   const int kdir = zdir >= 0 ? 1 : -1;
+
+   // stage the halo of one layer: patch-boundary values from the neighbouring patch's psi, mirrored
+   // values from the reflective boundary buffers
+   auto stage = [&](double* dst_buf, int kk, int step_ahead) {
+      if (kind0 == SRC_GLOBAL) {
+#pragma unroll
+         for (int d = 0; d < DT; d++) cp_async8(dst_buf + d * PS + hx0, g0 + (int64_t)step_ahead * BUF + d * PS);
+      } else if (EXTRAS && kind0 == SRC_REFL) {
+         const int pay = cl->in_src[slot] & SRC_PAYLOAD;
+         const int axis = pay >> SRC_AXIS_SHIFT, rf = pay & ((1 << SRC_AXIS_SHIFT) - 1);
+#pragma unroll
+         for (int d = 0; d < DT; d++)
+            cp_async8(dst_buf + d * PS + hx0,
+                      gp.bnd_old + (((int64_t)ch->mrefl[d][axis] * gp.G + g) * nz + kk) * gp.nrf + rf);
+      }
+      if (kind1 == SRC_GLOBAL) {
+#pragma unroll
+         for (int d = 0; d < DT; d++) cp_async8(dst_buf + d * PS + hx1, g1 + (int64_t)step_ahead * BUF + d * PS);
+      } else if (EXTRAS && kind1 == SRC_REFL) {
+         const int pay = cl->in_src[S + slot] & SRC_PAYLOAD;
+         const int axis = pay >> SRC_AXIS_SHIFT, rf = pay & ((1 << SRC_AXIS_SHIFT) - 1);
+#pragma unroll
+         for (int d = 0; d < DT; d++)
+            cp_async8(dst_buf + d * PS + hx1,
+                      gp.bnd_old + (((int64_t)ch->mrefl[d][axis] * gp.G + g) * nz + kk) * gp.nrf + rf);
+      }
+   };
+
+   // z-upwind start values
+   double psiz[DT];
+#pragma unroll
+   for (int d = 0; d < DT; d++) psiz[d] = 0.0;
+   if (gp.has_z && valid) {
+      if (kp0 > 0) {
+#pragma unroll
+         for (int d = 0; d < DT; d++) psiz[d] = ldcg_f64(psi_w - BUF + d * PS);
+      } else if (EXTRAS) {
+         const int face = zdir > 0 ? 0 : 1;
+         if (face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl) {
+#pragma unroll
+            for (int d = 0; d < DT; d++)
+               psiz[d] = gp.bndz_old[(((int64_t)face * gp.M + ch->mrefl[d][2]) * gp.G + g) * gp.Sb + cell];
+         }
+      }
+   }
+
+   // prime: inputs and halo of my first layer
+   int mat_c = 0;
+   double q_c = 0.0;
+   if (valid) { mat_c = mats_w[0]; q_c = q_w[0]; }
+   if (staged) { stage(halo, k, 0); cp_async_wait_all(); }
+   __syncthreads();
+
+   int tog = 0;                                        // 0 / BUF: which of the two buffers my layer uses
+   for (int step = 0; step < nsteps; step++) {
+      const int kl = step - lv0;
+      if (valid && kl >= 0 && kl < kcnt) {
+         const bool more = kl + 1 < kcnt;
+         if (staged && more) stage(halo + (BUF - tog), k + kdir, kl + 1);
+         const int mat = mat_c;
+         const double qv = q_c;
+         if (more) { mat_c = mats_w[PS]; q_c = q_w[PS]; }
+         const double st = s_sigt[mat];
+         const double idz = s_idz[k];
+         const double* r0 = smem + off0 + tog;
+         const double* r1 = smem + off1 + tog;
+         double* rw = ring + tog + t;
+         double ph = 0.0;
+#pragma unroll
+         for (int d = 0; d < DT; d++) {
+            const double az = s_muz[d] * idz;
+            double acc = fma(az, psiz[d], qv);
+            acc = fma(a0[d], r0[d * PS], acc);
+            acc = fma(a1[d], r1[d * PS], acc);
+            const double v = acc * fast_rcp(st + so[d] + az);
+            psiz[d] = v;
+            rw[d * PS] = v;
+            psi_w[d * PS] = v;
+            ph = fma(s_w[d], v, ph);
+         }
+         ph_w[0] = ph;
+         if (EXTRAS) {
+#pragma unroll
+            for (int r = 0; r < ROUT_MAX; r++)
+               if (rout[r] >= 0) {
+#pragma unroll
+                  for (int d = 0; d < DT; d++)
+                     gp.bnd_new[(((int64_t)ch->m[d] * gp.G + g) * nz + k) * gp.nrf + rout[r]] = psiz[d];
+               }
+            if (gp.has_z && kp0 + kl == nz - 1) {
+               const int face = zdir > 0 ? 1 : 0;
+               if (face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl) {
+#pragma unroll
+                  for (int d = 0; d < DT; d++)
+                     gp.bndz_new[(((int64_t)face * gp.M + ch->m[d]) * gp.G + g) * gp.Sb + cell] = psiz[d];
+               }
+            }
+         }
+         tog = BUF - tog;
+         psi_w += BUF;
+         mats_w += PS; q_w += PS; ph_w += PS;
+         k += kdir;
+         if (staged) cp_async_wait_all();
+      }
+      __syncthreads();
+   }
+}
+
+template <int DT>
+static void launch_tile_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, bool extras, cudaStream_t st) {
+   const size_t smem = ((size_t)4 * DT * PS + 4 * DT + gp.nz + gp.nmat) * sizeof(double);
+   if (extras) sn_sweep_tile_kernel<DT, true><<<ntasks, PS, smem, st>>>(gp, d_tasks);
+   else        sn_sweep_tile_kernel<DT, false><<<ntasks, PS, smem, st>>>(gp, d_tasks);
+}
+
+void launch_sweep_tile(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras,
+                       cudaStream_t st) {
+   if (ntasks <= 0) return;
+   switch (dt) {
+      case 1: launch_tile_dt<1>(gp, d_tasks, ntasks, extras, st); break;
+      case 2: launch_tile_dt<2>(gp, d_tasks, ntasks, extras, st); break;
+      case 3: launch_tile_dt<3>(gp, d_tasks, ntasks, extras, st); break;
+      case 4: launch_tile_dt<4>(gp, d_tasks, ntasks, extras, st); break;
+      case 5: launch_tile_dt<5>(gp, d_tasks, ntasks, extras, st); break;
+      case 6: launch_tile_dt<6>(gp, d_tasks, ntasks, extras, st); break;
+      case 7: launch_tile_dt<7>(gp, d_tasks, ntasks, extras, st); break;
+      case 8: launch_tile_dt<8>(gp, d_tasks, ntasks, extras, st); break;
+      case 9: launch_tile_dt<9>(gp, d_tasks, ntasks, extras, st); break;
+      default: launch_tile_dt<10>(gp, d_tasks, ntasks, extras, st); break;
+   }
+}
+
+template <int DT>
+static cudaError_t cfg_tile() {
+   cudaError_t e = cudaFuncSetAttribute(sn_sweep_tile_kernel<DT, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+   if (e != cudaSuccess) return e;
+   return cudaFuncSetAttribute(sn_sweep_tile_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               160 * 1024);
+}
+
+cudaError_t configure_tile_kernels() {
+   cudaError_t e;
+   if ((e = cfg_tile<1>()) != cudaSuccess) return e;
+   if ((e = cfg_tile<2>()) != cudaSuccess) return e;
+   if ((e = cfg_tile<3>()) != cudaSuccess) return e;
+   if ((e = cfg_tile<4>()) != cudaSuccess) return e;
+   if ((e = cfg_tile<5>()) != cudaSuccess) return e;
+   if ((e = cfg_tile<6>()) != cudaSuccess) return e;
+   if ((e = cfg_tile<7>()) != cudaSuccess) return e;
+   if ((e = cfg_tile<8>()) != cudaSuccess) return e;
+   if ((e = cfg_tile<9>()) != cudaSuccess) return e;
+   return cfg_tile<10>();
+}
+
+// q (base layout [g][k][slot]) -> each fast class's step-major copy.  One CTA per (patch, block of
+// KB layers); a thread stages its own column through shared memory so that both the read (one layer
+// row) and the writes (one pipeline-step row) are coalesced.
+constexpr int SHEAR_KB = 16;
+__global__ void __launch_bounds__(PS)
+sn_shear_q_kernel(const SweepGlobals gp, const ClassDev* __restrict__ classes,
+                  const int32_t* __restrict__ fast_classes, int nfast, int npatch_b) {
+   __shared__ double tile[SHEAR_KB][PS];
+   const int t = threadIdx.x;
+   const int patch = blockIdx.x % npatch_b;
+   const int k0 = (blockIdx.x / npatch_b) * SHEAR_KB;
+   const int kb = min(SHEAR_KB, gp.nz - k0);
+   const int64_t slot = (int64_t)patch * PS + t;
+   for (int g = 0; g < gp.G; g++) {
+      const double* qg = gp.q + ((int64_t)g * gp.nz + k0) * gp.Sb + slot;
+      for (int kk = 0; kk < kb; kk++) tile[kk][t] = qg[(int64_t)kk * gp.Sb];     // own column only
+      for (int c = 0; c < nfast; c++) {
+         const ClassDev* cl = classes + fast_classes[c];
+         const int lv = cl->lvl[slot];
+         const int NS = cl->nsteps;
+         // layers k0 .. k0+kb-1 are the sweep positions kp_lo .. kp_lo+kb-1
+         const int kp_lo = cl->zdir >= 0 ? k0 : gp.nz - k0 - kb;
+         double* out = cl->q_sheared + (((int64_t)g * cl->npatch + patch) * NS + kp_lo) * PS + t;
+         const int nrow = kb + cl->patch_nlev[patch] - 1;
+         for (int r = 0; r < nrow; r++) {              // every lane on the same step-row: coalesced
+            const int a = r - lv;
+            if (lv != LVL_EMPTY && a >= 0 && a < kb) out[(int64_t)r * PS] = tile[cl->zdir >= 0 ? a : kb - 1 - a][t];
+         }
+      }
+   }
+}
+
+void launch_shear_q(const SweepGlobals& gp, const ClassDev* d_classes, const int32_t* d_fast_classes,
+                    int nfast, int npatch_b, cudaStream_t st) {
+   if (nfast <= 0) return;
+   const int nkb = (gp.nz + SHEAR_KB - 1) / SHEAR_KB;
+   sn_shear_q_kernel<<<npatch_b * nkb, PS, 0, st>>>(gp, d_classes, d_fast_classes, nfast, npatch_b);
+}
+
+// phi_new[g][k][slot] += sum over the fast chunks of their step-major partial moments.
+__global__ void __launch_bounds__(PS)
+sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks,
+                      const ClassDev* __restrict__ classes, const int32_t* __restrict__ fast_chunks,
+                      int nfast, int npatch_b) {
+   __shared__ double tile[SHEAR_KB][PS];
+   const int t = threadIdx.x;
+   const int patch = blockIdx.x % npatch_b;
+   const int k0 = (blockIdx.x / npatch_b) * SHEAR_KB;
+   const int kb = min(SHEAR_KB, gp.nz - k0);
+   const int64_t slot = (int64_t)patch * PS + t;
+   for (int g = 0; g < gp.G; g++) {
+      const int gl = gp.gloc[g];
+      if (gl < 0) continue;
+      for (int kk = 0; kk < kb; kk++) tile[kk][t] = 0.0;
+      for (int c = 0; c < nfast; c++) {
+         const ChunkDev* ch = chunks + fast_chunks[c];
+         const ClassDev* cl = classes + ch->cls;
+         const int lv = cl->lvl[slot];
+         const int NS = cl->nsteps;
+         const int kp_lo = cl->zdir >= 0 ? k0 : gp.nz - k0 - kb;
+         const double* in = ch->phi_part + (((int64_t)gl * cl->npatch + patch) * NS + kp_lo) * PS + t;
+         const int nrow = kb + cl->patch_nlev[patch] - 1;
+         for (int r = 0; r < nrow; r++) {
+            const int a = r - lv;
+            if (lv != LVL_EMPTY && a >= 0 && a < kb) tile[cl->zdir >= 0 ? a : kb - 1 - a][t] += in[(int64_t)r * PS];
+         }
+      }
+      double* pg = gp.phi_new + ((int64_t)g * gp.nz + k0) * gp.Sb + slot;
+      for (int kk = 0; kk < kb; kk++) pg[(int64_t)kk * gp.Sb] += tile[kk][t];
+   }
+}
+
+void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
+                        const int32_t* d_fast_chunks, int nfast, int npatch_b, cudaStream_t st) {
+   if (nfast <= 0) return;
+   const int nkb = (gp.nz + SHEAR_KB - 1) / SHEAR_KB;
+   sn_unshear_phi_kernel<<<npatch_b * nkb, PS, 0, st>>>(gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b);
 }
 
 // ------------------------------------------------------------------------------------ source

@@ -37,6 +37,9 @@ struct ClassDev {
    const double2* in_vec;     // [FIN_MAX][S]
    const int32_t* rout;       // [ROUT_MAX][S]
    const int32_t* ls_of;      // [S] index into the LS cell list or -1 (nullptr: no LS)
+   const uint16_t* in_hidx;   // [FIN_MAX][S] halo index of patch-boundary / reflective sources
+   double* q_sheared;         // [G][npatch][nsteps][PS] source in this class's step-major order
+                              // (nullptr: class swept by the generic kernel)
 };
 
 // Per chunk of directions swept together by one CTA.
@@ -47,6 +50,7 @@ struct ChunkDev {
    int32_t mrefl[DT_MAX][3];  // mirrored direction about x, y, z
    double mux[DT_MAX], muy[DT_MAX], muz_abs[DT_MAX], w[DT_MAX];
    double* psi;               // [Gown][npatch][nsteps][nd][PS]
+   double* phi_part;          // [Gown][npatch][nsteps][PS] sum_d w_d psi_d of this chunk (tile kernel)
 };
 
 struct SweepGlobals {
@@ -70,6 +74,7 @@ struct SweepGlobals {
    int32_t G, Gown, M, nz, Kc, has_z, nrf, nls;
    int32_t bcz_minus_refl, bcz_plus_refl;   // 1 if that z boundary is reflective
    int32_t store_psi;
+   int32_t nmat;
 };
 
 struct ReduceScalars {        // device-resident iteration state
@@ -85,6 +90,14 @@ struct ReduceScalars {        // device-resident iteration state
 void launch_sweep(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, int fin,
                   int ring, bool extras, cudaStream_t st);
 cudaError_t configure_sweep_kernels();
+cudaError_t configure_tile_kernels();
+void launch_sweep_tile(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras,
+                       cudaStream_t st);
+// base [g][k][slot] <-> step-major [g][patch][step][lane] transforms for the tile kernel
+void launch_shear_q(const SweepGlobals& gp, const ClassDev* d_classes, const int32_t* d_fast_classes,
+                    int nfast, int npatch_b, cudaStream_t st);
+void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
+                        const int32_t* d_fast_chunks, int nfast, int npatch_b, cudaStream_t st);
 
 void launch_source(const double* phi, double* q, const int32_t* mats, const double* sig_s,
                    const double* chi, const double* nusf, const ReduceScalars* sc, int G, int nz,

@@ -66,6 +66,9 @@ struct ClassPlan {
    std::vector<int32_t> in_src;         // [FIN_MAX][S]
    std::vector<Vec2> in_vec;            // [FIN_MAX][S] cf*f/area of the incoming face
    std::vector<int32_t> rout;           // [ROUT_MAX][S] reflective face id written by this slot
+   std::vector<uint16_t> in_hidx;       // [FIN_MAX][S] halo index of a patch-boundary / reflective source
+   int max_halo = 0;                    // largest number of such sources in one patch
+   bool fast = false;                   // eligible for the staged tile kernel
 };
 
 struct Chunk {
@@ -362,6 +365,8 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
          cp.in_src.assign((size_t)FIN_MAX * S, SRC_NONE);
          cp.in_vec.assign((size_t)FIN_MAX * S, Vec2{0, 0});
          cp.rout.assign((size_t)ROUT_MAX * S, -1);
+         cp.in_hidx.assign((size_t)FIN_MAX * S, 0);
+         std::vector<int> halo_count(cp.npatch, 0);
          for (int c = 0; c < nxy; c++) {
             const int64_t s = (int64_t)patch_of[c] * P + lane_of[c];
             int nin = 0, nro = 0;
@@ -390,11 +395,17 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
                   if (code != SRC_NONE) {
                      cp.in_src[(size_t)nin * S + s] = code;
                      cp.in_vec[(size_t)nin * S + s] = Vec2{vx, vy};
+                     if ((code >> SRC_KIND_SHIFT) != SRC_LOCAL)
+                        cp.in_hidx[(size_t)nin * S + s] = (uint16_t)std::min(65535, halo_count[patch_of[c]]++);
                      nin++;
                   }
                }
             }
          }
+         cp.max_halo = *std::max_element(halo_count.begin(), halo_count.end());
+         // the staged tile kernel: shared tiles, <= 2 incoming faces, double-buffered ring, and a
+         // halo that fits the 256-wide staging rows
+         cp.fast = cp.tiles && cp.fin <= 2 && cp.ring == 2 && cp.max_halo <= 256;
       }
    }
    class_flags.clear();
