@@ -78,7 +78,8 @@ def test_single_sweep_cartesian_3d():
     qd = np.einsum("nfg,nf->ng", op.sig_s, phi0) + op.chi * np.sum(op.nusf * phi0, axis=1)[:, None] / keff
     b = np.repeat((qd * op.vol[:, None]).reshape(N * G), M)
     psi = spla.splu(op.T.tocsc()).solve(b).reshape(N, G, M)
-    for opts in ({}, {"z_chunk": 4}, {"tile_i": 8, "tile_j": 4}):
+    for opts in ({}, {"z_chunk": 4}, {"tile_i": 8, "tile_j": 4}, {"generic_only": 1}, {"dt_max": 2, "z_chunk": 3},
+                 {"dt_max": 3, "generic_only": 1}):
         dev = pb.SNDevice(em, xs, quad, **opts)
         dev.set("flux-moments", phi0.reshape(-1))
         dev.source(keff)
@@ -105,11 +106,12 @@ def test_keff_cartesian_3d_reflective():
     em = syn.cartesian_mesh(h, h, np.full(nz, 2.5), mats, bcs)
     mesh, op = _oracle_cart(h, h, np.full(nz, 2.5), mats, bcs, xs, quad, G)
     sol = orc.solve_matrix_free(op)
-    dev, k, it = _solve(em, xs, quad)
-    _check_solution(dev, k, sol.keff, sol.phi, sol.power)
-    psi = dev.get("angular-flux").reshape(sol.psi.shape)
-    assert util.rel_l2(psi, sol.psi) < TOL_L2
-    dev.close()
+    for opts in ({}, {"generic_only": 1}, {"z_chunk": 3, "dt_max": 2}):
+        dev, k, it = _solve(em, xs, quad, **opts)
+        _check_solution(dev, k, sol.keff, sol.phi, sol.power)
+        psi = dev.get("angular-flux").reshape(sol.psi.shape)
+        assert util.rel_l2(psi, sol.psi) < TOL_L2
+        dev.close()
 
 
 def _hex_problem(nrings, nz, G, order, seed):
