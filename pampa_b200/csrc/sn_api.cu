@@ -385,7 +385,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          if (chunk_owned[c]) {
             psi_off[c] = psi_doubles;
             const ClassPlan& cpc = pl.classes[pl.chunks[c].cls];
-            psi_doubles += (int64_t)pl.chunks[c].nd * h->Gown * cpc.npatch * cpc.nsteps * PS;
+            psi_doubles += (int64_t)pl.chunks[c].nd * h->Gown * cpc.npatch * cpc.nsteps * PSX;
          }
       if (dev_alloc(h, &h->d_psi, psi_doubles)) return 1;
       SN_CUDA(h, cudaMemsetAsync(h->d_psi, 0, (size_t)psi_doubles * sizeof(double), h->stream));
@@ -470,6 +470,9 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          uint16_t* d_hidx;
          if (dev_upload(h, &d_hidx, cp.in_hidx)) return 1;
          cd.in_hidx = d_hidx;
+         uint8_t* d_eidx;
+         if (dev_upload(h, &d_eidx, cp.eidx)) return 1;
+         cd.eidx = d_eidx;
          cd.q_sheared = nullptr;
          h->class_fast[ci] = cp.fast && h->nls == 0 && h->nmat <= 4096 && !h->opts.generic_only;
          if (h->class_fast[ci]) {

@@ -70,8 +70,8 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    const double2 ov = valid ? cl->out_vec[slot] : make_double2(0.0, 0.0);
    const int kfirst = zdir >= 0 ? kp0 : nz - 1 - kp0;
    const int NS = cl->nsteps;
-   constexpr int kstride_psi = DT * PS;
-   double* psi_w = ch->psi + ((((int64_t)gl * npatch + tk.patch) * NS + kp0 + (valid ? lv : 0)) * DT) * PS + t;
+   constexpr int kstride_psi = DT * PSX;
+   double* psi_w = ch->psi + ((((int64_t)gl * npatch + tk.patch) * NS + kp0 + (valid ? lv : 0)) * DT) * PSX + t;
    const int32_t* mats_w = cl->mats_s + ((int64_t)tk.patch * NS + kp0 + (valid ? lv : 0)) * PS + t;
 #pragma unroll
    for (int s = 0; s < FIN; s++) {
@@ -82,7 +82,7 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
       const int pay = src[s] & SRC_PAYLOAD;
       gsrc[s] = ch->psi;
       if (src[s] >= 0 && (src[s] >> SRC_KIND_SHIFT) == SRC_GLOBAL)
-         gsrc[s] += ((((int64_t)gl * npatch + (pay >> 8)) * NS + kp0 + cl->lvl[pay]) * DT) * PS + (pay & (PS - 1));
+         gsrc[s] += ((((int64_t)gl * npatch + (pay >> 8)) * NS + kp0 + cl->lvl[pay]) * DT) * PSX + (pay & (PS - 1));
    }
    int rout[ROUT_MAX];
    int lsb = -1;
@@ -107,7 +107,7 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
       if (kp0 > 0) {
          const double* pz = psi_w - kstride_psi;
 #pragma unroll
-         for (int d = 0; d < DT; d++) psiz[d] = ldcg_f64(pz + d * PS);
+         for (int d = 0; d < DT; d++) psiz[d] = ldcg_f64(pz + d * PSX);
       } else if (EXTRAS) {
          const int face = zdir > 0 ? 0 : 1;
          const bool refl = face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl;
@@ -144,7 +144,7 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
             for (int s = 0; s < FIN; s++)
                if (s == sg) {
 #pragma unroll
-                  for (int d = 0; d < DT; d++) upg[d] = ldcg_f64(gsrc[s] + d * PS);
+                  for (int d = 0; d < DT; d++) upg[d] = ldcg_f64(gsrc[s] + d * PSX);
                }
          }
          const int mat = mat_c;
@@ -183,7 +183,7 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
                } else if (kind == SRC_GLOBAL) {
                   if (s != sg) {
 #pragma unroll
-                     for (int d = 0; d < DT; d++) acc[d] = fma(a[s][d], ldcg_f64(gsrc[s] + d * PS), acc[d]);
+                     for (int d = 0; d < DT; d++) acc[d] = fma(a[s][d], ldcg_f64(gsrc[s] + d * PSX), acc[d]);
                   }
                } else if (EXTRAS) {
                   const int pay = code & SRC_PAYLOAD;
@@ -212,7 +212,7 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
             const double v = acc[d] * inv[d];
             psiz[d] = v;
             rw[d * PS] = v;
-            psi_w[d * PS] = v;
+            psi_w[d * PSX] = v;
             ph = fma(s_w[d], v, ph);
          }
          atomicAdd(phi_g + koff, ph);
@@ -333,11 +333,23 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int TILE_PFD = 3;                 // layers staged ahead
+constexpr int TILE_D = TILE_PFD + 1;        // depth of the shared-memory buffers
+
 template <int DT, bool EXTRAS>
 __global__ void __launch_bounds__(PS, (DT <= 5 ? 2 : 1))
 sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    extern __shared__ double smem[];
-   constexpr int BUF = DT * PS;                       // one ring / halo buffer
+   constexpr int ROW = DT * PSX;                      // one buffer: [DT][256 ring lanes | 32 halo entries]
+   constexpr int D = TILE_D, PFD = TILE_PFD;
    const Task tk = tasks[blockIdx.x];
    const ChunkDev* __restrict__ ch = gp.chunks + tk.chunk;
    const ClassDev* __restrict__ cl = gp.classes + ch->cls;
@@ -357,16 +369,17 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    const int kcnt = min(gp.Kc, nz - kp0);
    const int nsteps = cl->patch_nlev[tk.patch] + kcnt - 1;
 
-   // smem: ring[2][DT][PS] | halo[2][DT][PS] | mux,muy,muz,w [4][DT] | idz[nz] | sigma_t[nmat]
-   double* ring = smem;
-   double* halo = smem + 2 * BUF;
-   double* s_mux = smem + 4 * BUF;
+   // smem: bufs[D][DT][PSX] | q stage [D][PS] | material stage [D][PS] (int) | mux,muy,muz,w | idz[nz] | sigma_t
+   double* bufs = smem;
+   double* s_q = smem + D * ROW;
+   int* s_m = (int*)(s_q + D * PS);
+   double* s_mux = s_q + D * PS + (D * PS) / 2;
    double* s_muy = s_mux + DT;
    double* s_muz = s_muy + DT;
    double* s_w = s_muz + DT;
    double* s_idz = s_w + DT;
    double* s_sigt = s_idz + nz;
-   for (int a = t; a < 4 * BUF; a += PS) smem[a] = 0.0;
+   for (int a = t; a < D * ROW; a += PS) bufs[a] = 0.0;
    for (int kk = t; kk < nz; kk += PS) s_idz[kk] = gp.has_z ? gp.inv_dz[kk] : 0.0;
    for (int m = t; m < gp.nmat; m += PS) s_sigt[m] = gp.sigma_t[m * gp.G + g];
    if (t < DT) {
@@ -377,12 +390,13 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    }
    __syncthreads();
 
-   // per-lane constants: coefficients, outgoing sum, the smem offset of each of the two sources
+   // per-lane constants: coefficients, outgoing sum, the smem column of each of the two sources
    double a0[DT], a1[DT], so[DT];
    int off0 = t, off1 = t;                            // default: own ring entry with a zero coefficient
-   int kind0 = -1, kind1 = -1, hx0 = 0, hx1 = 0;
-   const double* g0 = nullptr;                        // running global pointers of the staged sources
+   int kind0 = -1, kind1 = -1;
+   const double* g0 = nullptr;                        // global rows the staged sources come from
    const double* g1 = nullptr;
+   int rf0 = 0, rf1 = 0, ax0 = 0, ax1 = 0;
    {
       const double2 ov = valid ? cl->out_vec[slot] : make_double2(0.0, 0.0);
       const double2 v0 = valid ? cl->in_vec[slot] : make_double2(0.0, 0.0);
@@ -395,15 +409,16 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
       }
       const int c0 = valid ? cl->in_src[slot] : SRC_NONE;
       const int c1 = valid ? cl->in_src[S + slot] : SRC_NONE;
-      const double* psi_gl = ch->psi + (int64_t)gl * npatch * NS * BUF;
+      const double* psi_gl = ch->psi + (int64_t)gl * npatch * NS * ROW;
       if (c0 >= 0) {
          kind0 = c0 >> SRC_KIND_SHIFT;
          const int pay = c0 & SRC_PAYLOAD;
          if (kind0 == SRC_LOCAL) off0 = pay;
          else {
-            hx0 = cl->in_hidx[slot]; off0 = 2 * BUF + hx0;
+            off0 = PS + cl->in_hidx[slot];
             if (kind0 == SRC_GLOBAL)
-               g0 = psi_gl + (((int64_t)(pay >> 8) * NS + kp0 + cl->lvl[pay]) * DT) * PS + (pay & (PS - 1));
+               g0 = psi_gl + ((int64_t)(pay >> 8) * NS + kp0 + cl->lvl[pay]) * ROW + PS + cl->eidx[pay];
+            else { ax0 = pay >> SRC_AXIS_SHIFT; rf0 = pay & ((1 << SRC_AXIS_SHIFT) - 1); }
          }
       }
       if (c1 >= 0) {
@@ -411,52 +426,59 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
          const int pay = c1 & SRC_PAYLOAD;
          if (kind1 == SRC_LOCAL) off1 = pay;
          else {
-            hx1 = cl->in_hidx[S + slot]; off1 = 2 * BUF + hx1;
+            off1 = PS + cl->in_hidx[S + slot];
             if (kind1 == SRC_GLOBAL)
-               g1 = psi_gl + (((int64_t)(pay >> 8) * NS + kp0 + cl->lvl[pay]) * DT) * PS + (pay & (PS - 1));
+               g1 = psi_gl + ((int64_t)(pay >> 8) * NS + kp0 + cl->lvl[pay]) * ROW + PS + cl->eidx[pay];
+            else { ax1 = pay >> SRC_AXIS_SHIFT; rf1 = pay & ((1 << SRC_AXIS_SHIFT) - 1); }
          }
       }
    }
    const bool staged = valid && (kind0 == SRC_GLOBAL || kind1 == SRC_GLOBAL || kind0 == SRC_REFL || kind1 == SRC_REFL);
+   const int ex = valid ? (int)cl->eidx[slot] : 255;   // my compact edge index, if another patch reads me
    int rout[ROUT_MAX];
    if (EXTRAS) {
 #pragma unroll
       for (int r = 0; r < ROUT_MAX; r++) rout[r] = valid ? cl->rout[(size_t)r * S + slot] : -1;
    }
 
-   const int64_t row0 = ((int64_t)tk.patch * NS + kp0 + lv0) * PS + t;      // (patch, step, lane) offset
-   double* psi_w = ch->psi + (((int64_t)gl * npatch * NS) * DT) * PS + (row0 - t) * DT + t;
-   const int32_t* mats_w = cl->mats_s + row0;
-   const double* q_w = cl->q_sheared + (int64_t)g * npatch * NS * PS + row0;
-   double* ph_w = ch->phi_part + (int64_t)gl * npatch * NS * PS + row0;
+   const int64_t row0 = (int64_t)tk.patch * NS + kp0 + lv0;                 // (patch, step) row
+   double* psi_w = ch->psi + ((int64_t)gl * npatch * NS + row0) * ROW + t;
+   const int32_t* mats_w = cl->mats_s + row0 * PS + t;
+   const double* q_w = cl->q_sheared + ((int64_t)g * npatch * NS + row0) * PS + t;
+   double* ph_w = ch->phi_part + ((int64_t)gl * npatch * NS + row0) * PS + t;
    const int cell = (int)slot;                         // tile classes: class slot == base slot
-   int k = zdir >= 0 ? kp0 : nz - 1 - kp0;
    const int kdir = zdir >= 0 ? 1 : -1;
+   const int kstart = zdir >= 0 ? kp0 : nz - 1 - kp0;
 
-   // stage the halo of one layer: patch-boundary values from the neighbouring patch's psi, mirrored
-   // values from the reflective boundary buffers
-   auto stage = [&](double* dst_buf, int kk, int step_ahead) {
-      if (kind0 == SRC_GLOBAL) {
+   // stage everything layer `kl` of my column needs into buffer kl % D: q, material, and the lateral
+   // values that do not come from a lane of this CTA (neighbouring patch's edge copies, mirrored
+   // directions of a reflective face)
+   auto stage = [&](int kl) {
+      const int b = kl % D;
+      cp_async8(s_q + b * PS + t, q_w + (int64_t)kl * PS);
+      cp_async4(s_m + b * PS + t, mats_w + (int64_t)kl * PS);
+      if (staged) {
+         double* dst = bufs + b * ROW;
+         if (kind0 == SRC_GLOBAL) {
 #pragma unroll
-         for (int d = 0; d < DT; d++) cp_async8(dst_buf + d * PS + hx0, g0 + (int64_t)step_ahead * BUF + d * PS);
-      } else if (EXTRAS && kind0 == SRC_REFL) {
-         const int pay = cl->in_src[slot] & SRC_PAYLOAD;
-         const int axis = pay >> SRC_AXIS_SHIFT, rf = pay & ((1 << SRC_AXIS_SHIFT) - 1);
+            for (int d = 0; d < DT; d++) cp_async8(dst + d * PSX + off0, g0 + (int64_t)kl * ROW + d * PSX);
+         } else if (EXTRAS && kind0 == SRC_REFL) {
+            const int kk = kstart + kl * kdir;
 #pragma unroll
-         for (int d = 0; d < DT; d++)
-            cp_async8(dst_buf + d * PS + hx0,
-                      gp.bnd_old + (((int64_t)ch->mrefl[d][axis] * gp.G + g) * nz + kk) * gp.nrf + rf);
-      }
-      if (kind1 == SRC_GLOBAL) {
+            for (int d = 0; d < DT; d++)
+               cp_async8(dst + d * PSX + off0,
+                         gp.bnd_old + (((int64_t)ch->mrefl[d][ax0] * gp.G + g) * nz + kk) * gp.nrf + rf0);
+         }
+         if (kind1 == SRC_GLOBAL) {
 #pragma unroll
-         for (int d = 0; d < DT; d++) cp_async8(dst_buf + d * PS + hx1, g1 + (int64_t)step_ahead * BUF + d * PS);
-      } else if (EXTRAS && kind1 == SRC_REFL) {
-         const int pay = cl->in_src[S + slot] & SRC_PAYLOAD;
-         const int axis = pay >> SRC_AXIS_SHIFT, rf = pay & ((1 << SRC_AXIS_SHIFT) - 1);
+            for (int d = 0; d < DT; d++) cp_async8(dst + d * PSX + off1, g1 + (int64_t)kl * ROW + d * PSX);
+         } else if (EXTRAS && kind1 == SRC_REFL) {
+            const int kk = kstart + kl * kdir;
 #pragma unroll
-         for (int d = 0; d < DT; d++)
-            cp_async8(dst_buf + d * PS + hx1,
-                      gp.bnd_old + (((int64_t)ch->mrefl[d][axis] * gp.G + g) * nz + kk) * gp.nrf + rf);
+            for (int d = 0; d < DT; d++)
+               cp_async8(dst + d * PSX + off1,
+                         gp.bnd_old + (((int64_t)ch->mrefl[d][ax1] * gp.G + g) * nz + kk) * gp.nrf + rf1);
+         }
       }
    };
 
@@ -467,7 +489,7 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    if (gp.has_z && valid) {
       if (kp0 > 0) {
 #pragma unroll
-         for (int d = 0; d < DT; d++) psiz[d] = ldcg_f64(psi_w - BUF + d * PS);
+         for (int d = 0; d < DT; d++) psiz[d] = ldcg_f64(psi_w - ROW + d * PSX);
       } else if (EXTRAS) {
          const int face = zdir > 0 ? 0 : 1;
          if (face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl) {
@@ -478,41 +500,48 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
       }
    }
 
-   // prime: inputs and halo of my first layer
-   int mat_c = 0;
-   double q_c = 0.0;
-   if (valid) { mat_c = mats_w[0]; q_c = q_w[0]; }
-   if (staged) { stage(halo, k, 0); cp_async_wait_all(); }
-   __syncthreads();
+   // prologue: PFD layers in flight, one cp.async group per layer
+   if (valid) {
+#pragma unroll
+      for (int a = 0; a < PFD; a++) {
+         if (a < kcnt) stage(a);
+         cp_async_commit();
+      }
+   }
 
-   int tog = 0;                                        // 0 / BUF: which of the two buffers my layer uses
+   int b = 0;                                          // buffer of my current layer = kl % D
+   int k = kstart;
    for (int step = 0; step < nsteps; step++) {
       const int kl = step - lv0;
       if (valid && kl >= 0 && kl < kcnt) {
-         const bool more = kl + 1 < kcnt;
-         if (staged && more) stage(halo + (BUF - tog), k + kdir, kl + 1);
-         const int mat = mat_c;
-         const double qv = q_c;
-         if (more) { mat_c = mats_w[PS]; q_c = q_w[PS]; }
+         if (kl + PFD < kcnt) stage(kl + PFD);
+         cp_async_commit();
+         cp_async_wait_group<PFD>();                   // the group of layer kl has landed
+         const int mat = s_m[b * PS + t];
+         const double qv = s_q[b * PS + t];
          const double st = s_sigt[mat];
          const double idz = s_idz[k];
-         const double* r0 = smem + off0 + tog;
-         const double* r1 = smem + off1 + tog;
-         double* rw = ring + tog + t;
+         double* buf = bufs + b * ROW;
+         const double* r0 = buf + off0;
+         const double* r1 = buf + off1;
          double ph = 0.0;
 #pragma unroll
          for (int d = 0; d < DT; d++) {
             const double az = s_muz[d] * idz;
             double acc = fma(az, psiz[d], qv);
-            acc = fma(a0[d], r0[d * PS], acc);
-            acc = fma(a1[d], r1[d * PS], acc);
+            acc = fma(a0[d], r0[d * PSX], acc);
+            acc = fma(a1[d], r1[d * PSX], acc);
             const double v = acc * fast_rcp(st + so[d] + az);
             psiz[d] = v;
-            rw[d * PS] = v;
-            psi_w[d * PS] = v;
+            buf[d * PSX + t] = v;
+            psi_w[d * PSX] = v;
             ph = fma(s_w[d], v, ph);
          }
-         ph_w[0] = ph;
+         if (ex < PEDGE) {
+#pragma unroll
+            for (int d = 0; d < DT; d++) psi_w[d * PSX + (PS - t) + ex] = psiz[d];
+         }
+         ph_w[(int64_t)kl * PS] = ph;
          if (EXTRAS) {
 #pragma unroll
             for (int r = 0; r < ROUT_MAX; r++)
@@ -530,11 +559,9 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
                }
             }
          }
-         tog = BUF - tog;
-         psi_w += BUF;
-         mats_w += PS; q_w += PS; ph_w += PS;
+         b = (b + 1 == D) ? 0 : b + 1;
+         psi_w += ROW;
          k += kdir;
-         if (staged) cp_async_wait_all();
       }
       __syncthreads();
    }
@@ -542,7 +569,8 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
 
 template <int DT>
 static void launch_tile_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, bool extras, cudaStream_t st) {
-   const size_t smem = ((size_t)4 * DT * PS + 4 * DT + gp.nz + gp.nmat) * sizeof(double);
+   const size_t smem = ((size_t)TILE_D * DT * PSX + TILE_D * PS + (TILE_D * PS) / 2 + 4 * DT + gp.nz + gp.nmat) *
+                       sizeof(double);
    if (extras) sn_sweep_tile_kernel<DT, true><<<ntasks, PS, smem, st>>>(gp, d_tasks);
    else        sn_sweep_tile_kernel<DT, false><<<ntasks, PS, smem, st>>>(gp, d_tasks);
 }

@@ -10,14 +10,16 @@ namespace pampa_sn {
 
 // Per ordering class, device pointers into the uploaded plan.
 constexpr int PS = 256;       // patch slots = sweep CTA size
+constexpr int PEDGE = 32;     // compact copies of the lanes other patches read, behind each psi row
+constexpr int PSX = PS + PEDGE;
 
-// psi of a chunk: [owned group][patch][pipeline step][direction][lane].  The pipeline step of
+// psi of a chunk: [owned group][patch][pipeline step][direction][lane | edge copies] (row = PSX).  The pipeline step of
 // (lane, layer) is kp + lvl(lane), kp = position of the layer in sweep order: the lanes of a CTA
 // work on different layers in the same step (wavefront skew), and storing by step instead of by
 // layer makes every CTA-step one contiguous, fully coalesced block of nd x 256 doubles.
 __host__ __device__ inline int64_t psi_index(int gl, int64_t slot, int step, int d, int npatch,
                                              int nsteps, int nd) {
-   return ((((int64_t)gl * npatch + (slot >> 8)) * nsteps + step) * nd + d) * PS + (slot & (PS - 1));
+   return ((((int64_t)gl * npatch + (slot >> 8)) * nsteps + step) * nd + d) * PSX + (slot & (PS - 1));
 }
 
 struct ClassDev {
@@ -38,6 +40,7 @@ struct ClassDev {
    const int32_t* rout;       // [ROUT_MAX][S]
    const int32_t* ls_of;      // [S] index into the LS cell list or -1 (nullptr: no LS)
    const uint16_t* in_hidx;   // [FIN_MAX][S] halo index of patch-boundary / reflective sources
+   const uint8_t* eidx;       // [S] edge index of lanes read by other patches (255: none)
    double* q_sheared;         // [G][npatch][nsteps][PS] source in this class's step-major order
                               // (nullptr: class swept by the generic kernel)
 };
@@ -49,7 +52,7 @@ struct ChunkDev {
    int32_t m[DT_MAX];         // quadrature index
    int32_t mrefl[DT_MAX][3];  // mirrored direction about x, y, z
    double mux[DT_MAX], muy[DT_MAX], muz_abs[DT_MAX], w[DT_MAX];
-   double* psi;               // [Gown][npatch][nsteps][nd][PS]
+   double* psi;               // [Gown][npatch][nsteps][nd][PSX]
    double* phi_part;          // [Gown][npatch][nsteps][PS] sum_d w_d psi_d of this chunk (tile kernel)
 };
 

@@ -68,6 +68,8 @@ struct ClassPlan {
    std::vector<int32_t> rout;           // [ROUT_MAX][S] reflective face id written by this slot
    std::vector<uint16_t> in_hidx;       // [FIN_MAX][S] halo index of a patch-boundary / reflective source
    int max_halo = 0;                    // largest number of such sources in one patch
+   std::vector<uint8_t> eidx;           // [S] compact index of a lane other patches read from (255: none)
+   int max_export = 0;
    bool fast = false;                   // eligible for the staged tile kernel
 };
 
@@ -403,9 +405,25 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
             }
          }
          cp.max_halo = *std::max_element(halo_count.begin(), halo_count.end());
+         // lanes whose flux another patch reads get a compact "edge" index: the tile kernel stores a
+         // contiguous copy of them behind each psi row so that the importing patch reads whole sectors
+         cp.eidx.assign(S, 255);
+         std::vector<char> exported(S, 0);
+         for (int f = 0; f < FIN_MAX; f++)
+            for (int64_t sl = 0; sl < S; sl++) {
+               const int32_t code = cp.in_src[(size_t)f * S + sl];
+               if (code >= 0 && (code >> SRC_KIND_SHIFT) == SRC_GLOBAL) exported[code & SRC_PAYLOAD] = 1;
+            }
+         cp.max_export = 0;
+         for (int p = 0; p < cp.npatch; p++) {
+            int n = 0;
+            for (int l = 0; l < P; l++)
+               if (exported[(int64_t)p * P + l]) { cp.eidx[(int64_t)p * P + l] = (uint8_t)std::min(254, n); n++; }
+            cp.max_export = std::max(cp.max_export, n);
+         }
          // the staged tile kernel: shared tiles, <= 2 incoming faces, double-buffered ring, and a
          // halo that fits the 256-wide staging rows
-         cp.fast = cp.tiles && cp.fin <= 2 && cp.ring == 2 && cp.max_halo <= 256;
+         cp.fast = cp.tiles && cp.fin <= 2 && cp.ring == 2 && cp.max_halo <= 32 && cp.max_export <= 32;
       }
    }
    class_flags.clear();
