@@ -349,6 +349,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       SN_CUDA(h, cudaEventCreate(&h->ev1));
       SN_CUDA(h, configure_sweep_kernels());
       SN_CUDA(h, configure_tile_kernels());
+      SN_CUDA(h, configure_shear_kernels());
 
       const int nr = h->opts.num_ranks, rank = h->opts.rank;
       h->gloc.assign(h->G, -1); h->Gown = 0;
@@ -440,6 +441,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       // classes
       std::vector<ClassDev> cdev(pl.classes.size());
       h->class_fast.assign(pl.classes.size(), 0);
+      int fast_chunk_count[2] = {0, 0};
       h->d_pos_of.assign(pl.classes.size(), nullptr);
       for (size_t ci = 0; ci < pl.classes.size(); ci++) {
          const ClassPlan& cp = pl.classes[ci];
@@ -479,6 +481,12 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
             bool any_owned = false;
             for (size_t c = 0; c < pl.chunks.size(); c++) any_owned |= (pl.chunks[c].cls == (int)ci && chunk_owned[c]);
             if (!any_owned) h->class_fast[ci] = 0;
+         }
+         if (h->class_fast[ci]) {   // the streaming shear kernels take a bounded number per z direction
+            int& cnt = fast_chunk_count[cp.zdir >= 0 ? 0 : 1];
+            int mine = 0;
+            for (size_t c = 0; c < pl.chunks.size(); c++) mine += (pl.chunks[c].cls == (int)ci && chunk_owned[c]);
+            if (cnt + mine > SHEAR_MAX_PER_PASS) h->class_fast[ci] = 0; else cnt += mine;
          }
          if (h->class_fast[ci]) {
             double* d_qs;

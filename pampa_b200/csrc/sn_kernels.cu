@@ -615,34 +615,61 @@ cudaError_t configure_tile_kernels() {
    return cfg_tile<10>();
 }
 
-// q (base layout [g][k][slot]) -> each fast class's step-major copy.  One CTA per (patch, block of
-// KB layers); a thread stages its own column through shared memory so that both the read (one layer
-// row) and the writes (one pipeline-step row) are coalesced.
-constexpr int SHEAR_KB = 16;
+// q (base layout [g][k][slot]) -> each fast class's step-major copy, streamed: one CTA per (patch,
+// group, z direction) walks the pipeline steps in order; a thread keeps the last 32 layers of its own
+// column in a shared-memory ring and writes, for every class, the entry its level selects.  Every
+// global access is a full 2 KB row.
+constexpr int SHEAR_RING = 32;          // >= local levels of a patch (fast classes: <= 32)
+constexpr int SHEAR_MAXC = 32;          // fast classes / chunks per z direction handled per pass
+
+struct ShearSmem {
+   double ring[SHEAR_RING][PS];
+   int lv[SHEAR_MAXC][PS];
+   double* base[SHEAR_MAXC];
+   int nc, maxlev;
+};
+
 __global__ void __launch_bounds__(PS)
 sn_shear_q_kernel(const SweepGlobals gp, const ClassDev* __restrict__ classes,
                   const int32_t* __restrict__ fast_classes, int nfast, int npatch_b) {
-   __shared__ double tile[SHEAR_KB][PS];
+   extern __shared__ __align__(16) unsigned char shear_raw[];
+   ShearSmem& sm = *reinterpret_cast<ShearSmem*>(shear_raw);
    const int t = threadIdx.x;
    const int patch = blockIdx.x % npatch_b;
-   const int k0 = (blockIdx.x / npatch_b) * SHEAR_KB;
-   const int kb = min(SHEAR_KB, gp.nz - k0);
+   const int g = (blockIdx.x / npatch_b) % gp.G;
+   const int zpass = blockIdx.x / (npatch_b * gp.G);            // 0: ascending k, 1: descending k
    const int64_t slot = (int64_t)patch * PS + t;
-   for (int g = 0; g < gp.G; g++) {
-      const double* qg = gp.q + ((int64_t)g * gp.nz + k0) * gp.Sb + slot;
-      for (int kk = 0; kk < kb; kk++) tile[kk][t] = qg[(int64_t)kk * gp.Sb];     // own column only
-      for (int c = 0; c < nfast; c++) {
+   const int nz = gp.nz;
+   if (t == 0) {
+      int nc = 0, maxlev = 1;
+      for (int c = 0; c < nfast && nc < SHEAR_MAXC; c++) {
          const ClassDev* cl = classes + fast_classes[c];
+         if ((cl->zdir >= 0 ? 0 : 1) != zpass) continue;
+         sm.base[nc] = cl->q_sheared + ((int64_t)g * cl->npatch + patch) * cl->nsteps * PS;
+         maxlev = max(maxlev, cl->patch_nlev[patch]);
+         nc++;
+      }
+      sm.nc = nc; sm.maxlev = maxlev;
+   }
+   {
+      int nc = 0;
+      for (int c = 0; c < nfast && nc < SHEAR_MAXC; c++) {
+         const ClassDev* cl = classes + fast_classes[c];
+         if ((cl->zdir >= 0 ? 0 : 1) != zpass) continue;
          const int lv = cl->lvl[slot];
-         const int NS = cl->nsteps;
-         // layers k0 .. k0+kb-1 are the sweep positions kp_lo .. kp_lo+kb-1
-         const int kp_lo = cl->zdir >= 0 ? k0 : gp.nz - k0 - kb;
-         double* out = cl->q_sheared + (((int64_t)g * cl->npatch + patch) * NS + kp_lo) * PS + t;
-         const int nrow = kb + cl->patch_nlev[patch] - 1;
-         for (int r = 0; r < nrow; r++) {              // every lane on the same step-row: coalesced
-            const int a = r - lv;
-            if (lv != LVL_EMPTY && a >= 0 && a < kb) out[(int64_t)r * PS] = tile[cl->zdir >= 0 ? a : kb - 1 - a][t];
-         }
+         sm.lv[nc++][t] = lv == LVL_EMPTY ? (1 << 20) : lv;
+      }
+   }
+   __syncthreads();
+   const int nc = sm.nc;
+   if (nc == 0) return;
+   const double* qg = gp.q + (int64_t)g * nz * gp.Sb + slot;
+   const int nrow = nz + sm.maxlev - 1;
+   for (int s = 0; s < nrow; s++) {
+      if (s < nz) sm.ring[s & (SHEAR_RING - 1)][t] = qg[(int64_t)(zpass == 0 ? s : nz - 1 - s) * gp.Sb];
+      for (int c = 0; c < nc; c++) {
+         const int a = s - sm.lv[c][t];
+         if (a >= 0 && a < nz) sm.base[c][(int64_t)s * PS + t] = sm.ring[a & (SHEAR_RING - 1)][t];
       }
    }
 }
@@ -650,48 +677,82 @@ sn_shear_q_kernel(const SweepGlobals gp, const ClassDev* __restrict__ classes,
 void launch_shear_q(const SweepGlobals& gp, const ClassDev* d_classes, const int32_t* d_fast_classes,
                     int nfast, int npatch_b, cudaStream_t st) {
    if (nfast <= 0) return;
-   const int nkb = (gp.nz + SHEAR_KB - 1) / SHEAR_KB;
-   sn_shear_q_kernel<<<npatch_b * nkb, PS, 0, st>>>(gp, d_classes, d_fast_classes, nfast, npatch_b);
+   sn_shear_q_kernel<<<npatch_b * gp.G * 2, PS, sizeof(ShearSmem), st>>>(gp, d_classes, d_fast_classes, nfast,
+                                                                         npatch_b);
 }
 
-// phi_new[g][k][slot] += sum over the fast chunks of their step-major partial moments.
+// phi_new[g][k][slot] += sum over the fast chunks of their step-major partial moments (streamed the
+// same way: a layer of a column is complete once every class's level has passed it).
 __global__ void __launch_bounds__(PS)
 sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks,
                       const ClassDev* __restrict__ classes, const int32_t* __restrict__ fast_chunks,
                       int nfast, int npatch_b) {
-   __shared__ double tile[SHEAR_KB][PS];
+   extern __shared__ __align__(16) unsigned char shear_raw[];
+   ShearSmem& sm = *reinterpret_cast<ShearSmem*>(shear_raw);
    const int t = threadIdx.x;
    const int patch = blockIdx.x % npatch_b;
-   const int k0 = (blockIdx.x / npatch_b) * SHEAR_KB;
-   const int kb = min(SHEAR_KB, gp.nz - k0);
+   const int g = blockIdx.x / npatch_b;
+   const int gl = gp.gloc[g];
+   if (gl < 0) return;
    const int64_t slot = (int64_t)patch * PS + t;
-   for (int g = 0; g < gp.G; g++) {
-      const int gl = gp.gloc[g];
-      if (gl < 0) continue;
-      for (int kk = 0; kk < kb; kk++) tile[kk][t] = 0.0;
-      for (int c = 0; c < nfast; c++) {
-         const ChunkDev* ch = chunks + fast_chunks[c];
-         const ClassDev* cl = classes + ch->cls;
-         const int lv = cl->lvl[slot];
-         const int NS = cl->nsteps;
-         const int kp_lo = cl->zdir >= 0 ? k0 : gp.nz - k0 - kb;
-         const double* in = ch->phi_part + (((int64_t)gl * cl->npatch + patch) * NS + kp_lo) * PS + t;
-         const int nrow = kb + cl->patch_nlev[patch] - 1;
-         for (int r = 0; r < nrow; r++) {
-            const int a = r - lv;
-            if (lv != LVL_EMPTY && a >= 0 && a < kb) tile[cl->zdir >= 0 ? a : kb - 1 - a][t] += in[(int64_t)r * PS];
+   const int nz = gp.nz;
+   double* pg = gp.phi_new + (int64_t)g * nz * gp.Sb + slot;
+   for (int zpass = 0; zpass < 2; zpass++) {
+      __syncthreads();
+      if (t == 0) {
+         int nc = 0, maxlev = 1;
+         for (int c = 0; c < nfast && nc < SHEAR_MAXC; c++) {
+            const ChunkDev* ch = chunks + fast_chunks[c];
+            const ClassDev* cl = classes + ch->cls;
+            if ((cl->zdir >= 0 ? 0 : 1) != zpass) continue;
+            sm.base[nc] = ch->phi_part + ((int64_t)gl * cl->npatch + patch) * cl->nsteps * PS;
+            maxlev = max(maxlev, cl->patch_nlev[patch]);
+            nc++;
+         }
+         sm.nc = nc; sm.maxlev = maxlev;
+      }
+      {
+         int nc = 0;
+         for (int c = 0; c < nfast && nc < SHEAR_MAXC; c++) {
+            const ClassDev* cl = classes + chunks[fast_chunks[c]].cls;
+            if ((cl->zdir >= 0 ? 0 : 1) != zpass) continue;
+            const int lv = cl->lvl[slot];
+            sm.lv[nc++][t] = lv == LVL_EMPTY ? (1 << 20) : lv;
          }
       }
-      double* pg = gp.phi_new + ((int64_t)g * gp.nz + k0) * gp.Sb + slot;
-      for (int kk = 0; kk < kb; kk++) pg[(int64_t)kk * gp.Sb] += tile[kk][t];
+      for (int r = 0; r < SHEAR_RING; r++) sm.ring[r][t] = 0.0;
+      __syncthreads();
+      const int nc = sm.nc, maxlev = sm.maxlev;
+      if (nc == 0) continue;
+      const int nrow = nz + maxlev - 1;
+      for (int s = 0; s < nrow; s++) {
+         for (int c = 0; c < nc; c++) {
+            const int a = s - sm.lv[c][t];
+            if (a >= 0 && a < nz) sm.ring[a & (SHEAR_RING - 1)][t] += sm.base[c][(int64_t)s * PS + t];
+         }
+         const int ad = s - (maxlev - 1);               // complete for every class and lane
+         if (ad >= 0) {
+            const int k = zpass == 0 ? ad : nz - 1 - ad;
+            pg[(int64_t)k * gp.Sb] += sm.ring[ad & (SHEAR_RING - 1)][t];
+            sm.ring[ad & (SHEAR_RING - 1)][t] = 0.0;
+         }
+      }
    }
 }
 
 void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
                         const int32_t* d_fast_chunks, int nfast, int npatch_b, cudaStream_t st) {
    if (nfast <= 0) return;
-   const int nkb = (gp.nz + SHEAR_KB - 1) / SHEAR_KB;
-   sn_unshear_phi_kernel<<<npatch_b * nkb, PS, 0, st>>>(gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b);
+   sn_unshear_phi_kernel<<<npatch_b * gp.G, PS, sizeof(ShearSmem), st>>>(gp, d_chunks, d_classes, d_fast_chunks,
+                                                                       nfast, npatch_b);
+}
+
+cudaError_t configure_shear_kernels() {
+   cudaError_t e = cudaFuncSetAttribute(sn_shear_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(ShearSmem));
+   if (e != cudaSuccess) return e;
+   return cudaFuncSetAttribute(sn_unshear_phi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(ShearSmem));
 }
 
 // ------------------------------------------------------------------------------------ source

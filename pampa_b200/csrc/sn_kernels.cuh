@@ -94,6 +94,8 @@ void launch_sweep(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int d
                   int ring, bool extras, cudaStream_t st);
 cudaError_t configure_sweep_kernels();
 cudaError_t configure_tile_kernels();
+cudaError_t configure_shear_kernels();
+constexpr int SHEAR_MAX_PER_PASS = 32;   // fast classes / chunks per z direction the shear kernels handle
 void launch_sweep_tile(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras,
                        cudaStream_t st);
 // base [g][k][slot] <-> step-major [g][patch][step][lane] transforms for the tile kernel
