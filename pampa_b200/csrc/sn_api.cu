@@ -531,6 +531,9 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       {
          std::vector<int32_t> fast_classes;
          for (size_t ci = 0; ci < pl.classes.size(); ci++) if (h->class_fast[ci]) fast_classes.push_back((int32_t)ci);
+         // +z chunks first: the un-shear kernel processes one z direction per pass, 8 chunks at a time
+         std::stable_sort(fast_chunks.begin(), fast_chunks.end(), [&](int32_t a, int32_t b) {
+            return (pl.classes[pl.chunks[a].cls].zdir < 0) < (pl.classes[pl.chunks[b].cls].zdir < 0); });
          h->nfast_classes = (int)fast_classes.size(); h->nfast_chunks = (int)fast_chunks.size();
          if (dev_upload(h, &h->d_fast_classes, fast_classes) || dev_upload(h, &h->d_fast_chunks, fast_chunks)) return 1;
       }

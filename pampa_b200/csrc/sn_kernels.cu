@@ -682,13 +682,17 @@ void launch_shear_q(const SweepGlobals& gp, const ClassDev* d_classes, const int
 }
 
 // phi_new[g][k][slot] += sum over the fast chunks of their step-major partial moments (streamed the
-// same way: a layer of a column is complete once every class's level has passed it).
+// same way: a layer of a column is complete once every class's level has passed it).  The chunk rows
+// of two consecutive steps are loaded into registers before the shared-memory accumulation so that
+// 2 x UNSHEAR_NC independent global loads are in flight per thread.
+constexpr int UNSHEAR_NC = 8;
+
 __global__ void __launch_bounds__(PS)
 sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks,
                       const ClassDev* __restrict__ classes, const int32_t* __restrict__ fast_chunks,
                       int nfast, int npatch_b) {
    extern __shared__ __align__(16) unsigned char shear_raw[];
-   ShearSmem& sm = *reinterpret_cast<ShearSmem*>(shear_raw);
+   double (*ring)[PS] = reinterpret_cast<double (*)[PS]>(shear_raw);      // [SHEAR_RING][PS]
    const int t = threadIdx.x;
    const int patch = blockIdx.x % npatch_b;
    const int g = blockIdx.x / npatch_b;
@@ -698,43 +702,52 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
    const int nz = gp.nz;
    double* pg = gp.phi_new + (int64_t)g * nz * gp.Sb + slot;
    for (int zpass = 0; zpass < 2; zpass++) {
-      __syncthreads();
-      if (t == 0) {
-         int nc = 0, maxlev = 1;
-         for (int c = 0; c < nfast && nc < SHEAR_MAXC; c++) {
-            const ChunkDev* ch = chunks + fast_chunks[c];
-            const ClassDev* cl = classes + ch->cls;
-            if ((cl->zdir >= 0 ? 0 : 1) != zpass) continue;
-            sm.base[nc] = ch->phi_part + ((int64_t)gl * cl->npatch + patch) * cl->nsteps * PS;
-            maxlev = max(maxlev, cl->patch_nlev[patch]);
-            nc++;
+      for (int c0 = 0; c0 < nfast; c0 += UNSHEAR_NC) {
+         // up to UNSHEAR_NC chunks of this z direction, starting the search at chunk c0
+         const double* base[UNSHEAR_NC];
+         int lv[UNSHEAR_NC];
+         int maxlev = 1, found = 0;
+#pragma unroll
+         for (int j = 0; j < UNSHEAR_NC; j++) {
+            base[j] = nullptr; lv[j] = 1 << 20;
+            const int c = c0 + j;
+            if (c < nfast) {
+               const ChunkDev* ch = chunks + fast_chunks[c];
+               const ClassDev* cl = classes + ch->cls;
+               if ((cl->zdir >= 0 ? 0 : 1) == zpass) {
+                  const int l = cl->lvl[slot];
+                  lv[j] = l == LVL_EMPTY ? (1 << 20) : l;
+                  base[j] = ch->phi_part + ((int64_t)gl * cl->npatch + patch) * cl->nsteps * PS + t;
+                  maxlev = max(maxlev, cl->patch_nlev[patch]);
+                  found = 1;
+               }
+            }
          }
-         sm.nc = nc; sm.maxlev = maxlev;
-      }
-      {
-         int nc = 0;
-         for (int c = 0; c < nfast && nc < SHEAR_MAXC; c++) {
-            const ClassDev* cl = classes + chunks[fast_chunks[c]].cls;
-            if ((cl->zdir >= 0 ? 0 : 1) != zpass) continue;
-            const int lv = cl->lvl[slot];
-            sm.lv[nc++][t] = lv == LVL_EMPTY ? (1 << 20) : lv;
-         }
-      }
-      for (int r = 0; r < SHEAR_RING; r++) sm.ring[r][t] = 0.0;
-      __syncthreads();
-      const int nc = sm.nc, maxlev = sm.maxlev;
-      if (nc == 0) continue;
-      const int nrow = nz + maxlev - 1;
-      for (int s = 0; s < nrow; s++) {
-         for (int c = 0; c < nc; c++) {
-            const int a = s - sm.lv[c][t];
-            if (a >= 0 && a < nz) sm.ring[a & (SHEAR_RING - 1)][t] += sm.base[c][(int64_t)s * PS + t];
-         }
-         const int ad = s - (maxlev - 1);               // complete for every class and lane
-         if (ad >= 0) {
-            const int k = zpass == 0 ? ad : nz - 1 - ad;
-            pg[(int64_t)k * gp.Sb] += sm.ring[ad & (SHEAR_RING - 1)][t];
-            sm.ring[ad & (SHEAR_RING - 1)][t] = 0.0;
+         if (!found) continue;                            // uniform over the CTA
+         for (int r = 0; r < SHEAR_RING; r++) ring[r][t] = 0.0;
+         const int nrow = nz + maxlev - 1;
+         for (int s = 0; s < nrow; s += 2) {
+            double v0[UNSHEAR_NC], v1[UNSHEAR_NC];
+#pragma unroll
+            for (int j = 0; j < UNSHEAR_NC; j++) {
+               const int a0 = s - lv[j], a1 = s + 1 - lv[j];
+               v0[j] = (a0 >= 0 && a0 < nz) ? base[j][(int64_t)s * PS] : 0.0;
+               v1[j] = (a1 >= 0 && a1 < nz) ? base[j][(int64_t)(s + 1) * PS] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+#pragma unroll
+               for (int j = 0; j < UNSHEAR_NC; j++) {
+                  const int a = s + u - lv[j];
+                  if (a >= 0 && a < nz) ring[a & (SHEAR_RING - 1)][t] += (u == 0 ? v0[j] : v1[j]);
+               }
+               const int ad = s + u - (maxlev - 1);      // complete for every chunk and lane
+               if (ad >= 0 && ad < nz) {
+                  const int k = zpass == 0 ? ad : nz - 1 - ad;
+                  pg[(int64_t)k * gp.Sb] += ring[ad & (SHEAR_RING - 1)][t];
+                  ring[ad & (SHEAR_RING - 1)][t] = 0.0;
+               }
+            }
          }
       }
    }
@@ -743,8 +756,8 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
 void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
                         const int32_t* d_fast_chunks, int nfast, int npatch_b, cudaStream_t st) {
    if (nfast <= 0) return;
-   sn_unshear_phi_kernel<<<npatch_b * gp.G, PS, sizeof(ShearSmem), st>>>(gp, d_chunks, d_classes, d_fast_chunks,
-                                                                       nfast, npatch_b);
+   sn_unshear_phi_kernel<<<npatch_b * gp.G, PS, SHEAR_RING * PS * sizeof(double), st>>>(
+      gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b);
 }
 
 cudaError_t configure_shear_kernels() {

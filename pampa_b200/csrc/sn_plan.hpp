@@ -424,7 +424,7 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
          // the staged tile kernel: shared tiles, <= 2 incoming faces, double-buffered ring, and a
          // halo that fits the 256-wide staging rows
          cp.fast = cp.tiles && cp.fin <= 2 && cp.ring == 2 && cp.max_halo <= 32 && cp.max_export <= 32 &&
-                   *std::max_element(cp.patch_nlev.begin(), cp.patch_nlev.end()) <= 32;
+                   *std::max_element(cp.patch_nlev.begin(), cp.patch_nlev.end()) <= 31;
       }
    }
    class_flags.clear();
