@@ -106,6 +106,7 @@ typedef struct {
    int32_t verbose;
    int32_t dt_max;               /* directions swept together per CTA, 1..10 (0: default) */
    int32_t generic_only;         /* 1: never use the staged tile kernel (A/B testing) */
+   int32_t single_stream;        /* 1: launch all ordering classes on one stream (A/B testing) */
 } pampa_sn_options;
 
 void pampa_sn_default_options(pampa_sn_options* opts);

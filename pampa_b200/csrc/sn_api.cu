@@ -41,7 +41,7 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
 
-struct LaunchGroup { int wave, kind, dt, fin, ring; bool extras; int64_t offset; int count; };
+struct LaunchGroup { int wave, cls, kind, dt, fin, ring; bool extras; int64_t offset; int count; };
 
 }  // namespace
 
@@ -52,6 +52,11 @@ struct pampa_sn_handle {
    int device = 0;
    cudaStream_t stream = nullptr;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   // the ordering classes sweep independently: one stream each, so that the thin first / last
+   // wavefronts of one class overlap the wide ones of another
+   static constexpr int NSTREAMS = 8;
+   cudaStream_t cls_stream[NSTREAMS] = {};
+   cudaEvent_t ev_fork = nullptr, ev_join[NSTREAMS] = {};
    std::vector<void*> allocs;
    int64_t device_bytes = 0;
    int64_t launches = 0;
@@ -83,6 +88,7 @@ struct pampa_sn_handle {
    double *d_ls_coef = nullptr, *d_ls_dD = nullptr, *d_ls_rhs = nullptr;
    std::vector<int> dir_chunk, dir_d;
    bool extras = false;
+   bool multi_stream = false;
    // staged tile kernel
    std::vector<char> class_fast;
    int32_t *d_fast_classes = nullptr, *d_fast_chunks = nullptr;
@@ -203,10 +209,20 @@ int do_sweep(pampa_sn_handle* h) {
       launch_shear_q(gp, h->d_classes, h->d_fast_classes, h->nfast_classes, h->plan.npatch_b, h->stream);
       h->launches++;
    }
+   const int ns = h->multi_stream ? pampa_sn_handle::NSTREAMS : 0;
+   if (ns) {
+      cudaEventRecord(h->ev_fork, h->stream);
+      for (int i = 0; i < ns; i++) cudaStreamWaitEvent(h->cls_stream[i], h->ev_fork, 0);
+   }
    for (const LaunchGroup& lg : h->groups) {
-      if (lg.kind == 1) launch_sweep_tile(gp, h->d_tasks + lg.offset, lg.count, lg.dt, lg.extras, h->stream);
-      else launch_sweep(gp, h->d_tasks + lg.offset, lg.count, lg.dt, lg.fin, lg.ring, lg.extras, h->stream);
+      cudaStream_t st = ns ? h->cls_stream[lg.cls % ns] : h->stream;
+      if (lg.kind == 1) launch_sweep_tile(gp, h->d_tasks + lg.offset, lg.count, lg.dt, lg.extras, st);
+      else launch_sweep(gp, h->d_tasks + lg.offset, lg.count, lg.dt, lg.fin, lg.ring, lg.extras, st);
       h->launches++;
+   }
+   for (int i = 0; i < ns; i++) {
+      cudaEventRecord(h->ev_join[i], h->cls_stream[i]);
+      cudaStreamWaitEvent(h->stream, h->ev_join[i], 0);
    }
    if (h->nfast_chunks > 0) {
       launch_unshear_phi(gp, h->d_chunks, h->d_classes, h->d_fast_chunks, h->nfast_chunks, h->plan.npatch_b,
@@ -347,6 +363,11 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       SN_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
       SN_CUDA(h, cudaEventCreate(&h->ev0));
       SN_CUDA(h, cudaEventCreate(&h->ev1));
+      SN_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      for (int i = 0; i < pampa_sn_handle::NSTREAMS; i++) {
+         SN_CUDA(h, cudaStreamCreateWithFlags(&h->cls_stream[i], cudaStreamNonBlocking));
+         SN_CUDA(h, cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+      }
       SN_CUDA(h, configure_sweep_kernels());
       SN_CUDA(h, configure_tile_kernels());
       SN_CUDA(h, configure_shear_kernels());
@@ -550,7 +571,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          std::vector<Task> tasks = pl.waves[w];
          auto variant = [&](const Task& t) {
             const Chunk& ch = pl.chunks[t.chunk]; const ClassPlan& cp = pl.classes[ch.cls];
-            return std::make_tuple(h->class_fast[ch.cls] ? 1 : 0, dt_template(ch.nd), cp.fin <= 2 ? 2 : FIN_MAX, cp.ring);
+            return std::make_tuple(ch.cls, h->class_fast[ch.cls] ? 1 : 0, dt_template(ch.nd), cp.fin <= 2 ? 2 : FIN_MAX, cp.ring);
          };
          std::stable_sort(tasks.begin(), tasks.end(), [&](const Task& a, const Task& b) { return variant(a) < variant(b); });
          size_t i = 0;
@@ -558,13 +579,16 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
             size_t j = i;
             while (j < tasks.size() && variant(tasks[j]) == variant(tasks[i])) j++;
             auto v = variant(tasks[i]);
-            h->groups.push_back(LaunchGroup{(int)w, std::get<0>(v), std::get<1>(v), std::get<2>(v), std::get<3>(v), h->extras,
+            h->groups.push_back(LaunchGroup{(int)w, std::get<0>(v), std::get<1>(v), std::get<2>(v), std::get<3>(v), std::get<4>(v), h->extras,
                                             (int64_t)all.size() + (int64_t)i, (int)(j - i)});
             i = j;
          }
          all.insert(all.end(), tasks.begin(), tasks.end());
       }
       if (dev_upload(h, &h->d_tasks, all)) return 1;
+      // reflective / LS problems read what another class wrote in the previous sweep only, so classes
+      // stay independent within a sweep; streams are used unless the option turns them off
+      h->multi_stream = pl.classes.size() > 1 && !h->opts.single_stream;
 
       // reduction scratch and iteration state
       h->nblocks_reduce = (int)std::min<int64_t>(((int64_t)nz * Sb + 255) / 256, 148 * 8);
@@ -592,6 +616,11 @@ int pampa_sn_destroy(pampa_sn_handle* h) {
    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
    if (h->stream) cudaStreamSynchronize(h->stream);
    for (void* p : h->allocs) cudaFree(p);
+   for (int i = 0; i < pampa_sn_handle::NSTREAMS; i++) {
+      if (h->cls_stream[i]) { cudaStreamSynchronize(h->cls_stream[i]); cudaStreamDestroy(h->cls_stream[i]); }
+      if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+   }
+   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
    if (h->ev0) cudaEventDestroy(h->ev0);
    if (h->ev1) cudaEventDestroy(h->ev1);
    if (h->stream) cudaStreamDestroy(h->stream);

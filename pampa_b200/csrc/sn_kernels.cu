@@ -345,7 +345,7 @@ constexpr int TILE_PFD = 3;                 // layers staged ahead
 constexpr int TILE_D = TILE_PFD + 1;        // depth of the shared-memory buffers
 
 template <int DT, bool EXTRAS>
-__global__ void __launch_bounds__(PS, (DT <= 5 ? 2 : 1))
+__global__ void __launch_bounds__(PS, (DT <= 8 ? 2 : 1))
 sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    extern __shared__ double smem[];
    constexpr int ROW = DT * PSX;                      // one buffer: [DT][256 ring lanes | 32 halo entries]
