@@ -341,8 +341,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int TILE_PFD = 3;                 // layers staged ahead
-constexpr int TILE_D = TILE_PFD + 1;        // depth of the shared-memory buffers
+constexpr int TILE_PFD = 3;                 // pipeline steps staged ahead
+constexpr int TILE_D = 4;                   // depth of the shared-memory buffers (power of two > PFD)
 
 template <int DT, bool EXTRAS>
 __global__ void __launch_bounds__(PS, (DT <= 8 ? 2 : 1))
@@ -364,20 +364,22 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    const int zdir = cl->zdir;
    const int lv = cl->lvl[slot];
    const bool valid = (lv != LVL_EMPTY);
-   const int lv0 = valid ? lv : 0;
+   const int lv0 = valid ? lv : (1 << 20);            // holes are never active
    const int kp0 = tk.zc * gp.Kc;
    const int kcnt = min(gp.Kc, nz - kp0);
    const int nsteps = cl->patch_nlev[tk.patch] + kcnt - 1;
 
-   // smem: bufs[D][DT][PSX] | q stage [D][PS] | material stage [D][PS] (int) | mux,muy,muz,w | idz[nz] | sigma_t
+   // All shared-memory buffers rotate with the pipeline step (uniform over the CTA): at step s a
+   // lane reads its lateral upwind values from buffer (s-1)&3 -- the ring entry its neighbour
+   // wrote one step earlier, or the halo entry staged PFD steps earlier -- and writes buffer s&3.
+   // smem: bufs[D][DT][PSX] | q stage [D][PS] | material stage [D][PS] (int) | {muz,w}[DT] | mux,muy | idz | sigma_t
    double* bufs = smem;
    double* s_q = smem + D * ROW;
    int* s_m = (int*)(s_q + D * PS);
-   double* s_mux = s_q + D * PS + (D * PS) / 2;
+   double2* s_mw = (double2*)(s_q + D * PS + (D * PS) / 2);
+   double* s_mux = (double*)(s_mw + DT);
    double* s_muy = s_mux + DT;
-   double* s_muz = s_muy + DT;
-   double* s_w = s_muz + DT;
-   double* s_idz = s_w + DT;
+   double* s_idz = s_muy + DT;
    double* s_sigt = s_idz + nz;
    for (int a = t; a < D * ROW; a += PS) bufs[a] = 0.0;
    for (int kk = t; kk < nz; kk += PS) s_idz[kk] = gp.has_z ? gp.inv_dz[kk] : 0.0;
@@ -385,30 +387,29 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    if (t < DT) {
       s_mux[t] = ch->mux[t];
       s_muy[t] = ch->muy[t];
-      s_muz[t] = gp.has_z ? ch->muz_abs[t] : 0.0;
-      s_w[t] = ch->w[t];
+      s_mw[t] = make_double2(gp.has_z ? ch->muz_abs[t] : 0.0, ch->w[t]);
    }
    __syncthreads();
 
-   // per-lane constants: coefficients, outgoing sum, the smem column of each of the two sources
+   // per-lane constants: coefficients, outgoing sum, the buffer column of each of the two sources
    double a0[DT], a1[DT], so[DT];
    int off0 = t, off1 = t;                            // default: own ring entry with a zero coefficient
    int kind0 = -1, kind1 = -1;
-   const double* g0 = nullptr;                        // global rows the staged sources come from
+   const double* g0 = nullptr;                        // global rows the staged sources come from (step 0)
    const double* g1 = nullptr;
    int rf0 = 0, rf1 = 0, ax0 = 0, ax1 = 0;
-   {
-      const double2 ov = valid ? cl->out_vec[slot] : make_double2(0.0, 0.0);
-      const double2 v0 = valid ? cl->in_vec[slot] : make_double2(0.0, 0.0);
-      const double2 v1 = valid ? cl->in_vec[S + slot] : make_double2(0.0, 0.0);
+   if (valid) {
+      const double2 ov = cl->out_vec[slot];
+      const double2 v0 = cl->in_vec[slot];
+      const double2 v1 = cl->in_vec[S + slot];
 #pragma unroll
       for (int d = 0; d < DT; d++) {
          so[d] = s_mux[d] * ov.x + s_muy[d] * ov.y;
          a0[d] = -(s_mux[d] * v0.x + s_muy[d] * v0.y);
          a1[d] = -(s_mux[d] * v1.x + s_muy[d] * v1.y);
       }
-      const int c0 = valid ? cl->in_src[slot] : SRC_NONE;
-      const int c1 = valid ? cl->in_src[S + slot] : SRC_NONE;
+      const int c0 = cl->in_src[slot];
+      const int c1 = cl->in_src[S + slot];
       const double* psi_gl = ch->psi + (int64_t)gl * npatch * NS * ROW;
       if (c0 >= 0) {
          kind0 = c0 >> SRC_KIND_SHIFT;
@@ -417,7 +418,7 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
          else {
             off0 = PS + cl->in_hidx[slot];
             if (kind0 == SRC_GLOBAL)
-               g0 = psi_gl + ((int64_t)(pay >> 8) * NS + kp0 + cl->lvl[pay]) * ROW + PS + cl->eidx[pay];
+               g0 = psi_gl + ((int64_t)(pay >> 8) * NS + kp0 + (int)cl->lvl[pay] - lv0) * ROW + PS + cl->eidx[pay];
             else { ax0 = pay >> SRC_AXIS_SHIFT; rf0 = pay & ((1 << SRC_AXIS_SHIFT) - 1); }
          }
       }
@@ -428,12 +429,15 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
          else {
             off1 = PS + cl->in_hidx[S + slot];
             if (kind1 == SRC_GLOBAL)
-               g1 = psi_gl + ((int64_t)(pay >> 8) * NS + kp0 + cl->lvl[pay]) * ROW + PS + cl->eidx[pay];
+               g1 = psi_gl + ((int64_t)(pay >> 8) * NS + kp0 + (int)cl->lvl[pay] - lv0) * ROW + PS + cl->eidx[pay];
             else { ax1 = pay >> SRC_AXIS_SHIFT; rf1 = pay & ((1 << SRC_AXIS_SHIFT) - 1); }
          }
       }
+   } else {
+#pragma unroll
+      for (int d = 0; d < DT; d++) { so[d] = 0.0; a0[d] = 0.0; a1[d] = 0.0; }
    }
-   const bool staged = valid && (kind0 == SRC_GLOBAL || kind1 == SRC_GLOBAL || kind0 == SRC_REFL || kind1 == SRC_REFL);
+   const bool staged = (kind0 == SRC_GLOBAL || kind1 == SRC_GLOBAL || kind0 == SRC_REFL || kind1 == SRC_REFL);
    const int ex = valid ? (int)cl->eidx[slot] : 255;   // my compact edge index, if another patch reads me
    int rout[ROUT_MAX];
    if (EXTRAS) {
@@ -441,29 +445,30 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
       for (int r = 0; r < ROUT_MAX; r++) rout[r] = valid ? cl->rout[(size_t)r * S + slot] : -1;
    }
 
-   const int64_t row0 = (int64_t)tk.patch * NS + kp0 + lv0;                 // (patch, step) row
-   double* psi_w = ch->psi + ((int64_t)gl * npatch * NS + row0) * ROW + t;
-   const int32_t* mats_w = cl->mats_s + row0 * PS + t;
-   const double* q_w = cl->q_sheared + ((int64_t)g * npatch * NS + row0) * PS + t;
-   double* ph_w = ch->phi_part + ((int64_t)gl * npatch * NS + row0) * PS + t;
+   // global rows of pipeline step 0 of this task; step s is s rows further
+   const int64_t prow = (int64_t)tk.patch * NS + kp0;
+   double* psi_row = ch->psi + ((int64_t)gl * npatch * NS + prow) * ROW + t;
+   const int32_t* m_row = cl->mats_s + prow * PS + t;
+   const double* q_row = cl->q_sheared + ((int64_t)g * npatch * NS + prow) * PS + t;
+   double* ph_row = ch->phi_part + ((int64_t)gl * npatch * NS + prow) * PS + t;
    const int cell = (int)slot;                         // tile classes: class slot == base slot
    const int kdir = zdir >= 0 ? 1 : -1;
    const int kstart = zdir >= 0 ? kp0 : nz - 1 - kp0;
 
-   // stage everything layer `kl` of my column needs into buffer kl % D: q, material, and the lateral
-   // values that do not come from a lane of this CTA (neighbouring patch's edge copies, mirrored
-   // directions of a reflective face)
-   auto stage = [&](int kl) {
-      const int b = kl % D;
-      cp_async8(s_q + b * PS + t, q_w + (int64_t)kl * PS);
-      cp_async4(s_m + b * PS + t, mats_w + (int64_t)kl * PS);
+   // stage what step `st` needs for my column: q, material, and the lateral values that do not come
+   // from a lane of this CTA (neighbouring patch's edge copies, mirrored directions of a reflective face)
+   auto stage = [&](int st) {
+      const int klt = st - lv0;
+      if (klt < 0 || klt >= kcnt) return;
+      cp_async8(s_q + (st & (D - 1)) * PS + t, q_row + (int64_t)st * PS);
+      cp_async4(s_m + (st & (D - 1)) * PS + t, m_row + (int64_t)st * PS);
       if (staged) {
-         double* dst = bufs + b * ROW;
+         double* dst = bufs + ((st - 1) & (D - 1)) * ROW;
          if (kind0 == SRC_GLOBAL) {
 #pragma unroll
-            for (int d = 0; d < DT; d++) cp_async8(dst + d * PSX + off0, g0 + (int64_t)kl * ROW + d * PSX);
+            for (int d = 0; d < DT; d++) cp_async8(dst + d * PSX + off0, g0 + (int64_t)st * ROW + d * PSX);
          } else if (EXTRAS && kind0 == SRC_REFL) {
-            const int kk = kstart + kl * kdir;
+            const int kk = kstart + klt * kdir;
 #pragma unroll
             for (int d = 0; d < DT; d++)
                cp_async8(dst + d * PSX + off0,
@@ -471,9 +476,9 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
          }
          if (kind1 == SRC_GLOBAL) {
 #pragma unroll
-            for (int d = 0; d < DT; d++) cp_async8(dst + d * PSX + off1, g1 + (int64_t)kl * ROW + d * PSX);
+            for (int d = 0; d < DT; d++) cp_async8(dst + d * PSX + off1, g1 + (int64_t)st * ROW + d * PSX);
          } else if (EXTRAS && kind1 == SRC_REFL) {
-            const int kk = kstart + kl * kdir;
+            const int kk = kstart + klt * kdir;
 #pragma unroll
             for (int d = 0; d < DT; d++)
                cp_async8(dst + d * PSX + off1,
@@ -489,7 +494,7 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    if (gp.has_z && valid) {
       if (kp0 > 0) {
 #pragma unroll
-         for (int d = 0; d < DT; d++) psiz[d] = ldcg_f64(psi_w - ROW + d * PSX);
+         for (int d = 0; d < DT; d++) psiz[d] = ldcg_f64(psi_row + (int64_t)(lv0 - 1) * ROW + d * PSX);
       } else if (EXTRAS) {
          const int face = zdir > 0 ? 0 : 1;
          if (face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl) {
@@ -500,48 +505,48 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
       }
    }
 
-   // prologue: PFD layers in flight, one cp.async group per layer
-   if (valid) {
+   // prologue: steps 0 .. PFD-1 in flight, one cp.async group per step
 #pragma unroll
-      for (int a = 0; a < PFD; a++) {
-         if (a < kcnt) stage(a);
-         cp_async_commit();
-      }
+   for (int st = 0; st < PFD; st++) {
+      stage(st);
+      cp_async_commit();
    }
 
-   int b = 0;                                          // buffer of my current layer = kl % D
    int k = kstart;
    for (int step = 0; step < nsteps; step++) {
+      stage(step + PFD);
+      cp_async_commit();
+      cp_async_wait_group<PFD>();                      // the group of this step has landed
       const int kl = step - lv0;
-      if (valid && kl >= 0 && kl < kcnt) {
-         if (kl + PFD < kcnt) stage(kl + PFD);
-         cp_async_commit();
-         cp_async_wait_group<PFD>();                   // the group of layer kl has landed
-         const int mat = s_m[b * PS + t];
-         const double qv = s_q[b * PS + t];
+      if (kl >= 0 && kl < kcnt) {
+         const int mat = s_m[(step & (D - 1)) * PS + t];
+         const double qv = s_q[(step & (D - 1)) * PS + t];
          const double st = s_sigt[mat];
          const double idz = s_idz[k];
-         double* buf = bufs + b * ROW;
-         const double* r0 = buf + off0;
-         const double* r1 = buf + off1;
+         const double* rbuf = bufs + ((step - 1) & (D - 1)) * ROW;
+         double* wbuf = bufs + (step & (D - 1)) * ROW + t;
+         double* pw = psi_row + (int64_t)step * ROW;
+         const double* r0 = rbuf + off0;
+         const double* r1 = rbuf + off1;
          double ph = 0.0;
 #pragma unroll
          for (int d = 0; d < DT; d++) {
-            const double az = s_muz[d] * idz;
+            const double2 mw = s_mw[d];
+            const double az = mw.x * idz;
             double acc = fma(az, psiz[d], qv);
             acc = fma(a0[d], r0[d * PSX], acc);
             acc = fma(a1[d], r1[d * PSX], acc);
             const double v = acc * fast_rcp(st + so[d] + az);
             psiz[d] = v;
-            buf[d * PSX + t] = v;
-            psi_w[d * PSX] = v;
-            ph = fma(s_w[d], v, ph);
+            wbuf[d * PSX] = v;
+            pw[d * PSX] = v;
+            ph = fma(mw.y, v, ph);
          }
          if (ex < PEDGE) {
 #pragma unroll
-            for (int d = 0; d < DT; d++) psi_w[d * PSX + (PS - t) + ex] = psiz[d];
+            for (int d = 0; d < DT; d++) pw[d * PSX + (PS - t) + ex] = psiz[d];
          }
-         ph_w[(int64_t)kl * PS] = ph;
+         ph_row[(int64_t)step * PS] = ph;
          if (EXTRAS) {
 #pragma unroll
             for (int r = 0; r < ROUT_MAX; r++)
@@ -559,8 +564,6 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
                }
             }
          }
-         b = (b + 1 == D) ? 0 : b + 1;
-         psi_w += ROW;
          k += kdir;
       }
       __syncthreads();
@@ -570,7 +573,7 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
 template <int DT>
 static void launch_tile_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, bool extras, cudaStream_t st) {
    const size_t smem = ((size_t)TILE_D * DT * PSX + TILE_D * PS + (TILE_D * PS) / 2 + 4 * DT + gp.nz + gp.nmat) *
-                       sizeof(double);
+                       sizeof(double);   // bufs | q stage | material stage | {muz,w}, mux, muy | idz | sigma_t
    if (extras) sn_sweep_tile_kernel<DT, true><<<ntasks, PS, smem, st>>>(gp, d_tasks);
    else        sn_sweep_tile_kernel<DT, false><<<ntasks, PS, smem, st>>>(gp, d_tasks);
 }
