@@ -156,7 +156,10 @@ def run_b200(a, rank, world, local_rank):
     mesh, xs = syn.checkerboard_core(nx, ny, nz, num_groups=a.groups)
     quad = syn.level_symmetric(a.order)
     M = len(quad.weights)
-    opts = dict(device=local_rank, rank=rank, num_ranks=world)
+    # sharding: by energy group when the groups divide evenly over the ranks (allgather of the group
+    # slabs, sharded source / reduction), else by angle set (allreduce of the flux moments)
+    opts = dict(device=local_rank, rank=rank, num_ranks=world,
+                shard_mode=1 if (world > 1 and a.groups % world == 0) else 0)
     opts.update(json.loads(a.opts))
     dev = pb.SNDevice(mesh, xs, quad, **opts)
     if world > 1:
@@ -249,7 +252,7 @@ def run_b200(a, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(a), "parallelism": "angle-set sharding x%d" % world,
+                "config": {"workload": workload_name(a), "parallelism": "%s sharding x%d" % ("energy-group" if opts["shard_mode"] == 1 else "angle-set", world),
                            "l2_policy": "working set (%.1f GB) far exceeds the 126 MB L2" % (info0["device_bytes"] / 1e9),
                            "keff_after_steps": k, "options": json.loads(a.opts)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,

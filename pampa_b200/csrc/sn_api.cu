@@ -23,6 +23,7 @@ struct NcclApi {
    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
    int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
    int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+   int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
    int (*CommDestroy)(NcclComm) = nullptr;
    const char* (*GetErrorString)(int) = nullptr;
    bool load(std::string& err) {
@@ -32,14 +33,15 @@ struct NcclApi {
       GetUniqueId = (int (*)(NcclUniqueId*))dlsym(lib, "ncclGetUniqueId");
       CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(lib, "ncclCommInitRank");
       AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+      AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(lib, "ncclAllGather");
       CommDestroy = (int (*)(NcclComm))dlsym(lib, "ncclCommDestroy");
       GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
-      if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "incomplete NCCL library"; return false; }
+      if (!GetUniqueId || !CommInitRank || !AllReduce || !AllGather || !CommDestroy) { err = "incomplete NCCL library"; return false; }
       return true;
    }
 };
 NcclApi g_nccl;
-constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MIN = 3;
 
 struct LaunchGroup { int wave, cls, kind, dt, fin, ring; bool extras; int64_t offset; int count; };
 
@@ -73,7 +75,8 @@ struct pampa_sn_handle {
    double *d_bnd[2] = {nullptr, nullptr}, *d_bndz[2] = {nullptr, nullptr};
    int bnd_cur = 0;
    int64_t bnd_count = 0, bndz_count = 0;
-   double *d_partials = nullptr;
+   double *d_partials = nullptr, *d_sums = nullptr;
+   bool group_gather = false;           // group-sharded run with the in-place allgather of phi
    int nblocks_reduce = 0;
    ReduceScalars* d_sc = nullptr;
    ClassDev* d_classes = nullptr;
@@ -186,7 +189,7 @@ int sync_scalars(pampa_sn_handle* h) {
 }
 
 int do_source(pampa_sn_handle* h) {
-   launch_source(h->d_phi, h->d_q, h->d_mats, h->d_sig_s, h->d_chi, h->d_nusf, h->d_sc, h->G,
+   launch_source(h->d_phi, h->d_q, h->d_mats, h->d_sig_s, h->d_chi, h->d_nusf, h->d_sc, h->d_gloc, h->G,
                  h->plan.nz, h->plan.Sb, h->stream);
    h->launches++;
    return 0;
@@ -233,28 +236,56 @@ int do_sweep(pampa_sn_handle* h) {
    return 0;
 }
 
-int do_exchange(pampa_sn_handle* h) {
-   if (!h->comm) return 0;
-   const int64_t n = (int64_t)h->G * h->plan.nz * h->plan.Sb;
-   int r = g_nccl.AllReduce(h->d_phi_new, h->d_phi_new, (size_t)n, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
-   if (r != 0) SN_FAIL(h, std::string("NCCL error in the flux-moment allreduce: ") +
-                          (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
-   // mirrored-direction boundary fluxes may live on another rank
+int nccl_fail(pampa_sn_handle* h, int r, const char* what) {
+   h->err = std::string("NCCL error in ") + what + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+   return 1;
+}
+
+// mirrored-direction boundary fluxes may live on another rank: sum the (zero-filled) buffers
+int exchange_boundaries(pampa_sn_handle* h) {
    double* bufs[2] = {h->d_bnd[h->bnd_cur], h->d_bndz[h->bnd_cur]};
    int64_t cnt[2] = {h->bnd_count, h->bndz_count};
    for (int b = 0; b < 2; b++)
       if (bufs[b] && cnt[b] > 0) {
-         r = g_nccl.AllReduce(bufs[b], bufs[b], (size_t)cnt[b], NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
-         if (r != 0) SN_FAIL(h, "NCCL error in the boundary-flux allreduce");
+         int r = g_nccl.AllReduce(bufs[b], bufs[b], (size_t)cnt[b], NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+         if (r != 0) return nccl_fail(h, r, "the boundary-flux allreduce");
       }
    return 0;
 }
 
+// One exchange + reduction step after a sweep.
+//  * one GPU:            reduce (production, norms, phi <- phi_new), k update.
+//  * angle-set sharding: allreduce(phi_new) over the ranks, then the same on every rank.
+//  * group sharding:     every rank reduces the groups it swept, the five scalars are allreduced,
+//                        and the new phi is completed with an in-place allgather of the group slabs
+//                        (half the wire bytes of the allreduce, and source / reduce are sharded too).
 int do_reduce(pampa_sn_handle* h, int update_k) {
-   launch_reduce(h->d_phi, h->d_phi_new, h->d_mats, h->d_nusf, h->d_kapsf, h->d_area, h->d_dz,
-                 h->plan.has_z, h->G, h->plan.nz, h->plan.Sb, h->d_partials, h->nblocks_reduce, h->d_sc,
-                 update_k, h->stream);
+   const Plan& pl = h->plan;
+   const int64_t slab = (int64_t)pl.nz * pl.Sb;
+   if (h->comm && !h->group_gather) {
+      int r = g_nccl.AllReduce(h->d_phi_new, h->d_phi_new, (size_t)(h->G * slab), NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+      if (r != 0) return nccl_fail(h, r, "the flux-moment allreduce");
+   }
+   if (h->comm && exchange_boundaries(h)) return 1;
+   const int owned_only = (h->comm && h->group_gather) ? 1 : 0;
+   launch_reduce(h->d_phi, h->d_phi_new, h->d_mats, h->d_nusf, h->d_kapsf, h->d_area, h->d_dz, pl.has_z, h->G,
+                 pl.nz, pl.Sb, h->d_gloc, owned_only, h->d_partials, h->nblocks_reduce, h->d_sums, h->stream);
    h->launches += 2;
+   if (owned_only) {
+      int r = g_nccl.AllReduce(h->d_sums, h->d_sums, 4, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+      if (r == 0) r = g_nccl.AllReduce(h->d_sums + 4, h->d_sums + 4, 1, NCCL_FLOAT64, NCCL_MIN, h->comm, h->stream);
+      if (r != 0) return nccl_fail(h, r, "the scalar allreduce");
+   }
+   launch_update_k(h->d_sums, h->d_sc, update_k, h->stream);
+   h->launches++;
+   if (owned_only) {
+      const int nr = h->opts.num_ranks;
+      for (int j = 0; j < h->G / nr; j++) {             // groups j*nr .. j*nr+nr-1: rank r owns j*nr + r
+         double* base = h->d_phi + (int64_t)j * nr * slab;
+         int r = g_nccl.AllGather(base + (int64_t)h->opts.rank * slab, base, (size_t)slab, NCCL_FLOAT64, h->comm, h->stream);
+         if (r != 0) return nccl_fail(h, r, "the flux-moment allgather");
+      }
+   }
    return 0;
 }
 
@@ -592,7 +623,8 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
 
       // reduction scratch and iteration state
       h->nblocks_reduce = (int)std::min<int64_t>(((int64_t)nz * Sb + 255) / 256, 148 * 8);
-      if (dev_alloc(h, &h->d_partials, 5LL * h->nblocks_reduce) || dev_alloc(h, &h->d_sc, 1)) return 1;
+      if (dev_alloc(h, &h->d_partials, 5LL * h->nblocks_reduce) || dev_alloc(h, &h->d_sc, 1) ||
+          dev_alloc(h, &h->d_sums, 8)) return 1;
       ReduceScalars sc0{}; sc0.keff = 1.0;
       SN_CUDA(h, cudaMemcpyAsync(h->d_sc, &sc0, sizeof(sc0), cudaMemcpyHostToDevice, h->stream));
       SN_CUDA(h, cudaMemsetAsync(h->d_phi, 0, (size_t)nphi * sizeof(double), h->stream));
@@ -657,7 +689,6 @@ int pampa_sn_sweep(pampa_sn_handle* h) {
 
 int pampa_sn_reduce(pampa_sn_handle* h, double* production, double* power, double* dphi_rel) {
    SN_CUDA(h, cudaSetDevice(h->device));
-   if (do_exchange(h)) return 1;
    SN_CUDA(h, cudaEventRecord(h->ev0, h->stream));
    if (do_reduce(h, 0)) return 1;
    SN_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -672,7 +703,7 @@ int pampa_sn_reduce(pampa_sn_handle* h, double* production, double* power, doubl
 int pampa_sn_iterate(pampa_sn_handle* h, int32_t iterations, double* keff) {
    SN_CUDA(h, cudaSetDevice(h->device));
    for (int it = 0; it < iterations; it++) {
-      if (do_source(h) || do_sweep(h) || do_exchange(h) || do_reduce(h, 1)) return 1;
+      if (do_source(h) || do_sweep(h) || do_reduce(h, 1)) return 1;
    }
    if (sync_scalars(h)) return 1;
    h->keff = h->sc.keff;
@@ -693,7 +724,6 @@ int pampa_sn_iterate_timed(pampa_sn_handle* h, int32_t iterations, double* keff,
       cudaEventRecord(ev[2 + 2 * it], h->stream);
       if (!rc) rc = do_sweep(h);
       cudaEventRecord(ev[3 + 2 * it], h->stream);
-      if (!rc) rc = do_exchange(h);
       if (!rc) rc = do_reduce(h, 1);
    }
    cudaEventRecord(ev[1], h->stream);
@@ -718,7 +748,7 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
    int it = 0;
    bool converged = false;
    while (it < max_it) {
-      if (do_source(h) || do_sweep(h) || do_exchange(h) || do_reduce(h, 1)) return 1;
+      if (do_source(h) || do_sweep(h) || do_reduce(h, 1)) return 1;
       it++;
       if (sync_scalars(h)) return 1;
       const double dphi = h->sc.phi2 > 0 ? std::sqrt(h->sc.dphi2 / h->sc.phi2) : 0.0;
@@ -847,6 +877,7 @@ int pampa_sn_comm_init(pampa_sn_handle* h, const void* id, int32_t id_bytes) {
    std::memcpy(&uid, id, sizeof(uid));
    int r = g_nccl.CommInitRank(&h->comm, h->opts.num_ranks, uid, h->opts.rank);
    if (r != 0) SN_FAIL(h, std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+   h->group_gather = h->opts.shard_mode == 1 && h->G % h->opts.num_ranks == 0;
    return 0;
 }
 

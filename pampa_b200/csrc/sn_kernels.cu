@@ -643,6 +643,7 @@ sn_shear_q_kernel(const SweepGlobals gp, const ClassDev* __restrict__ classes,
    const int zpass = blockIdx.x / (npatch_b * gp.G);            // 0: ascending k, 1: descending k
    const int64_t slot = (int64_t)patch * PS + t;
    const int nz = gp.nz;
+   if (gp.gloc[g] < 0) return;                                   // not swept by this rank
    if (t == 0) {
       int nc = 0, maxlev = 1;
       for (int c = 0; c < nfast && nc < SHEAR_MAXC; c++) {
@@ -777,7 +778,7 @@ __global__ void __launch_bounds__(256)
 sn_source_kernel(const double* __restrict__ phi, double* __restrict__ q,
                  const int32_t* __restrict__ mats, const double* __restrict__ sig_s,
                  const double* __restrict__ chi, const double* __restrict__ nusf,
-                 const ReduceScalars* __restrict__ sc, int G, int64_t n) {
+                 const ReduceScalars* __restrict__ sc, const int32_t* __restrict__ gloc, int G, int64_t n) {
    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (idx >= n) return;
    const int mat = mats[idx];
@@ -788,6 +789,7 @@ sn_source_kernel(const double* __restrict__ phi, double* __restrict__ q,
    fis *= ik;
    const double* ss = sig_s + (size_t)mat * G * G;
    for (int g = 0; g < G; g++) {
+      if (gloc[g] < 0) continue;                       // group-sharded run: another rank sweeps this group
       double acc = chi[mat * G + g] * fis;
       for (int g2 = 0; g2 < G; g2++) acc = fma(ss[g2 * G + g], phi[(int64_t)g2 * n + idx], acc);
       q[(int64_t)g * n + idx] = acc;
@@ -795,11 +797,11 @@ sn_source_kernel(const double* __restrict__ phi, double* __restrict__ q,
 }
 
 void launch_source(const double* phi, double* q, const int32_t* mats, const double* sig_s,
-                   const double* chi, const double* nusf, const ReduceScalars* sc, int G, int nz,
-                   int64_t Sb, cudaStream_t st) {
+                   const double* chi, const double* nusf, const ReduceScalars* sc, const int32_t* gloc,
+                   int G, int nz, int64_t Sb, cudaStream_t st) {
    const int64_t n = (int64_t)nz * Sb;
    const int nb = (int)((n + 255) / 256);
-   sn_source_kernel<<<nb, 256, 0, st>>>(phi, q, mats, sig_s, chi, nusf, sc, G, n);
+   sn_source_kernel<<<nb, 256, 0, st>>>(phi, q, mats, sig_s, chi, nusf, sc, gloc, G, n);
 }
 
 // ------------------------------------------------------------------------------------ reduce
@@ -810,7 +812,7 @@ sn_reduce_kernel(double* __restrict__ phi, double* __restrict__ phi_new,
                  const int32_t* __restrict__ mats, const double* __restrict__ nusf,
                  const double* __restrict__ kapsf, const double* __restrict__ area,
                  const double* __restrict__ dz, int has_z, int G, int nz, int64_t Sb,
-                 double* __restrict__ partials) {
+                 const int32_t* __restrict__ gloc, int owned_only, double* __restrict__ partials) {
    const int64_t n = (int64_t)nz * Sb;
    double prod = 0.0, pow_ = 0.0, d2 = 0.0, p2 = 0.0, mn = 1.0e300;
    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
@@ -820,6 +822,7 @@ sn_reduce_kernel(double* __restrict__ phi, double* __restrict__ phi_new,
       const int k = (int)(idx / Sb);
       const double vol = area[idx - (int64_t)k * Sb] * (has_z ? dz[k] : 1.0);
       for (int g = 0; g < G; g++) {
+         if (owned_only && gloc[g] < 0) continue;
          const int64_t a = (int64_t)g * n + idx;
          const double pn = phi_new[a], po = phi[a];
          phi[a] = pn;
@@ -846,9 +849,9 @@ sn_reduce_kernel(double* __restrict__ phi, double* __restrict__ phi_new,
       for (int j = 0; j < 5; j++) partials[(size_t)j * gridDim.x + blockIdx.x] = sh[j][0];
 }
 
-// Deterministic final sum + power-iteration update k <- k * P_new / P_old.
-__global__ void sn_reduce_final_kernel(const double* __restrict__ partials, int nblocks,
-                                       ReduceScalars* sc, int update_k) {
+// Deterministic final sum of the block partials into sums[5] = {production, power, ||dphi||^2,
+// ||phi||^2, min phi}; group-sharded runs allreduce sums before the k update.
+__global__ void sn_reduce_final_kernel(const double* __restrict__ partials, int nblocks, double* sums) {
    __shared__ double sh[5][256];
    double v[5] = {0, 0, 0, 0, 1.0e300};
    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
@@ -864,28 +867,35 @@ __global__ void sn_reduce_final_kernel(const double* __restrict__ partials, int 
       }
       __syncthreads();
    }
-   if (threadIdx.x == 0) {
-      const double pnew = sh[0][0];
-      if (update_k && sc->production > 0.0) {
-         const double knew = sc->keff * pnew / sc->production;
-         sc->dk = knew - sc->keff;
-         sc->keff = knew;
-      }
-      sc->production = pnew;
-      sc->power = sh[1][0];
-      sc->dphi2 = sh[2][0];
-      sc->phi2 = sh[3][0];
-      sc->min_phi = sh[4][0];
+   if (threadIdx.x < 5) sums[threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// Power-iteration update k <- k * P_new / P_old.
+__global__ void sn_update_k_kernel(const double* __restrict__ sums, ReduceScalars* sc, int update_k) {
+   const double pnew = sums[0];
+   if (update_k && sc->production > 0.0) {
+      const double knew = sc->keff * pnew / sc->production;
+      sc->dk = knew - sc->keff;
+      sc->keff = knew;
    }
+   sc->production = pnew;
+   sc->power = sums[1];
+   sc->dphi2 = sums[2];
+   sc->phi2 = sums[3];
+   sc->min_phi = sums[4];
 }
 
 void launch_reduce(double* phi, double* phi_new, const int32_t* mats, const double* nusf,
                    const double* kapsf, const double* area, const double* dz, int has_z, int G,
-                   int nz, int64_t Sb, double* partials, int nblocks, ReduceScalars* sc,
-                   int update_k, cudaStream_t st) {
+                   int nz, int64_t Sb, const int32_t* gloc, int owned_only, double* partials, int nblocks,
+                   double* sums, cudaStream_t st) {
    sn_reduce_kernel<<<nblocks, 256, 0, st>>>(phi, phi_new, mats, nusf, kapsf, area, dz, has_z, G,
-                                             nz, Sb, partials);
-   sn_reduce_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, sc, update_k);
+                                             nz, Sb, gloc, owned_only, partials);
+   sn_reduce_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, sums);
+}
+
+void launch_update_k(const double* sums, ReduceScalars* sc, int update_k, cudaStream_t st) {
+   sn_update_k_kernel<<<1, 1, 0, st>>>(sums, sc, update_k);
 }
 
 // ------------------------------------------------------------------------------------ LS term

@@ -105,13 +105,14 @@ void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const 
                         const int32_t* d_fast_chunks, int nfast, int npatch_b, cudaStream_t st);
 
 void launch_source(const double* phi, double* q, const int32_t* mats, const double* sig_s,
-                   const double* chi, const double* nusf, const ReduceScalars* sc, int G, int nz,
-                   int64_t Sb, cudaStream_t st);
+                   const double* chi, const double* nusf, const ReduceScalars* sc, const int32_t* gloc,
+                   int G, int nz, int64_t Sb, cudaStream_t st);
 
 void launch_reduce(double* phi, double* phi_new, const int32_t* mats, const double* nusf,
                    const double* kapsf, const double* area, const double* dz, int has_z, int G,
-                   int nz, int64_t Sb, double* partials, int nblocks, ReduceScalars* sc,
-                   int update_k, cudaStream_t st);
+                   int nz, int64_t Sb, const int32_t* gloc, int owned_only, double* partials, int nblocks,
+                   double* sums, cudaStream_t st);
+void launch_update_k(const double* sums, ReduceScalars* sc, int update_k, cudaStream_t st);
 
 void launch_ls_rhs(const SweepGlobals& gp, const int32_t* ls_ptr, const int32_t* ls_nbr_slot,
                    const double* ls_coef, int64_t nnz, const int32_t* dir_chunk,

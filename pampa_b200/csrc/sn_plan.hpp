@@ -449,6 +449,12 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
    int Kc = pl.nz;
    if (in.opts.z_chunk > 0) Kc = std::min(pl.nz, in.opts.z_chunk);
    else if (pl.has_z && pl.tile_classes < (int)pl.classes.size()) Kc = std::min(pl.nz, 32);
+   else if (pl.has_z && in.opts.num_ranks > 2) {
+      // sharded over many GPUs a rank owns too few sweeps to fill its SMs wavefront by wavefront:
+      // pipeline in z as well (tasks x nzc, critical path ~ (patch levels + nzc) x (levels + nz/nzc))
+      const int nzc = std::min(4, in.opts.num_ranks / 2);
+      if (pl.nz / nzc >= 32) Kc = (pl.nz + nzc - 1) / nzc;
+   }
    pl.Kc = Kc; pl.nzc = (pl.nz + Kc - 1) / Kc;
 
    const int rank = in.opts.rank, nr = std::max(1, in.opts.num_ranks);
