@@ -211,7 +211,8 @@ def run_b200(a, rank, world, local_rank):
         if per_update:
             traffic = per_update * U_own / max(1, info0["sweep_launches"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "sn_sweep_kernel", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "sn_sweep_tile_kernel (sweep time includes sn_shear_q / sn_unshear_phi)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_update": b_alg, "launches_per_step": info0["sweep_launches"],
                 "algorithmic_bytes_per_launch": b_alg * U_own / max(1, info0["sweep_launches"]),
                 "sweep_ms_per_step": sweep_ms / a.steps}
