@@ -107,6 +107,8 @@ typedef struct {
    int32_t dt_max;               /* directions swept together per CTA, 1..10 (0: default) */
    int32_t generic_only;         /* 1: never use the staged tile kernel (A/B testing) */
    int32_t single_stream;        /* 1: launch all ordering classes on one stream (A/B testing) */
+   int32_t anderson_depth;       /* Anderson acceleration of the k-eff iteration: history depth 1..7
+                                    (0: default 4, < 0: plain power iteration) */
 } pampa_sn_options;
 
 void pampa_sn_default_options(pampa_sn_options* opts);
@@ -126,7 +128,8 @@ int pampa_sn_source(pampa_sn_handle* h, double keff);
 int pampa_sn_sweep(pampa_sn_handle* h);
 int pampa_sn_reduce(pampa_sn_handle* h, double* production, double* power, double* dphi_rel);
 
-/* Power iteration to |dk| < tol_k and ||dphi||_2/||phi||_2 < tol_phi (or max_it). */
+/* k-eigenvalue solve: source iterations (Anderson-accelerated by default) until |dk| < tol_k and the
+ * relative L2 change of the flux moments over one source iteration is < tol_phi (or max_it). */
 int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_t max_it,
                         double power, double* keff, int32_t* iterations);
 

@@ -76,6 +76,12 @@ struct pampa_sn_handle {
    int bnd_cur = 0;
    int64_t bnd_count = 0, bndz_count = 0;
    double *d_partials = nullptr, *d_sums = nullptr;
+   // Anderson acceleration state (allocated by the first accelerated solve)
+   double* aa_f[AA_SLOTS] = {};
+   double* aa_g[AA_SLOTS] = {};
+   double *d_aa_partials = nullptr, *d_aa_dots = nullptr;
+   int aa_slots = 0;
+   double psi_scale_factor = 1.0;       // psi normalisation relative to phi (1 unless accelerated)
    bool group_gather = false;           // group-sharded run with the in-place allgather of phi
    int nblocks_reduce = 0;
    ReduceScalars* d_sc = nullptr;
@@ -259,7 +265,8 @@ int exchange_boundaries(pampa_sn_handle* h) {
 //  * group sharding:     every rank reduces the groups it swept, the five scalars are allreduced,
 //                        and the new phi is completed with an in-place allgather of the group slabs
 //                        (half the wire bytes of the allreduce, and source / reduce are sharded too).
-int do_reduce(pampa_sn_handle* h, int update_k) {
+// exchange (sharded runs) + block reduction of the sweep result into d_sums[5]
+int reduce_sums(pampa_sn_handle* h, int rotate) {
    const Plan& pl = h->plan;
    const int64_t slab = (int64_t)pl.nz * pl.Sb;
    if (h->comm && !h->group_gather) {
@@ -269,24 +276,40 @@ int do_reduce(pampa_sn_handle* h, int update_k) {
    if (h->comm && exchange_boundaries(h)) return 1;
    const int owned_only = (h->comm && h->group_gather) ? 1 : 0;
    launch_reduce(h->d_phi, h->d_phi_new, h->d_mats, h->d_nusf, h->d_kapsf, h->d_area, h->d_dz, pl.has_z, h->G,
-                 pl.nz, pl.Sb, h->d_gloc, owned_only, h->d_partials, h->nblocks_reduce, h->d_sums, h->stream);
+                 pl.nz, pl.Sb, h->d_gloc, owned_only, rotate, h->d_partials, h->nblocks_reduce, h->d_sums, h->stream);
    h->launches += 2;
    if (owned_only) {
       int r = g_nccl.AllReduce(h->d_sums, h->d_sums, 4, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
       if (r == 0) r = g_nccl.AllReduce(h->d_sums + 4, h->d_sums + 4, 1, NCCL_FLOAT64, NCCL_MIN, h->comm, h->stream);
       if (r != 0) return nccl_fail(h, r, "the scalar allreduce");
    }
-   launch_update_k(h->d_sums, h->d_sc, update_k, h->stream);
-   h->launches++;
-   if (owned_only) {
-      const int nr = h->opts.num_ranks;
-      for (int j = 0; j < h->G / nr; j++) {             // groups j*nr .. j*nr+nr-1: rank r owns j*nr + r
-         double* base = h->d_phi + (int64_t)j * nr * slab;
-         int r = g_nccl.AllGather(base + (int64_t)h->opts.rank * slab, base, (size_t)slab, NCCL_FLOAT64, h->comm, h->stream);
-         if (r != 0) return nccl_fail(h, r, "the flux-moment allgather");
-      }
+   return 0;
+}
+
+// group-sharded runs: complete phi with an in-place allgather of the group slabs
+int gather_phi(pampa_sn_handle* h) {
+   if (!(h->comm && h->group_gather)) return 0;
+   const int64_t slab = (int64_t)h->plan.nz * h->plan.Sb;
+   const int nr = h->opts.num_ranks;
+   for (int j = 0; j < h->G / nr; j++) {                // groups j*nr .. j*nr+nr-1: rank r owns j*nr + r
+      double* base = h->d_phi + (int64_t)j * nr * slab;
+      int r = g_nccl.AllGather(base + (int64_t)h->opts.rank * slab, base, (size_t)slab, NCCL_FLOAT64, h->comm, h->stream);
+      if (r != 0) return nccl_fail(h, r, "the flux-moment allgather");
    }
    return 0;
+}
+
+// One exchange + reduction step after a sweep.
+//  * one GPU:            reduce (production, norms, phi <- phi_new), k update.
+//  * angle-set sharding: allreduce(phi_new) over the ranks, then the same on every rank.
+//  * group sharding:     every rank reduces the groups it swept, the five scalars are allreduced,
+//                        and the new phi is completed with an in-place allgather of the group slabs
+//                        (half the wire bytes of the allreduce, and source / reduce are sharded too).
+int do_reduce(pampa_sn_handle* h, int update_k) {
+   if (reduce_sums(h, 1)) return 1;
+   launch_update_k(h->d_sums, h->d_sc, update_k, h->stream);
+   h->launches++;
+   return gather_phi(h);
 }
 
 int check_async(pampa_sn_handle* h, const char* what) {
@@ -742,27 +765,146 @@ int pampa_sn_iterate_timed(pampa_sn_handle* h, int32_t iterations, double* keff,
    return check_async(h, "the source iteration");
 }
 
+// Solve min ||sum_j alpha_j f_j|| subject to sum alpha = 1 over the `n` history slots in `idx`
+// (Gram matrix M of the residuals); false when the system is too ill-conditioned.
+static bool aa_weights(const double M[AA_SLOTS][AA_SLOTS], const int* idx, int n, double* alpha) {
+   double A[AA_SLOTS][AA_SLOTS + 1];
+   double dmax = 0.0;
+   for (int i = 0; i < n; i++) dmax = std::max(dmax, M[idx[i]][idx[i]]);
+   if (!(dmax > 0.0)) return false;
+   for (int i = 0; i < n; i++) {
+      for (int j = 0; j < n; j++) A[i][j] = M[idx[i]][idx[j]] / dmax + (i == j ? 1.0e-13 : 0.0);
+      A[i][n] = 1.0;
+   }
+   for (int c = 0; c < n; c++) {                        // Gaussian elimination with partial pivoting
+      int p = c;
+      for (int r = c + 1; r < n; r++) if (std::fabs(A[r][c]) > std::fabs(A[p][c])) p = r;
+      if (std::fabs(A[p][c]) < 1.0e-300) return false;
+      for (int j = 0; j <= n; j++) std::swap(A[c][j], A[p][j]);
+      for (int r = 0; r < n; r++) {
+         if (r == c) continue;
+         const double m = A[r][c] / A[c][c];
+         for (int j = c; j <= n; j++) A[r][j] -= m * A[c][j];
+      }
+   }
+   double sum = 0.0;
+   for (int i = 0; i < n; i++) { alpha[i] = A[i][n] / A[i][i]; sum += alpha[i]; }
+   if (!(std::fabs(sum) > 1.0e-300)) return false;
+   double amax = 0.0;
+   for (int i = 0; i < n; i++) { alpha[i] /= sum; amax = std::max(amax, std::fabs(alpha[i])); }
+   return amax == amax && amax < 1.0e4;
+}
+
 int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_t max_it, double power,
                         double* keff, int32_t* iterations) {
    SN_CUDA(h, cudaSetDevice(h->device));
+   const Plan& pl = h->plan;
+   const int64_t nslab = (int64_t)pl.nz * pl.Sb, nphi = h->G * nslab;
+   int depth = h->opts.anderson_depth == 0 ? 4 : h->opts.anderson_depth;     // < 0: plain power iteration
+   depth = std::min(depth, AA_SLOTS - 1);
    int it = 0;
    bool converged = false;
-   while (it < max_it) {
-      if (do_source(h) || do_sweep(h) || do_reduce(h, 1)) return 1;
-      it++;
+   h->psi_scale_factor = 1.0;
+   double power_integral = 0.0, min_phi = 0.0;
+
+   if (depth < 1) {
+      while (it < max_it) {
+         if (do_source(h) || do_sweep(h) || do_reduce(h, 1)) return 1;
+         it++;
+         if (sync_scalars(h)) return 1;
+         const double dphi = h->sc.phi2 > 0 ? std::sqrt(h->sc.dphi2 / h->sc.phi2) : 0.0;
+         if (!(h->sc.keff == h->sc.keff)) SN_FAIL(h, "the power iteration diverged (NaN)");
+         if (it > 1 && std::fabs(h->sc.dk) < tol_k && dphi < tol_phi) { converged = true; break; }
+      }
+      power_integral = h->sc.power; min_phi = h->sc.min_phi;
+   } else {
+      // Anderson-accelerated fixed-point iteration on x = phi (unit production) and k
+      const int slots = depth + 1;
+      if (h->aa_slots < slots) {
+         for (int j = h->aa_slots; j < slots; j++)
+            if (dev_alloc(h, &h->aa_f[j], nphi) || dev_alloc(h, &h->aa_g[j], nphi)) return 1;
+         if (!h->d_aa_partials && (dev_alloc(h, &h->d_aa_partials, (int64_t)AA_SLOTS * h->nblocks_reduce) ||
+                                   dev_alloc(h, &h->d_aa_dots, AA_SLOTS))) return 1;
+         h->aa_slots = slots;
+      }
+      const int owned_only = (h->comm && h->group_gather) ? 1 : 0;
+      double M[AA_SLOTS][AA_SLOTS] = {};
+      double kg[AA_SLOTS] = {};
+      int age[AA_SLOTS];                                // iteration that filled each slot (-1: empty)
+      for (int j = 0; j < AA_SLOTS; j++) age[j] = -1;
       if (sync_scalars(h)) return 1;
-      const double dphi = h->sc.phi2 > 0 ? std::sqrt(h->sc.dphi2 / h->sc.phi2) : 0.0;
-      if (!(h->sc.keff == h->sc.keff)) SN_FAIL(h, "the power iteration diverged (NaN)");
-      if (it > 1 && std::fabs(h->sc.dk) < tol_k && dphi < tol_phi) { converged = true; break; }
+      double kn = h->sc.keff;
+      const double prod_x = h->sc.production;           // production of the iterate, kept constant
+      if (!(prod_x > 0.0)) SN_FAIL(h, "zero fission production: no fissile material in the mesh");
+      double best = 1.0e300;
+      int cur = 0;
+      while (it < max_it) {
+         if (do_source(h) || do_sweep(h) || reduce_sums(h, 0)) return 1;
+         it++;
+         double sums[5];
+         SN_CUDA(h, cudaMemcpyAsync(sums, h->d_sums, sizeof(sums), cudaMemcpyDeviceToHost, h->stream));
+         SN_CUDA(h, cudaStreamSynchronize(h->stream));
+         if (!(sums[0] == sums[0]) || !(sums[0] > 0.0)) SN_FAIL(h, "the power iteration diverged");
+         const double inv = prod_x / sums[0];
+         kg[cur] = kn * sums[0] / prod_x;
+         age[cur] = it;
+         int nh = 0;
+         for (int j = 0; j < slots; j++) nh += age[j] >= 0;
+         // history slots are packed in [0, slots): the kernel visits every slot < slots that is filled
+         double* fptr[AA_SLOTS]; double* gptr[AA_SLOTS];
+         for (int j = 0; j < AA_SLOTS; j++) { fptr[j] = h->aa_f[j < slots ? j : 0]; gptr[j] = h->aa_g[j < slots ? j : 0]; }
+         int nvisit = 0;
+         for (int j = 0; j < slots; j++) if (age[j] >= 0) nvisit = j + 1;
+         launch_aa_store(h->d_phi, h->d_phi_new, h->d_mats, h->d_gloc, owned_only, h->G, nslab, inv, fptr, gptr, cur,
+                         nvisit, h->d_aa_partials, h->nblocks_reduce, h->d_aa_dots, h->stream);
+         h->launches += 2;
+         if (owned_only) {
+            int r = g_nccl.AllReduce(h->d_aa_dots, h->d_aa_dots, AA_SLOTS, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+            if (r != 0) return nccl_fail(h, r, "the Anderson allreduce");
+         }
+         double dots[AA_SLOTS];
+         SN_CUDA(h, cudaMemcpyAsync(dots, h->d_aa_dots, sizeof(dots), cudaMemcpyDeviceToHost, h->stream));
+         SN_CUDA(h, cudaStreamSynchronize(h->stream));
+         for (int j = 0; j < nvisit; j++) M[cur][j] = M[j][cur] = dots[j];
+         const double res = std::sqrt(dots[cur] / (sums[3] * inv * inv));
+         const double dk = kg[cur] - kn;
+         power_integral = sums[1] * inv; min_phi = sums[4] * inv;
+         h->psi_scale_factor = inv;
+         double alpha[AA_SLOTS] = {};
+         double mix[AA_SLOTS] = {};
+         if (it > 1 && std::fabs(dk) < tol_k && res < tol_phi) {
+            converged = true;
+            mix[cur] = 1.0; kn = kg[cur];
+         } else {
+            if (res > 10.0 * best) { for (int j = 0; j < slots; j++) if (j != cur) age[j] = -1; }   // restart
+            best = std::min(best, res);
+            // window = filled slots, newest first; shrink it until the weights are well conditioned
+            int idx[AA_SLOTS], n = 0;
+            for (int a = 0; a < slots; a++) { int j = (cur - a + slots) % slots; if (age[j] >= 0) idx[n++] = j; }
+            while (n > 1 && !aa_weights(M, idx, n, alpha)) n--;
+            if (n <= 1) { n = 1; alpha[0] = 1.0; }
+            kn = 0.0;
+            for (int a = 0; a < n; a++) { mix[idx[a]] = alpha[a]; kn += alpha[a] * kg[idx[a]]; }
+         }
+         launch_aa_mix(h->d_phi, h->d_mats, h->d_gloc, owned_only, h->G, nslab, fptr, gptr, mix, slots,
+                       h->nblocks_reduce, h->stream);
+         h->launches++;
+         SN_CUDA(h, cudaMemcpyAsync(&h->d_sc->keff, &kn, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+         if (gather_phi(h)) return 1;
+         if (converged) break;
+         cur = (cur + 1) % slots;
+      }
+      SN_CUDA(h, cudaStreamSynchronize(h->stream));
+      h->sc.keff = kn;
    }
    if (check_async(h, "the k-eff iteration")) return 1;
    h->keff = h->sc.keff;
    if (keff) *keff = h->sc.keff;
    if (iterations) *iterations = it;
-   if (h->sc.power == 0.0) SN_FAIL(h, "zero fission power: no fissile material in the mesh");
-   h->scale = power / h->sc.power;
+   if (power_integral == 0.0) SN_FAIL(h, "zero fission power: no fissile material in the mesh");
+   h->scale = power / power_integral;
    h->solved = true;
-   if (h->sc.min_phi * h->scale < 0.0) SN_FAIL(h, "negative values in the scalar-flux solution");
+   if (min_phi * h->scale < 0.0) SN_FAIL(h, "negative values in the scalar-flux solution");
    if (!converged) SN_FAIL(h, "the power iteration did not converge in " + std::to_string(max_it) + " iterations");
    return 0;
 }
@@ -827,7 +969,8 @@ int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
          cudaMemcpyAsync(&cd, h->d_chunks + c, sizeof(ChunkDev), cudaMemcpyDeviceToHost, h->stream);
          cudaStreamSynchronize(h->stream);
          launch_export_psi(cd.psi, h->d_classes + ch.cls, h->d_pos_of[ch.cls], h->d_slot_of_xy, h->dir_d[m],
-                           ch.nd, m, h->d_gloc, h->scale, h->G, h->M, pl.nz, pl.nxy, d_out, d_min, h->stream);
+                           ch.nd, m, h->d_gloc, h->scale * h->psi_scale_factor, h->G, h->M, pl.nz, pl.nxy, d_out, d_min,
+                           h->stream);
       }
       double mn = 0.0;
       cudaMemcpyAsync(&mn, d_min, sizeof(double), cudaMemcpyDeviceToHost, h->stream);

@@ -812,7 +812,7 @@ sn_reduce_kernel(double* __restrict__ phi, double* __restrict__ phi_new,
                  const int32_t* __restrict__ mats, const double* __restrict__ nusf,
                  const double* __restrict__ kapsf, const double* __restrict__ area,
                  const double* __restrict__ dz, int has_z, int G, int nz, int64_t Sb,
-                 const int32_t* __restrict__ gloc, int owned_only, double* __restrict__ partials) {
+                 const int32_t* __restrict__ gloc, int owned_only, int rotate, double* __restrict__ partials) {
    const int64_t n = (int64_t)nz * Sb;
    double prod = 0.0, pow_ = 0.0, d2 = 0.0, p2 = 0.0, mn = 1.0e300;
    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
@@ -825,8 +825,7 @@ sn_reduce_kernel(double* __restrict__ phi, double* __restrict__ phi_new,
          if (owned_only && gloc[g] < 0) continue;
          const int64_t a = (int64_t)g * n + idx;
          const double pn = phi_new[a], po = phi[a];
-         phi[a] = pn;
-         phi_new[a] = 0.0;
+         if (rotate) { phi[a] = pn; phi_new[a] = 0.0; }
          prod = fma(vol * nusf[mat * G + g], pn, prod);
          pow_ = fma(vol * kapsf[mat * G + g], pn, pow_);
          d2 = fma(pn - po, pn - po, d2);
@@ -887,15 +886,115 @@ __global__ void sn_update_k_kernel(const double* __restrict__ sums, ReduceScalar
 
 void launch_reduce(double* phi, double* phi_new, const int32_t* mats, const double* nusf,
                    const double* kapsf, const double* area, const double* dz, int has_z, int G,
-                   int nz, int64_t Sb, const int32_t* gloc, int owned_only, double* partials, int nblocks,
-                   double* sums, cudaStream_t st) {
+                   int nz, int64_t Sb, const int32_t* gloc, int owned_only, int rotate, double* partials,
+                   int nblocks, double* sums, cudaStream_t st) {
    sn_reduce_kernel<<<nblocks, 256, 0, st>>>(phi, phi_new, mats, nusf, kapsf, area, dz, has_z, G,
-                                             nz, Sb, gloc, owned_only, partials);
+                                             nz, Sb, gloc, owned_only, rotate, partials);
    sn_reduce_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, sums);
 }
 
 void launch_update_k(const double* sums, ReduceScalars* sc, int update_k, cudaStream_t st) {
    sn_update_k_kernel<<<1, 1, 0, st>>>(sums, sc, update_k);
+}
+
+// ------------------------------------------------------------------------------------ Anderson
+// Anderson acceleration of the fixed-point map x -> G(x) = A(k) x / P(A(k) x) (one source iteration,
+// normalised to unit production).  History slot `cur` receives g = G(x) and the residual f = g - x;
+// the dot products of the new residual with every stored residual go to partials.
+constexpr int AA_MAX = 8;
+struct AAHist { double* f[AA_MAX]; double* g[AA_MAX]; };
+
+__global__ void __launch_bounds__(256)
+sn_aa_store_kernel(const double* __restrict__ phi, double* __restrict__ phi_new, const int32_t* __restrict__ mats,
+                   const int32_t* __restrict__ gloc, int owned_only, int G, int64_t n, double inv_prod,
+                   AAHist hist, int cur, int nhist, double* __restrict__ partials) {
+   double dots[AA_MAX];
+#pragma unroll
+   for (int j = 0; j < AA_MAX; j++) dots[j] = 0.0;
+   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+        idx += (int64_t)gridDim.x * blockDim.x) {
+      if (mats[idx] < 0) continue;
+      for (int g = 0; g < G; g++) {
+         if (owned_only && gloc[g] < 0) continue;
+         const int64_t a = (int64_t)g * n + idx;
+         const double xg = phi_new[a] * inv_prod;
+         const double f = xg - phi[a];
+         phi_new[a] = 0.0;
+         hist.g[cur][a] = xg;
+         hist.f[cur][a] = f;
+#pragma unroll
+         for (int j = 0; j < AA_MAX; j++)
+            if (j < nhist) dots[j] = fma(f, j == cur ? f : hist.f[j][a], dots[j]);
+      }
+   }
+   __shared__ double sh[256];
+   for (int j = 0; j < nhist; j++) {
+      sh[threadIdx.x] = dots[j];
+      __syncthreads();
+      for (int off = 128; off > 0; off >>= 1) {
+         if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+         __syncthreads();
+      }
+      if (threadIdx.x == 0) partials[(size_t)j * gridDim.x + blockIdx.x] = sh[0];
+      __syncthreads();
+   }
+}
+
+__global__ void sn_aa_dots_final_kernel(const double* __restrict__ partials, int nblocks, int nhist, double* out) {
+   __shared__ double sh[256];
+   for (int j = 0; j < nhist; j++) {
+      double v = 0.0;
+      for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += partials[(size_t)j * nblocks + b];
+      sh[threadIdx.x] = v;
+      __syncthreads();
+      for (int off = 128; off > 0; off >>= 1) {
+         if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+         __syncthreads();
+      }
+      if (threadIdx.x == 0) out[j] = sh[0];
+      __syncthreads();
+   }
+}
+
+struct AACoef { double alpha[AA_MAX]; };
+
+// x_next = sum_j alpha_j g_j  (sum alpha = 1, so the production of x_next is 1)
+__global__ void __launch_bounds__(256)
+sn_aa_mix_kernel(double* __restrict__ phi, const int32_t* __restrict__ mats, const int32_t* __restrict__ gloc,
+                 int owned_only, int G, int64_t n, AAHist hist, AACoef coef, int nhist) {
+   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+        idx += (int64_t)gridDim.x * blockDim.x) {
+      if (mats[idx] < 0) continue;
+      for (int g = 0; g < G; g++) {
+         if (owned_only && gloc[g] < 0) continue;
+         const int64_t a = (int64_t)g * n + idx;
+         double v = 0.0;
+#pragma unroll
+         for (int j = 0; j < AA_MAX; j++)
+            if (j < nhist && coef.alpha[j] != 0.0) v = fma(coef.alpha[j], hist.g[j][a], v);
+         phi[a] = v;
+      }
+   }
+}
+
+void launch_aa_store(const double* phi, double* phi_new, const int32_t* mats, const int32_t* gloc,
+                     int owned_only, int G, int64_t n, double inv_prod, double* const* hist_f,
+                     double* const* hist_g, int cur, int nhist, double* partials, int nblocks, double* dots,
+                     cudaStream_t st) {
+   AAHist h{};
+   for (int j = 0; j < AA_MAX; j++) { h.f[j] = hist_f[j]; h.g[j] = hist_g[j]; }
+   sn_aa_store_kernel<<<nblocks, 256, 0, st>>>(phi, phi_new, mats, gloc, owned_only, G, n, inv_prod, h, cur, nhist,
+                                               partials);
+   sn_aa_dots_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, nhist, dots);
+}
+
+void launch_aa_mix(double* phi, const int32_t* mats, const int32_t* gloc, int owned_only, int G, int64_t n,
+                   double* const* hist_f, double* const* hist_g, const double* alpha, int nhist, int nblocks,
+                   cudaStream_t st) {
+   AAHist h{};
+   AACoef c{};
+   for (int j = 0; j < AA_MAX; j++) { h.f[j] = hist_f[j]; h.g[j] = hist_g[j]; c.alpha[j] = j < nhist ? alpha[j] : 0.0; }
+   sn_aa_mix_kernel<<<nblocks, 256, 0, st>>>(phi, mats, gloc, owned_only, G, n, h, c, nhist);
 }
 
 // ------------------------------------------------------------------------------------ LS term

@@ -110,8 +110,17 @@ void launch_source(const double* phi, double* q, const int32_t* mats, const doub
 
 void launch_reduce(double* phi, double* phi_new, const int32_t* mats, const double* nusf,
                    const double* kapsf, const double* area, const double* dz, int has_z, int G,
-                   int nz, int64_t Sb, const int32_t* gloc, int owned_only, double* partials, int nblocks,
-                   double* sums, cudaStream_t st);
+                   int nz, int64_t Sb, const int32_t* gloc, int owned_only, int rotate, double* partials,
+                   int nblocks, double* sums, cudaStream_t st);
+// Anderson acceleration (history of up to 8 iterates, see sn_api.cu: pampa_sn_solve_keff)
+constexpr int AA_SLOTS = 8;
+void launch_aa_store(const double* phi, double* phi_new, const int32_t* mats, const int32_t* gloc,
+                     int owned_only, int G, int64_t n, double inv_prod, double* const* hist_f,
+                     double* const* hist_g, int cur, int nhist, double* partials, int nblocks, double* dots,
+                     cudaStream_t st);
+void launch_aa_mix(double* phi, const int32_t* mats, const int32_t* gloc, int owned_only, int G, int64_t n,
+                   double* const* hist_f, double* const* hist_g, const double* alpha, int nhist, int nblocks,
+                   cudaStream_t st);
 void launch_update_k(const double* sums, ReduceScalars* sc, int update_k, cudaStream_t st);
 
 void launch_ls_rhs(const SweepGlobals& gp, const int32_t* ls_ptr, const int32_t* ls_nbr_slot,

@@ -168,3 +168,18 @@ def test_errors_are_loud():
     with pytest.raises(pb.SNError):
         dev.solve_keff(max_it=5)
     dev.close()
+
+
+def test_anderson_matches_plain_power_iteration():
+    """The accelerated solve converges to the same eigenpair as the plain power iteration, faster."""
+    em, xs, quad, ls, z = util.load_golden("pwr_cartesian_s2_lsoff")
+    plain = pb.SNDevice(em, xs, quad, ls, anderson_depth=-1)
+    k0, it0 = plain.solve_keff(tol_k=1e-11, tol_phi=1e-9, max_it=20000)
+    acc = pb.SNDevice(em, xs, quad, ls)
+    k1, it1 = acc.solve_keff(tol_k=1e-11, tol_phi=1e-9, max_it=20000)
+    assert abs(k0 - k1) < 1e-8 and abs(k1 - float(z["keff"])) < TOL_K
+    assert util.rel_l2(acc.get("scalar-flux"), plain.get("scalar-flux")) < 1e-6
+    assert util.rel_l2(acc.get("angular-flux"), plain.get("angular-flux")) < 1e-6
+    assert it1 < it0, (it1, it0)
+    print("iterations: plain %d, Anderson %d" % (it0, it1))
+    plain.close(); acc.close()
