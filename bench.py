@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--cpu-scale", type=int, default=2, help="CPU sample: mesh edge divided by this")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--opts", default="{}", help="JSON of pampa_sn_options overrides")
     return ap.parse_args()
 
@@ -223,14 +224,16 @@ def run_b200(a, rank, world, local_rank):
     if not a.no_e2e:
         n_phi = mesh.num_cells * a.groups
         host_in = torch.empty(n_phi, dtype=torch.float64, pin_memory=True).numpy()
+        host_phi = torch.empty(n_phi, dtype=torch.float64, pin_memory=True).numpy()
+        host_pow = torch.empty(mesh.num_cells, dtype=torch.float64, pin_memory=True).numpy()
         host_in[:] = 1.0
         barrier()
         t0 = time.perf_counter()
         dev.update_xs(xs)
         dev.set("flux-moments", host_in)
         dev.iterate(a.steps)
-        phi_out = dev.get("scalar-flux")
-        pow_out = dev.get("power")
+        phi_out = dev.get("scalar-flux", out=host_phi)
+        pow_out = dev.get("power", out=host_pow)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if dist is not None:
@@ -244,6 +247,17 @@ def run_b200(a, rank, world, local_rank):
                "d2h_bytes_per_step": (phi_out.nbytes + pow_out.nbytes) / a.steps,
                "call": "update_xs + set(flux-moments) + %d source iterations + get(scalar-flux, power)" % a.steps}
 
+    # the other half of the headline metric: wall time of a full k-eff solve (Anderson-accelerated
+    # source iteration to |dk| < 1e-7 and a relative flux change < 1e-7)
+    keff_solve = None
+    if not a.no_solve:
+        dev.set("flux-moments", np.ones(mesh.num_cells * a.groups))
+        barrier()
+        t0 = time.perf_counter()
+        ks, its = dev.solve_keff(tol_k=1e-7, tol_phi=1e-7, max_it=20000)
+        torch.cuda.synchronize()
+        keff_solve = {"wall_s": time.perf_counter() - t0, "iterations": its, "keff": ks, "tol_k": 1e-7, "tol_phi": 1e-7}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         v, ms, threads, sample = cpu_time_steps(a, max(a.cpu_scale, 2), 2, 1)
@@ -256,7 +270,8 @@ def run_b200(a, rank, world, local_rank):
                 "config": {"workload": workload_name(a), "parallelism": "%s sharding x%d" % ("energy-group" if opts["shard_mode"] == 1 else "angle-set", world),
                            "l2_policy": "working set (%.1f GB) far exceeds the 126 MB L2" % (info0["device_bytes"] / 1e9),
                            "keff_after_steps": k, "options": json.loads(a.opts)},
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "keff_solve": keff_solve,
+                "gpu_launches": launches,
                 "clocks": clocks}
         print(json.dumps(line), flush=True)
     dev.close()

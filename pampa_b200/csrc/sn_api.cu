@@ -82,6 +82,8 @@ struct pampa_sn_handle {
    double *d_aa_partials = nullptr, *d_aa_dots = nullptr;
    int aa_slots = 0;
    double psi_scale_factor = 1.0;       // psi normalisation relative to phi (1 unless accelerated)
+   double* d_stage = nullptr;           // device staging buffer of the field import / export calls
+   int64_t stage_count = 0;
    bool group_gather = false;           // group-sharded run with the in-place allgather of phi
    int nblocks_reduce = 0;
    ReduceScalars* d_sc = nullptr;
@@ -671,6 +673,7 @@ int pampa_sn_destroy(pampa_sn_handle* h) {
    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
    if (h->stream) cudaStreamSynchronize(h->stream);
    for (void* p : h->allocs) cudaFree(p);
+   if (h->d_stage) cudaFree(h->d_stage);
    for (int i = 0; i < pampa_sn_handle::NSTREAMS; i++) {
       if (h->cls_stream[i]) { cudaStreamSynchronize(h->cls_stream[i]); cudaStreamDestroy(h->cls_stream[i]); }
       if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
@@ -942,8 +945,19 @@ int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
       for (int64_t i = 0; i < N; i++) out[i] = (int64_t)v.size() == N ? v[i] : 0.0;
       return 0;
    }
+   // staging buffer: kept between calls up to 256 M doubles (2 GB), temporary above that
    double* d_out = nullptr;
-   SN_CUDA(h, cudaMalloc(&d_out, (size_t)count * sizeof(double)));
+   bool temp = false;
+   if (count <= h->stage_count) d_out = h->d_stage;
+   else if (count <= (int64_t)1 << 28) {
+      if (h->d_stage) cudaFree(h->d_stage);
+      h->d_stage = nullptr; h->stage_count = 0;
+      SN_CUDA(h, cudaMalloc(&h->d_stage, (size_t)count * sizeof(double)));
+      h->stage_count = count; d_out = h->d_stage;
+   } else {
+      SN_CUDA(h, cudaMalloc(&d_out, (size_t)count * sizeof(double)));
+      temp = true;
+   }
    int rc = 0;
    if (s == "scalar-flux") {
       launch_export_phi(h->d_phi, h->d_slot_of_xy, h->scale, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
@@ -978,9 +992,9 @@ int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
       cudaFree(d_min);
       if (mn < 0.0) { h->err = "negative values in the angular-flux solution"; rc = 1; }
    }
-   cudaError_t e = cudaStreamSynchronize(h->stream);
-   if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost);
-   cudaFree(d_out);
+   cudaError_t e = cudaMemcpyAsync(out, d_out, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+   if (temp) cudaFree(d_out);
    if (e != cudaSuccess) SN_FAIL(h, std::string("CUDA error exporting field: ") + cudaGetErrorString(e));
    return rc;
 }
@@ -993,14 +1007,18 @@ int pampa_sn_set(pampa_sn_handle* h, const char* name, const double* in) {
    if (s == "flux-moments") {      // iteration state / initial guess, layout [i][g]
       SN_CUDA(h, cudaSetDevice(h->device));
       const int64_t count = N * h->G;
-      double* d_in = nullptr;
-      SN_CUDA(h, cudaMalloc(&d_in, (size_t)count * sizeof(double)));
-      cudaMemcpy(d_in, in, (size_t)count * sizeof(double), cudaMemcpyHostToDevice);
+      if (count > h->stage_count) {
+         if (h->d_stage) cudaFree(h->d_stage);
+         h->d_stage = nullptr; h->stage_count = 0;
+         SN_CUDA(h, cudaMalloc(&h->d_stage, (size_t)count * sizeof(double)));
+         h->stage_count = count;
+      }
+      double* d_in = h->d_stage;
+      cudaMemcpyAsync(d_in, in, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->stream);
       cudaMemsetAsync(h->d_phi, 0, (size_t)h->G * h->plan.nz * h->plan.Sb * sizeof(double), h->stream);
       launch_import_phi(h->d_phi_new, h->d_slot_of_xy, h->G, h->plan.nz, h->plan.nxy, h->plan.Sb, d_in, h->stream);
       do_reduce(h, 0);
       int rc = sync_scalars(h);
-      cudaFree(d_in);
       return rc ? 1 : check_async(h, "field import");
    }
    SN_FAIL(h, "unable to find field '" + s + "'");

@@ -244,13 +244,17 @@ class SNDevice:
         self._check(self.lib.pampa_sn_solve_keff(self.h, tol_k, tol_phi, max_it, power, C.byref(k), C.byref(it)))
         return k.value, it.value
 
-    def get(self, name: str) -> np.ndarray:
+    def get(self, name: str, out: np.ndarray | None = None) -> np.ndarray:
+        """Field in the reference layout; `out` may be a caller-owned (e.g. pinned) float64 buffer."""
         n = self.lib.pampa_sn_field_size(self.h, name.encode())
         if n < 0:
             raise SNError("unable to find field '%s'" % name)
-        out = np.empty(n, dtype=np.float64)
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        elif out.dtype != np.float64 or out.size < n or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 buffer of at least %d elements" % n)
         self._check(self.lib.pampa_sn_get(self.h, name.encode(), out.ctypes.data_as(_lib.p_f64)))
-        return out
+        return out[:n]
 
     def set(self, name: str, values):
         v = _f64(values)
