@@ -108,7 +108,7 @@ typedef struct {
    int32_t generic_only;         /* 1: never use the staged tile kernel (A/B testing) */
    int32_t single_stream;        /* 1: launch all ordering classes on one stream (A/B testing) */
    int32_t anderson_depth;       /* Anderson acceleration of the k-eff iteration: history depth 1..7
-                                    (0: default 4, < 0: plain power iteration) */
+                                    (0: default 7, < 0: plain power iteration) */
 } pampa_sn_options;
 
 void pampa_sn_default_options(pampa_sn_options* opts);

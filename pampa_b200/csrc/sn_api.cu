@@ -803,7 +803,7 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
    SN_CUDA(h, cudaSetDevice(h->device));
    const Plan& pl = h->plan;
    const int64_t nslab = (int64_t)pl.nz * pl.Sb, nphi = h->G * nslab;
-   int depth = h->opts.anderson_depth == 0 ? 4 : h->opts.anderson_depth;     // < 0: plain power iteration
+   int depth = h->opts.anderson_depth == 0 ? AA_SLOTS - 1 : h->opts.anderson_depth;     // < 0: plain power iteration
    depth = std::min(depth, AA_SLOTS - 1);
    int it = 0;
    bool converged = false;
@@ -841,9 +841,14 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
       if (!(prod_x > 0.0)) SN_FAIL(h, "zero fission production: no fissile material in the mesh");
       double best = 1.0e300;
       int cur = 0;
+      // the first iterations only settle k and the gross flux shape: mixing them in slows the
+      // acceleration down, so the history starts after `aa_start` plain steps
+      const char* env_start = std::getenv("PAMPA_SN_AA_START");
+      const int aa_start = env_start ? std::atoi(env_start) : 0;   // measured: no benefit at depth 7
       while (it < max_it) {
          if (do_source(h) || do_sweep(h) || reduce_sums(h, 0)) return 1;
          it++;
+         if (it == aa_start) { for (int j = 0; j < slots; j++) if (j != cur) age[j] = -1; best = 1.0e300; }
          double sums[5];
          SN_CUDA(h, cudaMemcpyAsync(sums, h->d_sums, sizeof(sums), cudaMemcpyDeviceToHost, h->stream));
          SN_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -884,6 +889,7 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
             // window = filled slots, newest first; shrink it until the weights are well conditioned
             int idx[AA_SLOTS], n = 0;
             for (int a = 0; a < slots; a++) { int j = (cur - a + slots) % slots; if (age[j] >= 0) idx[n++] = j; }
+            if (it < aa_start) n = 1;                     // plain step
             while (n > 1 && !aa_weights(M, idx, n, alpha)) n--;
             if (n <= 1) { n = 1; alpha[0] = 1.0; }
             kn = 0.0;

@@ -9,9 +9,14 @@ ap.add_argument("--order", type=int, default=8)
 ap.add_argument("--tol", type=float, default=1e-7)
 ap.add_argument("--max-it", type=int, default=5000)
 ap.add_argument("--opts", default="{}")
+ap.add_argument("--pre", type=int, default=0, help="plain iterations before resetting the flux (perturbs the initial k)")
 a = ap.parse_args()
 mesh, xs = syn.checkerboard_core(*a.n, num_groups=a.groups)
 dev = pb.SNDevice(mesh, xs, syn.level_symmetric(a.order), **json.loads(a.opts))
+if a.pre > 0:
+    dev.iterate(a.pre)
+    import numpy as np
+    dev.set("flux-moments", np.ones(mesh.num_cells * a.groups))
 t0 = time.time()
 try:
     k, it = dev.solve_keff(tol_k=a.tol, tol_phi=a.tol, max_it=a.max_it)
