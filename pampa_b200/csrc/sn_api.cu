@@ -130,9 +130,11 @@ struct pampa_sn_handle {
       gp.bcz_minus_refl = bcz_refl[0]; gp.bcz_plus_refl = bcz_refl[1];
       gp.store_psi = 1;
       gp.nmat = nmat;
+      gp.uniform_dz = uniform_dz;
       return gp;
    }
    int bcz_refl[2] = {0, 0};
+   int uniform_dz = 1;
 };
 
 #define SN_FAIL(h, msg) do { (h)->err = (msg); return 1; } while (0)
@@ -445,6 +447,8 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          if (pl.has_z) { dz[k] = mesh->dz[k]; idz[k] = 1.0 / mesh->dz[k]; }
          for (int c = 0; c < pl.nxy; c++) mats[(size_t)k * Sb + pl.slot_of_xy[c]] = mesh->materials[(size_t)k * pl.nxy + c];
       }
+      h->uniform_dz = 1;
+      for (int k = 1; k < nz; k++) if (pl.has_z && mesh->dz[k] != mesh->dz[0]) h->uniform_dz = 0;
       if (dev_upload(h, &h->d_slot_of_xy, pl.slot_of_xy) || dev_upload(h, &h->d_mats, mats) ||
           dev_upload(h, &h->d_area, area) || dev_upload(h, &h->d_dz, dz) || dev_upload(h, &h->d_inv_dz, idz) ||
           dev_upload(h, &h->d_gloc, h->gloc)) return 1;

@@ -344,7 +344,9 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 constexpr int TILE_PFD = 3;                 // pipeline steps staged ahead
 constexpr int TILE_D = 4;                   // depth of the shared-memory buffers (power of two > PFD)
 
-template <int DT, bool EXTRAS>
+// UNIFORM_DZ: all layers have the same thickness, so 1/(sigma_t + outflow) of a lane depends on the
+// material only and is kept in a two-entry per-lane cache (reactor cores are piecewise constant in z).
+template <int DT, bool EXTRAS, bool UNIFORM_DZ>
 __global__ void __launch_bounds__(PS, (DT <= 8 ? 2 : 1))
 sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    extern __shared__ double smem[];
@@ -387,7 +389,8 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    if (t < DT) {
       s_mux[t] = ch->mux[t];
       s_muy[t] = ch->muy[t];
-      s_mw[t] = make_double2(gp.has_z ? ch->muz_abs[t] : 0.0, ch->w[t]);
+      // UNIFORM_DZ: .x holds |mu_z|/dz directly
+      s_mw[t] = make_double2(gp.has_z ? ch->muz_abs[t] * (UNIFORM_DZ ? gp.inv_dz[0] : 1.0) : 0.0, ch->w[t]);
    }
    __syncthreads();
 
@@ -513,6 +516,9 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    }
 
    int k = kstart;
+   int tagA = -1, tagB = -1;                           // materials of the two cached reciprocal sets
+   bool lastA = false;
+   double invA[UNIFORM_DZ ? DT : 1], invB[UNIFORM_DZ ? DT : 1];
    for (int step = 0; step < nsteps; step++) {
       stage(step + PFD);
       cp_async_commit();
@@ -521,26 +527,55 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
       if (kl >= 0 && kl < kcnt) {
          const int mat = s_m[(step & (D - 1)) * PS + t];
          const double qv = s_q[(step & (D - 1)) * PS + t];
-         const double st = s_sigt[mat];
-         const double idz = s_idz[k];
          const double* rbuf = bufs + ((step - 1) & (D - 1)) * ROW;
          double* wbuf = bufs + (step & (D - 1)) * ROW + t;
          double* pw = psi_row + (int64_t)step * ROW;
          const double* r0 = rbuf + off0;
          const double* r1 = rbuf + off1;
          double ph = 0.0;
+         if (UNIFORM_DZ) {
+            if (mat != tagA && mat != tagB) {           // miss: rare once both materials of a column are seen
+               const double st = s_sigt[mat];
+               if (lastA) {
+                  tagB = mat;
 #pragma unroll
-         for (int d = 0; d < DT; d++) {
-            const double2 mw = s_mw[d];
-            const double az = mw.x * idz;
-            double acc = fma(az, psiz[d], qv);
-            acc = fma(a0[d], r0[d * PSX], acc);
-            acc = fma(a1[d], r1[d * PSX], acc);
-            const double v = acc * fast_rcp(st + so[d] + az);
-            psiz[d] = v;
-            wbuf[d * PSX] = v;
-            pw[d * PSX] = v;
-            ph = fma(mw.y, v, ph);
+                  for (int d = 0; d < DT; d++) invB[d] = fast_rcp(st + so[d] + s_mw[d].x);
+               } else {
+                  tagA = mat;
+#pragma unroll
+                  for (int d = 0; d < DT; d++) invA[d] = fast_rcp(st + so[d] + s_mw[d].x);
+               }
+            }
+            const bool useA = (mat == tagA);
+            lastA = useA;
+#pragma unroll
+            for (int d = 0; d < DT; d++) {
+               const double2 mw = s_mw[d];
+               double acc = fma(mw.x, psiz[d], qv);
+               acc = fma(a0[d], r0[d * PSX], acc);
+               acc = fma(a1[d], r1[d * PSX], acc);
+               const double v = acc * (useA ? invA[d] : invB[d]);
+               psiz[d] = v;
+               wbuf[d * PSX] = v;
+               pw[d * PSX] = v;
+               ph = fma(mw.y, v, ph);
+            }
+         } else {
+            const double st = s_sigt[mat];
+            const double idz = s_idz[k];
+#pragma unroll
+            for (int d = 0; d < DT; d++) {
+               const double2 mw = s_mw[d];
+               const double az = mw.x * idz;
+               double acc = fma(az, psiz[d], qv);
+               acc = fma(a0[d], r0[d * PSX], acc);
+               acc = fma(a1[d], r1[d * PSX], acc);
+               const double v = acc * fast_rcp(st + so[d] + az);
+               psiz[d] = v;
+               wbuf[d * PSX] = v;
+               pw[d * PSX] = v;
+               ph = fma(mw.y, v, ph);
+            }
          }
          if (ex < PEDGE) {
 #pragma unroll
@@ -574,8 +609,13 @@ template <int DT>
 static void launch_tile_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, bool extras, cudaStream_t st) {
    const size_t smem = ((size_t)TILE_D * DT * PSX + TILE_D * PS + (TILE_D * PS) / 2 + 4 * DT + gp.nz + gp.nmat) *
                        sizeof(double);   // bufs | q stage | material stage | {muz,w}, mux, muy | idz | sigma_t
-   if (extras) sn_sweep_tile_kernel<DT, true><<<ntasks, PS, smem, st>>>(gp, d_tasks);
-   else        sn_sweep_tile_kernel<DT, false><<<ntasks, PS, smem, st>>>(gp, d_tasks);
+   if (gp.uniform_dz) {
+      if (extras) sn_sweep_tile_kernel<DT, true, true><<<ntasks, PS, smem, st>>>(gp, d_tasks);
+      else        sn_sweep_tile_kernel<DT, false, true><<<ntasks, PS, smem, st>>>(gp, d_tasks);
+   } else {
+      if (extras) sn_sweep_tile_kernel<DT, true, false><<<ntasks, PS, smem, st>>>(gp, d_tasks);
+      else        sn_sweep_tile_kernel<DT, false, false><<<ntasks, PS, smem, st>>>(gp, d_tasks);
+   }
 }
 
 void launch_sweep_tile(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras,
@@ -597,11 +637,12 @@ void launch_sweep_tile(const SweepGlobals& gp, const Task* d_tasks, int ntasks, 
 
 template <int DT>
 static cudaError_t cfg_tile() {
-   cudaError_t e = cudaFuncSetAttribute(sn_sweep_tile_kernel<DT, false>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-   if (e != cudaSuccess) return e;
-   return cudaFuncSetAttribute(sn_sweep_tile_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               160 * 1024);
+   cudaError_t e;
+   const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+   if ((e = cudaFuncSetAttribute(sn_sweep_tile_kernel<DT, false, false>, attr, 160 * 1024)) != cudaSuccess) return e;
+   if ((e = cudaFuncSetAttribute(sn_sweep_tile_kernel<DT, true, false>, attr, 160 * 1024)) != cudaSuccess) return e;
+   if ((e = cudaFuncSetAttribute(sn_sweep_tile_kernel<DT, false, true>, attr, 160 * 1024)) != cudaSuccess) return e;
+   return cudaFuncSetAttribute(sn_sweep_tile_kernel<DT, true, true>, attr, 160 * 1024);
 }
 
 cudaError_t configure_tile_kernels() {

@@ -78,6 +78,7 @@ struct SweepGlobals {
    int32_t bcz_minus_refl, bcz_plus_refl;   // 1 if that z boundary is reflective
    int32_t store_psi;
    int32_t nmat;
+   int32_t uniform_dz;        // 1: every layer has the same thickness (or the mesh has no z faces)
 };
 
 struct ReduceScalars {        // device-resident iteration state
