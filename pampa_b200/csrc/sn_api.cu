@@ -79,6 +79,8 @@ struct pampa_sn_handle {
    // Anderson acceleration state (allocated by the first accelerated solve)
    double* aa_f[AA_SLOTS] = {};
    double* aa_g[AA_SLOTS] = {};
+   double* aa_b[AA_SLOTS] = {};         // boundary-flux part of the state (reflective problems)
+   double* aa_bz[AA_SLOTS] = {};
    double *d_aa_partials = nullptr, *d_aa_dots = nullptr;
    int aa_slots = 0;
    double psi_scale_factor = 1.0;       // psi normalisation relative to phi (1 unless accelerated)
@@ -809,6 +811,9 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
    const int64_t nslab = (int64_t)pl.nz * pl.Sb, nphi = h->G * nslab;
    int depth = h->opts.anderson_depth == 0 ? AA_SLOTS - 1 : h->opts.anderson_depth;     // < 0: plain power iteration
    depth = std::min(depth, AA_SLOTS - 1);
+   // the lagged LS boundary term depends on the angular flux of the previous sweep, which is not
+   // part of the mixed state: keep the history short there (1-D / 2-D problems only)
+   if (h->nls > 0 && depth > 3) depth = 3;
    int it = 0;
    bool converged = false;
    h->psi_scale_factor = 1.0;
@@ -829,7 +834,8 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
       const int slots = depth + 1;
       if (h->aa_slots < slots) {
          for (int j = h->aa_slots; j < slots; j++)
-            if (dev_alloc(h, &h->aa_f[j], nphi) || dev_alloc(h, &h->aa_g[j], nphi)) return 1;
+            if (dev_alloc(h, &h->aa_f[j], nphi) || dev_alloc(h, &h->aa_g[j], nphi) ||
+                dev_alloc(h, &h->aa_b[j], h->bnd_count) || dev_alloc(h, &h->aa_bz[j], h->bndz_count)) return 1;
          if (!h->d_aa_partials && (dev_alloc(h, &h->d_aa_partials, (int64_t)AA_SLOTS * h->nblocks_reduce) ||
                                    dev_alloc(h, &h->d_aa_dots, AA_SLOTS))) return 1;
          h->aa_slots = slots;
@@ -870,6 +876,9 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
          launch_aa_store(h->d_phi, h->d_phi_new, h->d_mats, h->d_gloc, owned_only, h->G, nslab, inv, fptr, gptr, cur,
                          nvisit, h->d_aa_partials, h->nblocks_reduce, h->d_aa_dots, h->stream);
          h->launches += 2;
+         // the lagged boundary fluxes are part of the fixed-point state: same normalisation, same mixing
+         launch_scale_copy(h->aa_b[cur], h->d_bnd[h->bnd_cur], inv, h->bnd_count, h->stream);
+         launch_scale_copy(h->aa_bz[cur], h->d_bndz[h->bnd_cur], inv, h->bndz_count, h->stream);
          if (owned_only) {
             int r = g_nccl.AllReduce(h->d_aa_dots, h->d_aa_dots, AA_SLOTS, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
             if (r != 0) return nccl_fail(h, r, "the Anderson allreduce");
@@ -902,6 +911,8 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
          launch_aa_mix(h->d_phi, h->d_mats, h->d_gloc, owned_only, h->G, nslab, fptr, gptr, mix, slots,
                        h->nblocks_reduce, h->stream);
          h->launches++;
+         if (h->bnd_count > 0) launch_vec_mix(h->d_bnd[h->bnd_cur], h->aa_b, mix, slots, h->bnd_count, h->stream);
+         if (h->bndz_count > 0) launch_vec_mix(h->d_bndz[h->bnd_cur], h->aa_bz, mix, slots, h->bndz_count, h->stream);
          SN_CUDA(h, cudaMemcpyAsync(&h->d_sc->keff, &kn, sizeof(double), cudaMemcpyHostToDevice, h->stream));
          if (gather_phi(h)) return 1;
          if (converged) break;

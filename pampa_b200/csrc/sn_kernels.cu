@@ -1018,6 +1018,32 @@ sn_aa_mix_kernel(double* __restrict__ phi, const int32_t* __restrict__ mats, con
    }
 }
 
+// plain vector helpers for the boundary-flux part of the Anderson state
+__global__ void sn_scale_copy_kernel(double* __restrict__ dst, const double* __restrict__ src, double c, int64_t n) {
+   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      dst[i] = c * src[i];
+}
+__global__ void sn_vec_mix_kernel(double* __restrict__ out, AAHist hist, AACoef coef, int nhist, int64_t n) {
+   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < AA_MAX; j++)
+         if (j < nhist && coef.alpha[j] != 0.0) v = fma(coef.alpha[j], hist.g[j][i], v);
+      out[i] = v;
+   }
+}
+void launch_scale_copy(double* dst, const double* src, double c, int64_t n, cudaStream_t st) {
+   if (n <= 0) return;
+   sn_scale_copy_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(dst, src, c, n);
+}
+void launch_vec_mix(double* out, double* const* hist, const double* alpha, int nhist, int64_t n, cudaStream_t st) {
+   if (n <= 0) return;
+   AAHist h{};
+   AACoef c{};
+   for (int j = 0; j < AA_MAX; j++) { h.g[j] = hist[j]; h.f[j] = nullptr; c.alpha[j] = j < nhist ? alpha[j] : 0.0; }
+   sn_vec_mix_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(out, h, c, nhist, n);
+}
+
 void launch_aa_store(const double* phi, double* phi_new, const int32_t* mats, const int32_t* gloc,
                      int owned_only, int G, int64_t n, double inv_prod, double* const* hist_f,
                      double* const* hist_g, int cur, int nhist, double* partials, int nblocks, double* dots,

@@ -119,6 +119,8 @@ void launch_aa_store(const double* phi, double* phi_new, const int32_t* mats, co
                      int owned_only, int G, int64_t n, double inv_prod, double* const* hist_f,
                      double* const* hist_g, int cur, int nhist, double* partials, int nblocks, double* dots,
                      cudaStream_t st);
+void launch_scale_copy(double* dst, const double* src, double c, int64_t n, cudaStream_t st);
+void launch_vec_mix(double* out, double* const* hist, const double* alpha, int nhist, int64_t n, cudaStream_t st);
 void launch_aa_mix(double* phi, const int32_t* mats, const int32_t* gloc, int owned_only, int G, int64_t n,
                    double* const* hist_f, double* const* hist_g, const double* alpha, int nhist, int nblocks,
                    cudaStream_t st);
