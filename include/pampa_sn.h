@@ -109,6 +109,8 @@ typedef struct {
    int32_t single_stream;        /* 1: launch all ordering classes on one stream (A/B testing) */
    int32_t anderson_depth;       /* Anderson acceleration of the k-eff iteration: history depth 1..7
                                     (0: default 7, < 0: plain power iteration) */
+   int32_t wave_launch;          /* 1: sweep the tile classes with one launch per wavefront instead of the
+                                    single dataflow launch (A/B testing) */
 } pampa_sn_options;
 
 void pampa_sn_default_options(pampa_sn_options* opts);

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpampa_sn_b200.so")
+# PAMPA_SN_LIB: another build of the same library (kernel A/B runs); never a different implementation
+LIB_PATH = os.environ.get("PAMPA_SN_LIB") or os.path.join(_HERE, "lib", "libpampa_sn_b200.so")
 
 i32, i64, f64 = C.c_int32, C.c_int64, C.c_double
 p_i32, p_f64 = C.POINTER(C.c_int32), C.POINTER(C.c_double)
@@ -42,7 +43,7 @@ class Options(C.Structure):
     _fields_ = [("device", i32), ("store_psi", i32), ("patch_cells", i32), ("tile_i", i32), ("tile_j", i32),
                 ("z_chunk", i32), ("rank", i32), ("num_ranks", i32), ("shard_mode", i32), ("verbose", i32),
                 ("dt_max", i32), ("generic_only", i32), ("single_stream", i32),
-                ("anderson_depth", i32)]
+                ("anderson_depth", i32), ("wave_launch", i32)]
 
 
 class Info(C.Structure):

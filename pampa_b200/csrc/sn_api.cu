@@ -44,6 +44,8 @@ NcclApi g_nccl;
 constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MIN = 3;
 
 struct LaunchGroup { int wave, cls, kind, dt, fin, ring; bool extras; int64_t offset; int count; };
+// one dataflow launch: every tile-class task of one chunk size, in ticket (topological) order
+struct FlowLaunch { int dt; int64_t offset; int count; };
 
 }  // namespace
 
@@ -93,6 +95,9 @@ struct pampa_sn_handle {
    ChunkDev* d_chunks = nullptr;
    Task* d_tasks = nullptr;
    std::vector<LaunchGroup> groups;
+   std::vector<FlowLaunch> flows;
+   int* d_flow_ctl = nullptr;            // [16 ticket counters | progress[chunk][owned group][patch]]
+   int64_t flow_ctl_count = 0;
    std::vector<int32_t*> d_pos_of;       // per class
    int32_t** d_class_pos_of = nullptr;
    // LS
@@ -133,6 +138,7 @@ struct pampa_sn_handle {
       gp.store_psi = 1;
       gp.nmat = nmat;
       gp.uniform_dz = uniform_dz;
+      { const char* e = std::getenv("PAMPA_SN_DBG"); gp.dbg = e ? std::atoi(e) : 0; }
       return gp;
    }
    int bcz_refl[2] = {0, 0};
@@ -225,9 +231,19 @@ int do_sweep(pampa_sn_handle* h) {
       h->launches++;
    }
    const int ns = h->multi_stream ? pampa_sn_handle::NSTREAMS : 0;
+   if (!h->flows.empty()) {
+      // tickets and progress counters of the dataflow launches start from zero every sweep
+      cudaMemsetAsync(h->d_flow_ctl, 0, (size_t)h->flow_ctl_count * sizeof(int), h->stream);
+   }
    if (ns) {
       cudaEventRecord(h->ev_fork, h->stream);
       for (int i = 0; i < ns; i++) cudaStreamWaitEvent(h->cls_stream[i], h->ev_fork, 0);
+   }
+   for (size_t f = 0; f < h->flows.size(); f++) {
+      const FlowLaunch& fl = h->flows[f];
+      cudaStream_t st = ns ? h->cls_stream[f % ns] : h->stream;
+      launch_sweep_flow(gp, h->d_tasks + fl.offset, fl.count, fl.dt, h->extras, h->d_flow_ctl + f, h->d_flow_ctl + 16, st);
+      h->launches++;
    }
    for (const LaunchGroup& lg : h->groups) {
       cudaStream_t st = ns ? h->cls_stream[lg.cls % ns] : h->stream;
@@ -430,6 +446,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       }
       SN_CUDA(h, configure_sweep_kernels());
       SN_CUDA(h, configure_tile_kernels());
+      SN_CUDA(h, configure_flow_kernels());
       SN_CUDA(h, configure_shear_kernels());
 
       const int nr = h->opts.num_ranks, rank = h->opts.rank;
@@ -626,11 +643,33 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          if (dev_upload(h, &h->d_dir_chunk, a) || dev_upload(h, &h->d_dir_d, b)) return 1;
       }
 
-      // launch schedule: per wave, tasks grouped by kernel variant
+      // launch schedule.  Tile classes: one dataflow launch per chunk size, tasks in ticket order =
+      // wavefront number first, so that every class (octant) advances together and a task's upwind
+      // tasks always hold lower tickets.  Other classes (and wave_launch = 1): per wave, tasks grouped
+      // by kernel variant, one launch each.
       std::vector<Task> all;
-      h->groups.clear();
+      h->groups.clear(); h->flows.clear();
+      const bool use_flow = !h->opts.wave_launch && pl.nzc == 1;
+      if (use_flow) {
+         for (int dt = 1; dt <= DT_MAX; dt++) {
+            const size_t first = all.size();
+            for (size_t w = 0; w < pl.waves.size(); w++)
+               for (const Task& t : pl.waves[w])
+                  if (h->class_fast[pl.chunks[t.chunk].cls] && pl.chunks[t.chunk].nd == dt) all.push_back(t);
+            if (all.size() > first) {
+               if (h->flows.size() >= 16) SN_FAIL(h, "internal: too many dataflow launches");
+               h->flows.push_back(FlowLaunch{dt, (int64_t)first, (int)(all.size() - first)});
+            }
+         }
+         if (!h->flows.empty()) {
+            h->flow_ctl_count = 16 + (int64_t)pl.chunks.size() * h->Gown * pl.npatch_b;
+            if (dev_alloc(h, &h->d_flow_ctl, h->flow_ctl_count)) return 1;
+         }
+      }
       for (size_t w = 0; w < pl.waves.size(); w++) {
-         std::vector<Task> tasks = pl.waves[w];
+         std::vector<Task> tasks;
+         for (const Task& t : pl.waves[w])
+            if (!(use_flow && h->class_fast[pl.chunks[t.chunk].cls])) tasks.push_back(t);
          auto variant = [&](const Task& t) {
             const Chunk& ch = pl.chunks[t.chunk]; const ClassPlan& cp = pl.classes[ch.cls];
             return std::make_tuple(ch.cls, h->class_fast[ch.cls] ? 1 : 0, dt_template(ch.nd), cp.fin <= 2 ? 2 : FIN_MAX, cp.ring);
@@ -650,7 +689,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       if (dev_upload(h, &h->d_tasks, all)) return 1;
       // reflective / LS problems read what another class wrote in the previous sweep only, so classes
       // stay independent within a sweep; streams are used unless the option turns them off
-      h->multi_stream = pl.classes.size() > 1 && !h->opts.single_stream;
+      h->multi_stream = (pl.classes.size() > 1 || h->flows.size() > 1) && !h->opts.single_stream;
 
       // reduction scratch and iteration state
       h->nblocks_reduce = (int)std::min<int64_t>(((int64_t)nz * Sb + 255) / 256, 148 * 8);
@@ -668,7 +707,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
    if (h->opts.verbose)
       std::printf("pampa_sn: %d xy cells x %d layers, %d groups, %d directions, %zu classes (%d tiled), %zu chunks, "
                   "%zu sweep launches, %.1f MB on device %d\n", pl.nxy, pl.nz, h->G, h->M, pl.classes.size(),
-                  pl.tile_classes, pl.chunks.size(), h->groups.size(), h->device_bytes / 1.0e6, h->device);
+                  pl.tile_classes, pl.chunks.size(), h->groups.size() + h->flows.size(), h->device_bytes / 1.0e6, h->device);
    *out = hp.release();
    return 0;
 }
@@ -1078,7 +1117,7 @@ int pampa_sn_get_info(pampa_sn_handle* h, pampa_sn_info* info) {
    const Plan& pl = h->plan;
    info->num_cells = (int64_t)pl.nxy * pl.nz; info->num_groups = h->G; info->num_directions = h->M;
    info->updates_per_sweep = pl.owned_updates;
-   info->sweep_launches = (int64_t)h->groups.size();
+   info->sweep_launches = (int64_t)(h->groups.size() + h->flows.size());
    for (auto& g : h->groups) info->sweep_tasks += g.count;
    info->num_classes = (int64_t)pl.classes.size(); info->num_chunks = (int64_t)pl.chunks.size();
    info->tile_classes = pl.tile_classes;

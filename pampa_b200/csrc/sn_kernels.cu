@@ -659,6 +659,399 @@ cudaError_t configure_tile_kernels() {
    return cfg_tile<10>();
 }
 
+// ------------------------------------------------------------------------------------ flow kernel
+// The tile kernel as a dataflow pipeline: ONE launch per sweep (and chunk size) instead of one per
+// wavefront.  A CTA takes a ticket, which gives it the next task of a topologically sorted list, so
+// every task it depends on is already resident or finished; a task publishes the number of psi rows
+// it has completed in progress[task], and the task of the downwind patch polls that counter before it
+// stages a row of edge copies.  Neighbouring patches therefore run skewed by ~20 pipeline steps
+// instead of a whole task (246 steps at 216 layers): no wavefront tails on one GPU, and a critical
+// path ~9x shorter when the sweep is sharded over GPUs.
+//
+// Roles (warp specialisation, 288 threads): warps 0-7 are the 256 lanes of the patch and never touch
+// psi in global memory; warp 8 is the producer:
+//   * its 32 lanes own the 32 halo entries of the patch (values read from another patch's edge
+//     copies, or from the mirrored direction of a reflective face): poll the upwind task's progress
+//     counter (ld.acquire.gpu), then cp.async the DT values PFD steps ahead of their use;
+//   * lane 0 stores the finished psi row -- the shared-memory buffer of the step IS the global row
+//     [DT][256 lanes | 32 edge copies] -- with DT bulk async copies (cp.async.bulk, async proxy) and
+//     publishes the progress counter (st.release.gpu) once the copies of the previous step have landed.
+// The LSU pipe was the limiter of the per-lane version (81 % busy: 2 LDS + STS + STG per update, all
+// 64-bit); the row stores and halo loads are ~30 % of its wavefronts.
+constexpr int PSXS = PS + 2 * PEDGE;       // smem row: 256 ring lanes | 32 edge copies (out) | 32 halo (in)
+constexpr int FLOW_THREADS = PS + 32;
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+   int v;
+   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+   return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
+   const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
+                : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+struct HaloEntry { int32_t code; int32_t lv; };      // upwind source code and level of the reading lane
+
+template <int DT, bool EXTRAS, bool UNIFORM_DZ>
+__global__ void __launch_bounds__(FLOW_THREADS, (DT <= 8 ? 2 : 1))
+sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int* __restrict__ ticket,
+                     int* __restrict__ progress) {
+   extern __shared__ __align__(128) double smem[];
+   constexpr int ROWG = DT * PSX;                     // global psi row of one pipeline step
+   constexpr int ROWS = DT * PSXS;                    // its shared-memory buffer (+ halo columns)
+   constexpr int D = TILE_D, PFD = TILE_PFD;
+   __shared__ int s_task;
+   __shared__ HaloEntry s_halo[PEDGE];
+   const int t = threadIdx.x;
+   if (t == 0) s_task = atomicAdd(ticket, 1);
+   if (t < PEDGE) s_halo[t] = HaloEntry{-1, 0};
+   __syncthreads();
+   const Task tk = tasks[s_task];
+   const ChunkDev* __restrict__ ch = gp.chunks + tk.chunk;
+   const ClassDev* __restrict__ cl = gp.classes + ch->cls;
+   const int64_t S = cl->S;
+   const int g = tk.group;
+   const int gl = gp.gloc[g];
+   const int nz = gp.nz;
+   const int npatch = cl->npatch;
+   const int NS = cl->nsteps;
+   const int zdir = cl->zdir;
+   const int kcnt = nz;                               // the flow kernel never splits a column in z
+   const int nsteps = cl->patch_nlev[tk.patch] + kcnt - 1;
+   const bool lane_thread = t < PS;
+   const int64_t slot = (int64_t)tk.patch * PS + (lane_thread ? t : 0);
+
+   // smem: bufs[D][DT][PSXS] | q stage [D][PS] | material stage [D][PS] (int) | {muz,w}[DT] | mux,muy | idz | sigma_t
+   double* bufs = smem;
+   double* s_q = smem + D * ROWS;
+   int* s_m = (int*)(s_q + D * PS);
+   double2* s_mw = (double2*)(s_q + D * PS + (D * PS) / 2);
+   double* s_mux = (double*)(s_mw + DT);
+   double* s_muy = s_mux + DT;
+   double* s_idz = s_muy + DT;
+   double* s_sigt = s_idz + nz;
+   for (int a = t; a < D * ROWS; a += FLOW_THREADS) bufs[a] = 0.0;
+   for (int kk = t; kk < nz; kk += FLOW_THREADS) s_idz[kk] = gp.has_z ? gp.inv_dz[kk] : 0.0;
+   for (int m = t; m < gp.nmat; m += FLOW_THREADS) s_sigt[m] = gp.sigma_t[m * gp.G + g];
+   if (t < DT) {
+      s_mux[t] = ch->mux[t];
+      s_muy[t] = ch->muy[t];
+      s_mw[t] = make_double2(gp.has_z ? ch->muz_abs[t] * (UNIFORM_DZ ? gp.inv_dz[0] : 1.0) : 0.0, ch->w[t]);
+   }
+   __syncthreads();
+
+   const int64_t prow = (int64_t)tk.patch * NS;       // first row of this patch in the step-major arrays
+   double* psi_gl = ch->psi + (int64_t)gl * npatch * NS * ROWG;
+   const int kdir = zdir >= 0 ? 1 : -1;
+   const int kstart = zdir >= 0 ? 0 : nz - 1;
+   int* my_progress = progress + ((int64_t)tk.chunk * gp.Gown + gl) * npatch + tk.patch;
+
+   if (lane_thread) {
+      // ---------------------------------------------------------------- the 256 lanes of the patch
+      const int lv = cl->lvl[slot];
+      const bool valid = (lv != LVL_EMPTY);
+      const int lv0 = valid ? lv : (1 << 20);         // holes are never active
+      double a0[DT], a1[DT], so[DT];
+      int off0 = t, off1 = t;                         // default: own ring entry with a zero coefficient
+      if (valid) {
+         const double2 ov = cl->out_vec[slot];
+         const double2 v0 = cl->in_vec[slot];
+         const double2 v1 = cl->in_vec[S + slot];
+#pragma unroll
+         for (int d = 0; d < DT; d++) {
+            so[d] = s_mux[d] * ov.x + s_muy[d] * ov.y;
+            a0[d] = -(s_mux[d] * v0.x + s_muy[d] * v0.y);
+            a1[d] = -(s_mux[d] * v1.x + s_muy[d] * v1.y);
+         }
+         const int c0 = cl->in_src[slot];
+         const int c1 = cl->in_src[S + slot];
+         if (c0 >= 0) {
+            if ((c0 >> SRC_KIND_SHIFT) == SRC_LOCAL) off0 = c0 & SRC_PAYLOAD;
+            else {
+               const int hx = cl->in_hidx[slot];
+               off0 = PS + PEDGE + hx;
+               s_halo[hx] = HaloEntry{c0, lv};
+            }
+         }
+         if (c1 >= 0) {
+            if ((c1 >> SRC_KIND_SHIFT) == SRC_LOCAL) off1 = c1 & SRC_PAYLOAD;
+            else {
+               const int hx = cl->in_hidx[S + slot];
+               off1 = PS + PEDGE + hx;
+               s_halo[hx] = HaloEntry{c1, lv};
+            }
+         }
+      } else {
+#pragma unroll
+         for (int d = 0; d < DT; d++) { so[d] = 0.0; a0[d] = 0.0; a1[d] = 0.0; }
+      }
+      const int ex = valid ? (int)cl->eidx[slot] : 255;   // my compact edge index, if another patch reads me
+      int rout[ROUT_MAX];
+      if (EXTRAS) {
+#pragma unroll
+         for (int r = 0; r < ROUT_MAX; r++) rout[r] = valid ? cl->rout[(size_t)r * S + slot] : -1;
+      }
+      const int32_t* m_row = cl->mats_s + prow * PS + t;
+      const double* q_row = cl->q_sheared + ((int64_t)g * npatch * NS + prow) * PS + t;
+      double* ph_row = ch->phi_part + ((int64_t)gl * npatch * NS + prow) * PS + t;
+      const int cell = (int)slot;                      // tile classes: class slot == base slot
+
+      auto stage = [&](int st) {                       // q and material of my column for step `st`
+         const int klt = st - lv0;
+         if (klt < 0 || klt >= kcnt) return;
+         cp_async8(s_q + (st & (D - 1)) * PS + t, q_row + (int64_t)st * PS);
+         cp_async4(s_m + (st & (D - 1)) * PS + t, m_row + (int64_t)st * PS);
+      };
+
+      double psiz[DT];
+#pragma unroll
+      for (int d = 0; d < DT; d++) psiz[d] = 0.0;
+      if (EXTRAS && gp.has_z && valid) {
+         const int face = zdir > 0 ? 0 : 1;
+         if (face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl) {
+#pragma unroll
+            for (int d = 0; d < DT; d++)
+               psiz[d] = gp.bndz_old[(((int64_t)face * gp.M + ch->mrefl[d][2]) * gp.G + g) * gp.Sb + cell];
+         }
+      }
+#pragma unroll
+      for (int st = 0; st < PFD; st++) {
+         stage(st);
+         cp_async_commit();
+      }
+      __syncthreads();                                 // (A) halo table complete -> producer warp
+      __syncthreads();                                 // (B) halo of step 0 staged by the producer warp
+
+      int k = kstart;
+      int tagA = -1, tagB = -1;                        // materials of the two cached reciprocal sets
+      bool lastA = false;
+      double invA[UNIFORM_DZ ? DT : 1], invB[UNIFORM_DZ ? DT : 1];
+      for (int step = 0; step < nsteps; step++) {
+         stage(step + PFD);
+         cp_async_commit();
+         cp_async_wait_group<PFD>();                   // the group of this step has landed
+         const int kl = step - lv0;
+         if (kl >= 0 && kl < kcnt) {
+            const int mat = s_m[(step & (D - 1)) * PS + t];
+            const double qv = s_q[(step & (D - 1)) * PS + t];
+            const double* rbuf = bufs + ((step - 1) & (D - 1)) * ROWS;
+            double* wbuf = bufs + (step & (D - 1)) * ROWS + t;
+            const double* r0 = rbuf + off0;
+            const double* r1 = rbuf + off1;
+            double ph = 0.0;
+            if (UNIFORM_DZ) {
+               if (mat != tagA && mat != tagB) {        // miss: rare once both materials of a column are seen
+                  const double st = s_sigt[mat];
+                  if (lastA) {
+                     tagB = mat;
+#pragma unroll
+                     for (int d = 0; d < DT; d++) invB[d] = fast_rcp(st + so[d] + s_mw[d].x);
+                  } else {
+                     tagA = mat;
+#pragma unroll
+                     for (int d = 0; d < DT; d++) invA[d] = fast_rcp(st + so[d] + s_mw[d].x);
+                  }
+               }
+               const bool useA = (mat == tagA);
+               lastA = useA;
+#pragma unroll
+               for (int d = 0; d < DT; d++) {
+                  const double2 mw = s_mw[d];
+                  double acc = fma(mw.x, psiz[d], qv);
+                  acc = fma(a0[d], r0[d * PSXS], acc);
+                  acc = fma(a1[d], r1[d * PSXS], acc);
+                  const double v = acc * (useA ? invA[d] : invB[d]);
+                  psiz[d] = v;
+                  wbuf[d * PSXS] = v;
+                  ph = fma(mw.y, v, ph);
+               }
+            } else {
+               const double st = s_sigt[mat];
+               const double idz = s_idz[k];
+#pragma unroll
+               for (int d = 0; d < DT; d++) {
+                  const double2 mw = s_mw[d];
+                  const double az = mw.x * idz;
+                  double acc = fma(az, psiz[d], qv);
+                  acc = fma(a0[d], r0[d * PSXS], acc);
+                  acc = fma(a1[d], r1[d * PSXS], acc);
+                  const double v = acc * fast_rcp(st + so[d] + az);
+                  psiz[d] = v;
+                  wbuf[d * PSXS] = v;
+                  ph = fma(mw.y, v, ph);
+               }
+            }
+            if (ex < PEDGE) {
+#pragma unroll
+               for (int d = 0; d < DT; d++) wbuf[d * PSXS + (PS - t) + ex] = psiz[d];
+            }
+            ph_row[(int64_t)step * PS] = ph;
+            if (EXTRAS) {
+#pragma unroll
+               for (int r = 0; r < ROUT_MAX; r++)
+                  if (rout[r] >= 0) {
+#pragma unroll
+                     for (int d = 0; d < DT; d++)
+                        gp.bnd_new[(((int64_t)ch->m[d] * gp.G + g) * nz + k) * gp.nrf + rout[r]] = psiz[d];
+                  }
+               if (gp.has_z && kl == nz - 1) {
+                  const int face = zdir > 0 ? 1 : 0;
+                  if (face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl) {
+#pragma unroll
+                     for (int d = 0; d < DT; d++)
+                        gp.bndz_new[(((int64_t)face * gp.M + ch->m[d]) * gp.G + g) * gp.Sb + cell] = psiz[d];
+                  }
+               }
+            }
+            k += kdir;
+         }
+         if (!(gp.dbg & 2)) fence_proxy_async_smem();  // my row entries -> visible to the bulk store
+         __syncthreads();
+      }
+   } else {
+      // ---------------------------------------------------------------- producer warp
+      const int hl = t - PS;                           // halo entry of this lane
+      __syncthreads();                                 // (A) halo table written by the lanes
+      const HaloEntry he = s_halo[hl];
+      const int kind = he.code >= 0 ? (he.code >> SRC_KIND_SHIFT) : -1;
+      const int pay = he.code & SRC_PAYLOAD;
+      const int rlv = he.lv;
+      const double* gsrc = nullptr;                    // upwind row of staging step 0, direction 0
+      const int* flag = nullptr;
+      int need0 = 0;                                   // rows the upwind task must have completed for step 0
+      int rf = 0, ax = 0;
+      if (kind == SRC_GLOBAL) {
+         const int up = pay >> 8;
+         const int dlv = (int)cl->lvl[pay] - rlv;
+         gsrc = psi_gl + ((int64_t)up * NS + dlv) * ROWG + PS + cl->eidx[pay];
+         flag = progress + ((int64_t)tk.chunk * gp.Gown + gl) * npatch + up;
+         need0 = dlv + 1;
+      } else if (kind == SRC_REFL) {
+         ax = pay >> SRC_AXIS_SHIFT; rf = pay & ((1 << SRC_AXIS_SHIFT) - 1);
+      }
+      int seen = 0;
+      auto stage_halo = [&](int st) {
+         const int klt = st - rlv;
+         if (kind < 0 || klt < 0 || klt >= kcnt) return;
+         double* dst = bufs + ((st - 1) & (D - 1)) * ROWS + PS + PEDGE + hl;
+         if (kind == SRC_GLOBAL) {
+            const int need = st + need0;
+            if (!(gp.dbg & 1)) while (seen < need) seen = ld_acquire_gpu(flag);
+#pragma unroll
+            for (int d = 0; d < DT; d++) cp_async8(dst + d * PSXS, gsrc + (int64_t)st * ROWG + d * PSX);
+         } else if (EXTRAS) {
+            const int kk = kstart + klt * kdir;
+#pragma unroll
+            for (int d = 0; d < DT; d++)
+               cp_async8(dst + d * PSXS,
+                         gp.bnd_old + (((int64_t)ch->mrefl[d][ax] * gp.G + g) * nz + kk) * gp.nrf + rf);
+         }
+      };
+#pragma unroll
+      for (int st = 0; st < PFD; st++) {
+         stage_halo(st);
+         cp_async_commit();
+      }
+      cp_async_wait_group<PFD - 1>();                  // halo of step 0 has landed
+      __syncthreads();                                 // (B)
+      double* psi_rows = psi_gl + prow * ROWG;
+      for (int step = 0; step < nsteps; step++) {
+         stage_halo(step + PFD);
+         cp_async_commit();
+         cp_async_wait_group<PFD - 1>();               // halo of step + 1 has landed
+         if (hl == 0) bulk_wait_read<D - 2>();         // buffer (step+1)&3 is free to be rewritten
+         __syncthreads();                              // end of step: row `step` is complete in smem
+         if (hl == 0) {
+            const double* src = bufs + (step & (D - 1)) * ROWS;
+            double* dst = psi_rows + (int64_t)step * ROWG;
+#pragma unroll
+            for (int d = 0; d < DT; d++) bulk_store(dst + d * PSX, src + d * PSXS, PSX * sizeof(double));
+            bulk_commit();
+            // publish every `pub` steps: the wait + fence + release chain costs about half a step
+            const int pub = (gp.dbg >> 4) ? (gp.dbg >> 4) : 8;
+            if ((step % pub) == pub - 1) {
+               bulk_wait<1>();                         // rows < step are in global memory
+               fence_proxy_async_all();
+               st_release_gpu(my_progress, step);
+            }
+         }
+         __syncwarp();
+      }
+      if (hl == 0) {
+         bulk_wait<0>();
+         fence_proxy_async_all();
+         st_release_gpu(my_progress, nsteps);
+      }
+   }
+}
+
+template <int DT>
+static void launch_flow_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, bool extras, int* ticket,
+                           int* progress, cudaStream_t st) {
+   const size_t smem = ((size_t)TILE_D * DT * PSXS + TILE_D * PS + (TILE_D * PS) / 2 + 4 * DT + gp.nz + gp.nmat) *
+                       sizeof(double);
+   if (gp.uniform_dz) {
+      if (extras) sn_sweep_flow_kernel<DT, true, true><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress);
+      else        sn_sweep_flow_kernel<DT, false, true><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress);
+   } else {
+      if (extras) sn_sweep_flow_kernel<DT, true, false><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress);
+      else        sn_sweep_flow_kernel<DT, false, false><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress);
+   }
+}
+
+void launch_sweep_flow(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras, int* ticket,
+                       int* progress, cudaStream_t st) {
+   if (ntasks <= 0) return;
+   switch (dt) {
+      case 1: launch_flow_dt<1>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
+      case 2: launch_flow_dt<2>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
+      case 3: launch_flow_dt<3>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
+      case 4: launch_flow_dt<4>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
+      case 5: launch_flow_dt<5>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
+      case 6: launch_flow_dt<6>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
+      case 7: launch_flow_dt<7>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
+      case 8: launch_flow_dt<8>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
+      case 9: launch_flow_dt<9>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
+      default: launch_flow_dt<10>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
+   }
+}
+
+template <int DT>
+static cudaError_t cfg_flow() {
+   cudaError_t e;
+   const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+   if ((e = cudaFuncSetAttribute(sn_sweep_flow_kernel<DT, false, false>, attr, 200 * 1024)) != cudaSuccess) return e;
+   if ((e = cudaFuncSetAttribute(sn_sweep_flow_kernel<DT, true, false>, attr, 200 * 1024)) != cudaSuccess) return e;
+   if ((e = cudaFuncSetAttribute(sn_sweep_flow_kernel<DT, false, true>, attr, 200 * 1024)) != cudaSuccess) return e;
+   return cudaFuncSetAttribute(sn_sweep_flow_kernel<DT, true, true>, attr, 200 * 1024);
+}
+
+cudaError_t configure_flow_kernels() {
+   cudaError_t e;
+   if ((e = cfg_flow<1>()) != cudaSuccess) return e;
+   if ((e = cfg_flow<2>()) != cudaSuccess) return e;
+   if ((e = cfg_flow<3>()) != cudaSuccess) return e;
+   if ((e = cfg_flow<4>()) != cudaSuccess) return e;
+   if ((e = cfg_flow<5>()) != cudaSuccess) return e;
+   if ((e = cfg_flow<6>()) != cudaSuccess) return e;
+   if ((e = cfg_flow<7>()) != cudaSuccess) return e;
+   if ((e = cfg_flow<8>()) != cudaSuccess) return e;
+   if ((e = cfg_flow<9>()) != cudaSuccess) return e;
+   return cfg_flow<10>();
+}
+
 // q (base layout [g][k][slot]) -> each fast class's step-major copy, streamed: one CTA per (patch,
 // group, z direction) walks the pipeline steps in order; a thread keeps the last 32 layers of its own
 // column in a shared-memory ring and writes, for every class, the entry its level selects.  Every

@@ -79,6 +79,7 @@ struct SweepGlobals {
    int32_t store_psi;
    int32_t nmat;
    int32_t uniform_dz;        // 1: every layer has the same thickness (or the mesh has no z faces)
+   int32_t dbg;               // development knobs of the flow kernel (PAMPA_SN_DBG), 0 in production
 };
 
 struct ReduceScalars {        // device-resident iteration state
@@ -99,6 +100,11 @@ cudaError_t configure_shear_kernels();
 constexpr int SHEAR_MAX_PER_PASS = 32;   // fast classes / chunks per z direction the shear kernels handle
 void launch_sweep_tile(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras,
                        cudaStream_t st);
+// dataflow version of the tile kernel: one launch, tasks taken by ticket in topological order,
+// patch-to-patch dependencies through progress counters (see sn_kernels.cu)
+void launch_sweep_flow(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras, int* ticket,
+                       int* progress, cudaStream_t st);
+cudaError_t configure_flow_kernels();
 // base [g][k][slot] <-> step-major [g][patch][step][lane] transforms for the tile kernel
 void launch_shear_q(const SweepGlobals& gp, const ClassDev* d_classes, const int32_t* d_fast_classes,
                     int nfast, int npatch_b, cudaStream_t st);

@@ -449,7 +449,7 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
    int Kc = pl.nz;
    if (in.opts.z_chunk > 0) Kc = std::min(pl.nz, in.opts.z_chunk);
    else if (pl.has_z && pl.tile_classes < (int)pl.classes.size()) Kc = std::min(pl.nz, 32);
-   else if (pl.has_z && in.opts.num_ranks > 2) {
+   else if (pl.has_z && in.opts.num_ranks > 2 && in.opts.wave_launch) {
       // sharded over many GPUs a rank owns too few sweeps to fill its SMs wavefront by wavefront:
       // pipeline in z as well (tasks x nzc, critical path ~ (patch levels + nzc) x (levels + nz/nzc))
       const int nzc = 2;      // measured on 4 and 8 B200s: 2-3 chunks beat 1 and 4
