@@ -45,7 +45,7 @@ constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MIN = 3;
 
 struct LaunchGroup { int wave, cls, kind, dt, fin, ring; bool extras; int64_t offset; int count; };
 // one dataflow launch: every tile-class task of one chunk size, in ticket (topological) order
-struct FlowLaunch { int dt; int64_t offset; int count; };
+struct FlowLaunch { int dt; int64_t offset; int count; std::vector<double> mw; int nch; };
 
 }  // namespace
 
@@ -242,7 +242,8 @@ int do_sweep(pampa_sn_handle* h) {
    for (size_t f = 0; f < h->flows.size(); f++) {
       const FlowLaunch& fl = h->flows[f];
       cudaStream_t st = ns ? h->cls_stream[f % ns] : h->stream;
-      launch_sweep_flow(gp, h->d_tasks + fl.offset, fl.count, fl.dt, h->extras, h->d_flow_ctl + f, h->d_flow_ctl + 16, st);
+      launch_sweep_flow(gp, h->d_tasks + fl.offset, fl.count, fl.dt, h->extras, h->d_flow_ctl + f, h->d_flow_ctl + 16,
+                        fl.mw.data(), fl.nch, st);
       h->launches++;
    }
    for (const LaunchGroup& lg : h->groups) {
@@ -637,7 +638,6 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          h->nfast_classes = (int)fast_classes.size(); h->nfast_chunks = (int)fast_chunks.size();
          if (dev_upload(h, &h->d_fast_classes, fast_classes) || dev_upload(h, &h->d_fast_chunks, fast_chunks)) return 1;
       }
-      if (dev_upload(h, &h->d_chunks, chdev)) return 1;
       {
          std::vector<int32_t> a(h->dir_chunk.begin(), h->dir_chunk.end()), b(h->dir_d.begin(), h->dir_d.end());
          if (dev_upload(h, &h->d_dir_chunk, a) || dev_upload(h, &h->d_dir_d, b)) return 1;
@@ -649,7 +649,13 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       // by kernel variant, one launch each.
       std::vector<Task> all;
       h->groups.clear(); h->flows.clear();
-      const bool use_flow = !h->opts.wave_launch && pl.nzc == 1;
+      bool use_flow = !h->opts.wave_launch && pl.nzc == 1;
+      {  // every chunk of a flow launch needs a slot in the kernel-parameter direction table
+         int per_dt[DT_MAX + 1] = {};
+         for (size_t c = 0; c < pl.chunks.size(); c++)
+            if (chunk_owned[c] && h->class_fast[pl.chunks[c].cls]) per_dt[pl.chunks[c].nd]++;
+         for (int dt = 1; dt <= DT_MAX; dt++) if (per_dt[dt] > flow_max_chunks(dt)) use_flow = false;
+      }
       if (use_flow) {
          for (int dt = 1; dt <= DT_MAX; dt++) {
             const size_t first = all.size();
@@ -658,7 +664,16 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
                   if (h->class_fast[pl.chunks[t.chunk].cls] && pl.chunks[t.chunk].nd == dt) all.push_back(t);
             if (all.size() > first) {
                if (h->flows.size() >= 16) SN_FAIL(h, "internal: too many dataflow launches");
-               h->flows.push_back(FlowLaunch{dt, (int64_t)first, (int)(all.size() - first)});
+               FlowLaunch fl{dt, (int64_t)first, (int)(all.size() - first), {}, 0};
+               for (size_t c = 0; c < pl.chunks.size(); c++) {
+                  if (!(chunk_owned[c] && h->class_fast[pl.chunks[c].cls] && pl.chunks[c].nd == dt)) continue;
+                  chdev[c].flow_slot = fl.nch++;
+                  for (int d = 0; d < DT_MAX; d++) {
+                     fl.mw.push_back(pl.has_z ? chdev[c].muz_abs[d] * (h->uniform_dz ? 1.0 / mesh->dz[0] : 1.0) : 0.0);
+                     fl.mw.push_back(chdev[c].w[d]);
+                  }
+               }
+               h->flows.push_back(fl);
             }
          }
          if (!h->flows.empty()) {
@@ -686,6 +701,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          }
          all.insert(all.end(), tasks.begin(), tasks.end());
       }
+      if (dev_upload(h, &h->d_chunks, chdev)) return 1;
       if (dev_upload(h, &h->d_tasks, all)) return 1;
       // reflective / LS problems read what another class wrote in the previous sweep only, so classes
       // stay independent within a sweep; streams are used unless the option turns them off

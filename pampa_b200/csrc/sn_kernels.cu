@@ -680,6 +680,7 @@ cudaError_t configure_tile_kernels() {
 // 64-bit); the row stores and halo loads are ~30 % of its wavefronts.
 constexpr int PSXS = PS + 2 * PEDGE;       // smem row: 256 ring lanes | 32 edge copies (out) | 32 halo (in)
 constexpr int FLOW_THREADS = PS + 32;
+constexpr int FLOW_DQ = 8, FLOW_PFQ = 6;    // q / material row ring: depth and prefetch distance (steps)
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
    int v;
@@ -702,20 +703,63 @@ __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_g
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+   const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+   asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(a), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (async proxy), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// Direction constants {|mu_z| (/dz when uniform), weight} of every chunk of a flow launch, passed as a
+// kernel parameter: the lanes read them with LDC (constant cache) instead of shared memory, which
+// keeps them off the LSU pipe and out of the register file.
+constexpr int FLOW_DIRS_BYTES = 3328;
+template <int DT>
+struct FlowDirs {
+   static constexpr int MAXCH = FLOW_DIRS_BYTES / (16 * DT);
+   double2 mw[MAXCH][DT];
+};
+int flow_max_chunks(int dt) { return FLOW_DIRS_BYTES / (16 * dt); }
+
+__device__ __forceinline__ int ld_acquire_cta_smem(const int* p) {
+   int v;
+   asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+   return v;
+}
+__device__ __forceinline__ void st_release_cta_smem(int* p, int v) {
+   asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void lanes_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 struct HaloEntry { int32_t code; int32_t lv; };      // upwind source code and level of the reading lane
 
 template <int DT, bool EXTRAS, bool UNIFORM_DZ>
 __global__ void __launch_bounds__(FLOW_THREADS, (DT <= 8 ? 2 : 1))
 sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int* __restrict__ ticket,
-                     int* __restrict__ progress) {
+                     int* __restrict__ progress, const __grid_constant__ FlowDirs<DT> dirs) {
    extern __shared__ __align__(128) double smem[];
    constexpr int ROWG = DT * PSX;                     // global psi row of one pipeline step
    constexpr int ROWS = DT * PSXS;                    // its shared-memory buffer (+ halo columns)
    constexpr int D = TILE_D, PFD = TILE_PFD;
+   constexpr int DQ = FLOW_DQ, PFQ = FLOW_PFQ;        // q / material rows: deeper ring (they come from DRAM)
    __shared__ int s_task;
    __shared__ HaloEntry s_halo[PEDGE];
+   __shared__ __align__(8) uint64_t s_bar[FLOW_DQ];   // q / material rows of a step have landed
    const int t = threadIdx.x;
-   if (t == 0) s_task = atomicAdd(ticket, 1);
+   if (t == 0) {
+      s_task = atomicAdd(ticket, 1);
+#pragma unroll
+      for (int b = 0; b < FLOW_DQ; b++) mbar_init(&s_bar[b], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
    if (t < PEDGE) s_halo[t] = HaloEntry{-1, 0};
    __syncthreads();
    const Task tk = tasks[s_task];
@@ -733,11 +777,11 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
    const bool lane_thread = t < PS;
    const int64_t slot = (int64_t)tk.patch * PS + (lane_thread ? t : 0);
 
-   // smem: bufs[D][DT][PSXS] | q stage [D][PS] | material stage [D][PS] (int) | {muz,w}[DT] | mux,muy | idz | sigma_t
+   // smem: bufs[D][DT][PSXS] | q stage [DQ][PS] | material stage [DQ][PS] (int) | {muz,w}[DT] | mux,muy | idz | sigma_t
    double* bufs = smem;
    double* s_q = smem + D * ROWS;
-   int* s_m = (int*)(s_q + D * PS);
-   double2* s_mw = (double2*)(s_q + D * PS + (D * PS) / 2);
+   int* s_m = (int*)(s_q + DQ * PS);
+   double2* s_mw = (double2*)(s_q + DQ * PS + (DQ * PS) / 2);
    double* s_mux = (double*)(s_mw + DT);
    double* s_muy = s_mux + DT;
    double* s_idz = s_muy + DT;
@@ -803,17 +847,8 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
 #pragma unroll
          for (int r = 0; r < ROUT_MAX; r++) rout[r] = valid ? cl->rout[(size_t)r * S + slot] : -1;
       }
-      const int32_t* m_row = cl->mats_s + prow * PS + t;
-      const double* q_row = cl->q_sheared + ((int64_t)g * npatch * NS + prow) * PS + t;
       double* ph_row = ch->phi_part + ((int64_t)gl * npatch * NS + prow) * PS + t;
       const int cell = (int)slot;                      // tile classes: class slot == base slot
-
-      auto stage = [&](int st) {                       // q and material of my column for step `st`
-         const int klt = st - lv0;
-         if (klt < 0 || klt >= kcnt) return;
-         cp_async8(s_q + (st & (D - 1)) * PS + t, q_row + (int64_t)st * PS);
-         cp_async4(s_m + (st & (D - 1)) * PS + t, m_row + (int64_t)st * PS);
-      };
 
       double psiz[DT];
 #pragma unroll
@@ -826,11 +861,6 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
                psiz[d] = gp.bndz_old[(((int64_t)face * gp.M + ch->mrefl[d][2]) * gp.G + g) * gp.Sb + cell];
          }
       }
-#pragma unroll
-      for (int st = 0; st < PFD; st++) {
-         stage(st);
-         cp_async_commit();
-      }
       __syncthreads();                                 // (A) halo table complete -> producer warp
       __syncthreads();                                 // (B) halo of step 0 staged by the producer warp
 
@@ -838,14 +868,13 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       int tagA = -1, tagB = -1;                        // materials of the two cached reciprocal sets
       bool lastA = false;
       double invA[UNIFORM_DZ ? DT : 1], invB[UNIFORM_DZ ? DT : 1];
+      int cslot = ch->flow_slot;
       for (int step = 0; step < nsteps; step++) {
-         stage(step + PFD);
-         cp_async_commit();
-         cp_async_wait_group<PFD>();                   // the group of this step has landed
+         asm volatile("" : "+r"(cslot));               // keep the LDCs in the loop (not 20 hoisted registers)
          const int kl = step - lv0;
          if (kl >= 0 && kl < kcnt) {
-            const int mat = s_m[(step & (D - 1)) * PS + t];
-            const double qv = s_q[(step & (D - 1)) * PS + t];
+            const int mat = s_m[(step & (DQ - 1)) * PS + t];
+            const double qv = s_q[(step & (DQ - 1)) * PS + t];
             const double* rbuf = bufs + ((step - 1) & (D - 1)) * ROWS;
             double* wbuf = bufs + (step & (D - 1)) * ROWS + t;
             const double* r0 = rbuf + off0;
@@ -857,18 +886,18 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
                   if (lastA) {
                      tagB = mat;
 #pragma unroll
-                     for (int d = 0; d < DT; d++) invB[d] = fast_rcp(st + so[d] + s_mw[d].x);
+                     for (int d = 0; d < DT; d++) invB[d] = fast_rcp(st + so[d] + dirs.mw[cslot][d].x);
                   } else {
                      tagA = mat;
 #pragma unroll
-                     for (int d = 0; d < DT; d++) invA[d] = fast_rcp(st + so[d] + s_mw[d].x);
+                     for (int d = 0; d < DT; d++) invA[d] = fast_rcp(st + so[d] + dirs.mw[cslot][d].x);
                   }
                }
                const bool useA = (mat == tagA);
                lastA = useA;
 #pragma unroll
                for (int d = 0; d < DT; d++) {
-                  const double2 mw = s_mw[d];
+                  const double2 mw = dirs.mw[cslot][d];
                   double acc = fma(mw.x, psiz[d], qv);
                   acc = fma(a0[d], r0[d * PSXS], acc);
                   acc = fma(a1[d], r1[d * PSXS], acc);
@@ -882,7 +911,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
                const double idz = s_idz[k];
 #pragma unroll
                for (int d = 0; d < DT; d++) {
-                  const double2 mw = s_mw[d];
+                  const double2 mw = dirs.mw[cslot][d];
                   const double az = mw.x * idz;
                   double acc = fma(az, psiz[d], qv);
                   acc = fma(a0[d], r0[d * PSXS], acc);
@@ -917,7 +946,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
             }
             k += kdir;
          }
-         if (!(gp.dbg & 2)) fence_proxy_async_smem();  // my row entries -> visible to the bulk store
+         fence_proxy_async_smem();                     // my row entries -> visible to the bulk store
          __syncthreads();
       }
    } else {
@@ -959,19 +988,37 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
                          gp.bnd_old + (((int64_t)ch->mrefl[d][ax] * gp.G + g) * nz + kk) * gp.nrf + rf);
          }
       };
+      // q and material rows of a step: two bulk copies (2 KB + 1 KB) counted on the step's mbarrier
+      const double* q_rows = cl->q_sheared + ((int64_t)g * npatch * NS + prow) * PS;
+      const int32_t* m_rows = cl->mats_s + prow * PS;
+      auto stage_rows = [&](int st) {
+         if (hl != 0 || st >= nsteps) return;
+         uint64_t* bar = &s_bar[st & (DQ - 1)];
+         mbar_expect_tx(bar, PS * (sizeof(double) + sizeof(int32_t)));
+         bulk_load(s_q + (st & (DQ - 1)) * PS, q_rows + (int64_t)st * PS, PS * sizeof(double), bar);
+         bulk_load(s_m + (st & (DQ - 1)) * PS, m_rows + (int64_t)st * PS, PS * sizeof(int32_t), bar);
+      };
+#pragma unroll
+      for (int st = 0; st < PFQ; st++) stage_rows(st);
 #pragma unroll
       for (int st = 0; st < PFD; st++) {
          stage_halo(st);
          cp_async_commit();
       }
       cp_async_wait_group<PFD - 1>();                  // halo of step 0 has landed
+      if (hl == 0) mbar_wait(&s_bar[0], 0);            // and its q / material rows
       __syncthreads();                                 // (B)
       double* psi_rows = psi_gl + prow * ROWG;
+      const int pub = (gp.dbg >> 4) ? (gp.dbg >> 4) : 2;
       for (int step = 0; step < nsteps; step++) {
+         stage_rows(step + PFQ);                       // ring slot (step-2)&7: read by the lanes at step - 2
          stage_halo(step + PFD);
          cp_async_commit();
          cp_async_wait_group<PFD - 1>();               // halo of step + 1 has landed
-         if (hl == 0) bulk_wait_read<D - 2>();         // buffer (step+1)&3 is free to be rewritten
+         if (hl == 0) {
+            if (step + 1 < nsteps) mbar_wait(&s_bar[(step + 1) & (DQ - 1)], ((step + 1) / DQ) & 1);
+            bulk_wait_read<D - 2>();                   // buffer (step+1)&3 is free to be rewritten
+         }
          __syncthreads();                              // end of step: row `step` is complete in smem
          if (hl == 0) {
             const double* src = bufs + (step & (D - 1)) * ROWS;
@@ -979,12 +1026,15 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
 #pragma unroll
             for (int d = 0; d < DT; d++) bulk_store(dst + d * PSX, src + d * PSXS, PSX * sizeof(double));
             bulk_commit();
-            // publish every `pub` steps: the wait + fence + release chain costs about half a step
-            const int pub = (gp.dbg >> 4) ? (gp.dbg >> 4) : 8;
+            // Publish two rows behind the store, so that the wait finds the copies already landed.
+            // The flag is a relaxed store: wait_group (without .read) returns once the bulk copies
+            // are complete -- written and acknowledged by L2 -- and the flag is issued after that, to the
+            // same point of coherence the reader's ld.acquire.gpu goes to.  A st.release.gpu here
+            // (MEMBAR.GPU under full store load) costs about one pipeline step: 29.1 instead of 24.1 ms
+            // per sweep when publishing every 4th step.
             if ((step % pub) == pub - 1) {
-               bulk_wait<1>();                         // rows < step are in global memory
-               fence_proxy_async_all();
-               st_release_gpu(my_progress, step);
+               bulk_wait<2>();                         // rows < step - 1 are in global memory
+               asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(my_progress), "r"(step - 1) : "memory");
             }
          }
          __syncwarp();
@@ -999,32 +1049,37 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
 
 template <int DT>
 static void launch_flow_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, bool extras, int* ticket,
-                           int* progress, cudaStream_t st) {
-   const size_t smem = ((size_t)TILE_D * DT * PSXS + TILE_D * PS + (TILE_D * PS) / 2 + 4 * DT + gp.nz + gp.nmat) *
+                           int* progress, const double* mw_host, int nch, cudaStream_t st) {
+   const size_t smem = ((size_t)TILE_D * DT * PSXS + FLOW_DQ * PS + (FLOW_DQ * PS) / 2 + 4 * DT + gp.nz + gp.nmat) *
                        sizeof(double);
+   FlowDirs<DT> dirs;
+   std::memset(&dirs, 0, sizeof(dirs));
+   for (int c = 0; c < nch && c < FlowDirs<DT>::MAXCH; c++)
+      for (int d = 0; d < DT; d++) dirs.mw[c][d] = make_double2(mw_host[(c * DT_MAX + d) * 2], mw_host[(c * DT_MAX + d) * 2 + 1]);
    if (gp.uniform_dz) {
-      if (extras) sn_sweep_flow_kernel<DT, true, true><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress);
-      else        sn_sweep_flow_kernel<DT, false, true><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress);
+      if (extras) sn_sweep_flow_kernel<DT, true, true><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
+      else        sn_sweep_flow_kernel<DT, false, true><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
    } else {
-      if (extras) sn_sweep_flow_kernel<DT, true, false><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress);
-      else        sn_sweep_flow_kernel<DT, false, false><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress);
+      if (extras) sn_sweep_flow_kernel<DT, true, false><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
+      else        sn_sweep_flow_kernel<DT, false, false><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
    }
 }
 
+// mw_host: [nch][DT_MAX][2] = {|mu_z| (/dz when uniform), weight} of the launch's chunks, by ChunkDev::flow_slot
 void launch_sweep_flow(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras, int* ticket,
-                       int* progress, cudaStream_t st) {
+                       int* progress, const double* mw_host, int nch, cudaStream_t st) {
    if (ntasks <= 0) return;
    switch (dt) {
-      case 1: launch_flow_dt<1>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
-      case 2: launch_flow_dt<2>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
-      case 3: launch_flow_dt<3>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
-      case 4: launch_flow_dt<4>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
-      case 5: launch_flow_dt<5>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
-      case 6: launch_flow_dt<6>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
-      case 7: launch_flow_dt<7>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
-      case 8: launch_flow_dt<8>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
-      case 9: launch_flow_dt<9>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
-      default: launch_flow_dt<10>(gp, d_tasks, ntasks, extras, ticket, progress, st); break;
+      case 1: launch_flow_dt<1>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
+      case 2: launch_flow_dt<2>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
+      case 3: launch_flow_dt<3>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
+      case 4: launch_flow_dt<4>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
+      case 5: launch_flow_dt<5>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
+      case 6: launch_flow_dt<6>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
+      case 7: launch_flow_dt<7>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
+      case 8: launch_flow_dt<8>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
+      case 9: launch_flow_dt<9>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
+      default: launch_flow_dt<10>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
    }
 }
 

@@ -54,6 +54,8 @@ struct ChunkDev {
    double mux[DT_MAX], muy[DT_MAX], muz_abs[DT_MAX], w[DT_MAX];
    double* psi;               // [Gown][npatch][nsteps][nd][PSX]
    double* phi_part;          // [Gown][npatch][nsteps][PS] sum_d w_d psi_d of this chunk (tile kernel)
+   int32_t flow_slot;         // index of this chunk in the direction table of its flow launch
+   int32_t pad_;
 };
 
 struct SweepGlobals {
@@ -103,7 +105,8 @@ void launch_sweep_tile(const SweepGlobals& gp, const Task* d_tasks, int ntasks, 
 // dataflow version of the tile kernel: one launch, tasks taken by ticket in topological order,
 // patch-to-patch dependencies through progress counters (see sn_kernels.cu)
 void launch_sweep_flow(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras, int* ticket,
-                       int* progress, cudaStream_t st);
+                       int* progress, const double* mw_host, int nch, cudaStream_t st);
+int flow_max_chunks(int dt);
 cudaError_t configure_flow_kernels();
 // base [g][k][slot] <-> step-major [g][patch][step][lane] transforms for the tile kernel
 void launch_shear_q(const SweepGlobals& gp, const ClassDev* d_classes, const int32_t* d_fast_classes,
