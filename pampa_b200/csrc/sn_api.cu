@@ -135,7 +135,7 @@ struct pampa_sn_handle {
       gp.Sb = plan.Sb; gp.G = G; gp.Gown = Gown; gp.M = M; gp.nz = plan.nz; gp.Kc = plan.Kc;
       gp.has_z = plan.has_z; gp.nrf = plan.num_rfaces; gp.nls = nls;
       gp.bcz_minus_refl = bcz_refl[0]; gp.bcz_plus_refl = bcz_refl[1];
-      gp.store_psi = 1;
+      gp.store_psi = opts.store_psi ? 1 : 0;
       gp.nmat = nmat;
       gp.uniform_dz = uniform_dz;
       { const char* e = std::getenv("PAMPA_SN_DBG"); gp.dbg = e ? std::atoi(e) : 0; }
@@ -412,7 +412,6 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
    if (opts) h->opts = *opts; else pampa_sn_default_options(&h->opts);
    if (!mesh || !xs || !quad) { h->err = "null input"; return fail(1); }
    if (h->opts.num_ranks < 1 || h->opts.rank < 0 || h->opts.rank >= h->opts.num_ranks) { h->err = "wrong rank"; return fail(1); }
-   if (h->opts.store_psi != 1) { h->err = "store_psi = 0 is not implemented"; return fail(1); }
    if (h->opts.patch_cells > PS) { h->err = "patch_cells must be <= 256"; return fail(1); }
    h->G = xs->num_groups; h->M = quad->num_directions; h->nmat = xs->num_materials;
    for (int64_t i = 0; i < (int64_t)mesh->num_layers * mesh->num_xy_cells; i++)
@@ -487,7 +486,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          if (chunk_owned[c]) {
             psi_off[c] = psi_doubles;
             const ClassPlan& cpc = pl.classes[pl.chunks[c].cls];
-            psi_doubles += (int64_t)pl.chunks[c].nd * h->Gown * cpc.npatch * cpc.nsteps * PSX;
+            psi_doubles += (int64_t)pl.chunks[c].nd * h->Gown * cpc.npatch * cpc.nsteps * (h->opts.store_psi ? PSX : PEDGE);
          }
       if (dev_alloc(h, &h->d_psi, psi_doubles)) return 1;
       SN_CUDA(h, cudaMemsetAsync(h->d_psi, 0, (size_t)psi_doubles * sizeof(double), h->stream));
@@ -701,6 +700,9 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          }
          all.insert(all.end(), tasks.begin(), tasks.end());
       }
+      if (!h->opts.store_psi && !h->groups.empty())
+         SN_FAIL(h, "store_psi = 0 needs every ordering class on the dataflow tile kernel (Cartesian mesh, no "
+                    "least-squares term, wave_launch = 0)");
       if (dev_upload(h, &h->d_chunks, chdev)) return 1;
       if (dev_upload(h, &h->d_tasks, all)) return 1;
       // reflective / LS problems read what another class wrote in the previous sweep only, so classes
@@ -1004,6 +1006,7 @@ int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
    const int64_t N = (int64_t)pl.nxy * pl.nz;
    const int64_t count = pampa_sn_field_size(h, name);
    if (count < 0) SN_FAIL(h, "unable to find field '" + s + "'");
+   if (s == "angular-flux" && !h->opts.store_psi) SN_FAIL(h, "the angular flux is not kept in memory (store_psi = 0)");
    if (s == "temperature" || s == "delayed-source") {
       std::vector<double>& v = s == "temperature" ? h->h_temperature : h->h_delayed;
       if (s == "delayed-source" && h->solved) {

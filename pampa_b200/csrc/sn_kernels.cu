@@ -797,7 +797,12 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
    __syncthreads();
 
    const int64_t prow = (int64_t)tk.patch * NS;       // first row of this patch in the step-major arrays
-   double* psi_gl = ch->psi + (int64_t)gl * npatch * NS * ROWG;
+   // psi rows in global memory: [DT][256 lanes | 32 edge copies], or the edge copies alone when the
+   // angular flux is not kept (store_psi = 0): only other patches read them
+   const int gstr = gp.store_psi ? PSX : PEDGE;       // direction stride of a global row
+   const int goff = gp.store_psi ? PS : 0;            // offset of the edge copies in it
+   const int rowg = DT * gstr;
+   double* psi_gl = ch->psi + (int64_t)gl * npatch * NS * rowg;
    const int kdir = zdir >= 0 ? 1 : -1;
    const int kstart = zdir >= 0 ? 0 : nz - 1;
    int* my_progress = progress + ((int64_t)tk.chunk * gp.Gown + gl) * npatch + tk.patch;
@@ -964,7 +969,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       if (kind == SRC_GLOBAL) {
          const int up = pay >> 8;
          const int dlv = (int)cl->lvl[pay] - rlv;
-         gsrc = psi_gl + ((int64_t)up * NS + dlv) * ROWG + PS + cl->eidx[pay];
+         gsrc = psi_gl + ((int64_t)up * NS + dlv) * rowg + goff + cl->eidx[pay];
          flag = progress + ((int64_t)tk.chunk * gp.Gown + gl) * npatch + up;
          need0 = dlv + 1;
       } else if (kind == SRC_REFL) {
@@ -979,7 +984,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
             const int need = st + need0;
             if (!(gp.dbg & 1)) while (seen < need) seen = ld_acquire_gpu(flag);
 #pragma unroll
-            for (int d = 0; d < DT; d++) cp_async8(dst + d * PSXS, gsrc + (int64_t)st * ROWG + d * PSX);
+            for (int d = 0; d < DT; d++) cp_async8(dst + d * PSXS, gsrc + (int64_t)st * rowg + d * gstr);
          } else if (EXTRAS) {
             const int kk = kstart + klt * kdir;
 #pragma unroll
@@ -1008,7 +1013,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       cp_async_wait_group<PFD - 1>();                  // halo of step 0 has landed
       if (hl == 0) mbar_wait(&s_bar[0], 0);            // and its q / material rows
       __syncthreads();                                 // (B)
-      double* psi_rows = psi_gl + prow * ROWG;
+      double* psi_rows = psi_gl + prow * rowg;
       const int pub = (gp.dbg >> 4) ? (gp.dbg >> 4) : 2;
       for (int step = 0; step < nsteps; step++) {
          stage_rows(step + PFQ);                       // ring slot (step-2)&7: read by the lanes at step - 2
@@ -1021,10 +1026,11 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
          }
          __syncthreads();                              // end of step: row `step` is complete in smem
          if (hl == 0) {
-            const double* src = bufs + (step & (D - 1)) * ROWS;
-            double* dst = psi_rows + (int64_t)step * ROWG;
+            const double* src = bufs + (step & (D - 1)) * ROWS + (PS - goff);
+            double* dst = psi_rows + (int64_t)step * rowg;
+            const unsigned bytes = gstr * sizeof(double);
 #pragma unroll
-            for (int d = 0; d < DT; d++) bulk_store(dst + d * PSX, src + d * PSXS, PSX * sizeof(double));
+            for (int d = 0; d < DT; d++) bulk_store(dst + d * gstr, src + d * PSXS, bytes);
             bulk_commit();
             // Publish two rows behind the store, so that the wait finds the copies already landed.
             // The flag is a relaxed store: wait_group (without .read) returns once the bulk copies

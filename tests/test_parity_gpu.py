@@ -78,17 +78,24 @@ def test_single_sweep_cartesian_3d():
     qd = np.einsum("nfg,nf->ng", op.sig_s, phi0) + op.chi * np.sum(op.nusf * phi0, axis=1)[:, None] / keff
     b = np.repeat((qd * op.vol[:, None]).reshape(N * G), M)
     psi = spla.splu(op.T.tocsc()).solve(b).reshape(N, G, M)
-    for opts in ({}, {"z_chunk": 4}, {"tile_i": 8, "tile_j": 4}, {"generic_only": 1}, {"dt_max": 2, "z_chunk": 3},
-                 {"dt_max": 3, "generic_only": 1}):
+    # default = dataflow tile kernel; wave_launch = one launch per wavefront (old tile kernel); z_chunk and
+    # generic_only = the general kernel; store_psi = 0 keeps only the patch-edge copies of psi
+    for opts in ({}, {"wave_launch": 1}, {"z_chunk": 4}, {"tile_i": 8, "tile_j": 4}, {"generic_only": 1},
+                 {"dt_max": 2, "z_chunk": 3}, {"dt_max": 3, "generic_only": 1}, {"dt_max": 4}, {"store_psi": 0},
+                 {"store_psi": 0, "tile_i": 8, "tile_j": 8}):
         dev = pb.SNDevice(em, xs, quad, **opts)
         dev.set("flux-moments", phi0.reshape(-1))
         dev.source(keff)
         dev.sweep()
         dev.reduce()
-        got_psi = dev.get("angular-flux").reshape(N, G, M)
         got_phi = dev.get("flux-moments").reshape(N, G)
-        assert util.rel_l2(got_psi, psi) < 1e-12
         assert util.max_rel(got_phi, psi @ op.w) < 1e-11
+        if opts.get("store_psi", 1):
+            got_psi = dev.get("angular-flux").reshape(N, G, M)
+            assert util.rel_l2(got_psi, psi) < 1e-12
+        else:
+            with pytest.raises(pb.SNError, match="store_psi"):
+                dev.get("angular-flux")
         dev.close()
 
 
