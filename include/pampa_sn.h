@@ -111,6 +111,8 @@ typedef struct {
                                     (0: default 7, < 0: plain power iteration) */
    int32_t wave_launch;          /* 1: sweep the tile classes with one launch per wavefront instead of the
                                     single dataflow launch (A/B testing) */
+   int32_t group_merge;          /* energy groups a dataflow sweep task handles back to back (0: default 4);
+                                    more groups = less pipeline fill/drain padding in the step-major arrays */
 } pampa_sn_options;
 
 void pampa_sn_default_options(pampa_sn_options* opts);
@@ -170,6 +172,8 @@ typedef struct {
    int64_t device_bytes;
    double  last_sweep_ms, last_source_ms, last_reduce_ms;
    int64_t kernel_launches;          /* total launches issued by this handle */
+   double  timed_kernel_ms;          /* last pampa_sn_iterate_timed: device time of the sweep-kernel launches
+                                        alone (between the shear and un-shear passes), summed over iterations */
 } pampa_sn_info;
 int pampa_sn_get_info(pampa_sn_handle* h, pampa_sn_info* info);
 

@@ -43,14 +43,14 @@ class Options(C.Structure):
     _fields_ = [("device", i32), ("store_psi", i32), ("patch_cells", i32), ("tile_i", i32), ("tile_j", i32),
                 ("z_chunk", i32), ("rank", i32), ("num_ranks", i32), ("shard_mode", i32), ("verbose", i32),
                 ("dt_max", i32), ("generic_only", i32), ("single_stream", i32),
-                ("anderson_depth", i32), ("wave_launch", i32)]
+                ("anderson_depth", i32), ("wave_launch", i32), ("group_merge", i32)]
 
 
 class Info(C.Structure):
     _fields_ = [("num_cells", i64), ("num_groups", i64), ("num_directions", i64), ("updates_per_sweep", i64),
                 ("sweep_launches", i64), ("sweep_tasks", i64), ("num_classes", i64), ("num_chunks", i64),
                 ("tile_classes", i64), ("device_bytes", i64), ("last_sweep_ms", f64), ("last_source_ms", f64),
-                ("last_reduce_ms", f64), ("kernel_launches", i64)]
+                ("last_reduce_ms", f64), ("kernel_launches", i64), ("timed_kernel_ms", f64)]
 
 
 # every symbol include/pampa_sn.h declares: name -> (restype, argtypes)

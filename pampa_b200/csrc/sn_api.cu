@@ -111,6 +111,8 @@ struct pampa_sn_handle {
    std::vector<char> class_fast;
    int32_t *d_fast_classes = nullptr, *d_fast_chunks = nullptr;
    int nfast_classes = 0, nfast_chunks = 0;
+   int gm = 1;                           // owned groups per block of the step-major arrays (sn_kernels.cuh)
+   int32_t* d_gown = nullptr;            // [Gown] group of a local index
 
    // iteration state
    ReduceScalars sc{};
@@ -122,12 +124,16 @@ struct pampa_sn_handle {
    double keff = 1.0;
    bool solved = false;
    double last_sweep_ms = 0, last_source_ms = 0, last_reduce_ms = 0;
+   // pampa_sn_iterate_timed: events around the sweep-kernel launches alone (after the shear pass,
+   // before the un-shear pass), one pair per iteration
+   std::vector<cudaEvent_t>* kernel_events = nullptr;
+   double timed_kernel_ms = 0;
    std::vector<double> h_temperature, h_delayed;
    NcclComm comm = nullptr;
 
    SweepGlobals globals() const {
       SweepGlobals gp{};
-      gp.classes = d_classes; gp.chunks = d_chunks; gp.gloc = d_gloc; gp.q = d_q;
+      gp.classes = d_classes; gp.chunks = d_chunks; gp.gloc = d_gloc; gp.gown = d_gown; gp.gm = gm; gp.q = d_q;
       gp.phi_new = d_phi_new; gp.mats = d_mats; gp.sigma_t = d_sig_t; gp.inv_dz = d_inv_dz;
       gp.bnd_old = d_bnd[bnd_cur]; gp.bnd_new = d_bnd[1 - bnd_cur];
       gp.bndz_old = d_bndz[bnd_cur]; gp.bndz_new = d_bndz[1 - bnd_cur];
@@ -235,6 +241,9 @@ int do_sweep(pampa_sn_handle* h) {
       // tickets and progress counters of the dataflow launches start from zero every sweep
       cudaMemsetAsync(h->d_flow_ctl, 0, (size_t)h->flow_ctl_count * sizeof(int), h->stream);
    }
+   if (h->kernel_events) {
+      cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); h->kernel_events->push_back(e);
+   }
    if (ns) {
       cudaEventRecord(h->ev_fork, h->stream);
       for (int i = 0; i < ns; i++) cudaStreamWaitEvent(h->cls_stream[i], h->ev_fork, 0);
@@ -255,6 +264,9 @@ int do_sweep(pampa_sn_handle* h) {
    for (int i = 0; i < ns; i++) {
       cudaEventRecord(h->ev_join[i], h->cls_stream[i]);
       cudaStreamWaitEvent(h->stream, h->ev_join[i], 0);
+   }
+   if (h->kernel_events) {
+      cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); h->kernel_events->push_back(e);
    }
    if (h->nfast_chunks > 0) {
       launch_unshear_phi(gp, h->d_chunks, h->d_classes, h->d_fast_chunks, h->nfast_chunks, h->plan.npatch_b,
@@ -348,6 +360,7 @@ extern "C" {
 void pampa_sn_default_options(pampa_sn_options* o) {
    std::memset(o, 0, sizeof(*o));
    o->store_psi = 1;
+   o->group_merge = 0;
    o->num_ranks = 1;
 }
 
@@ -453,6 +466,22 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       h->gloc.assign(h->G, -1); h->Gown = 0;
       for (int g = 0; g < h->G; g++)
          if (h->opts.shard_mode != 1 || g % nr == rank) h->gloc[g] = h->Gown++;
+      {
+         std::vector<int32_t> gown;
+         for (int g = 0; g < h->G; g++) if (h->gloc[g] >= 0) gown.push_back(g);
+         if (dev_upload(h, &h->d_gown, gown)) return 1;
+      }
+      // Groups per block of the step-major arrays = groups a dataflow task sweeps back to back.  More
+      // groups: less pipeline fill / drain padding (max local levels - 1 rows per block); fewer, longer
+      // tasks: a longer tail at the end of the launch.  The sigma_t table of a block lives in shared memory.
+      h->gm = 1;
+      if (!h->opts.wave_launch && pl.nzc == 1 && pl.tile_classes > 0) {
+         int gm = h->opts.group_merge > 0 ? h->opts.group_merge : 4;
+         gm = std::min(gm, std::max(1, 2048 / std::max(1, h->nmat)));
+         h->gm = std::max(1, std::min(gm, h->Gown));
+      }
+      const int gm = h->gm, nblk = (h->Gown + gm - 1) / gm;
+      auto nsm_of = [&](const ClassPlan& cp) { return cp.nsteps + (gm - 1) * pl.nz; };
       std::vector<char> chunk_owned(pl.chunks.size(), 1);
       if (h->opts.shard_mode != 1)
          for (size_t c = 0; c < pl.chunks.size(); c++) chunk_owned[c] = ((int)(c % nr) == rank);
@@ -486,7 +515,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          if (chunk_owned[c]) {
             psi_off[c] = psi_doubles;
             const ClassPlan& cpc = pl.classes[pl.chunks[c].cls];
-            psi_doubles += (int64_t)pl.chunks[c].nd * h->Gown * cpc.npatch * cpc.nsteps * (h->opts.store_psi ? PSX : PEDGE);
+            psi_doubles += (int64_t)pl.chunks[c].nd * nblk * cpc.npatch * nsm_of(cpc) * (h->opts.store_psi ? PSX : PEDGE);
          }
       if (dev_alloc(h, &h->d_psi, psi_doubles)) return 1;
       SN_CUDA(h, cudaMemsetAsync(h->d_psi, 0, (size_t)psi_doubles * sizeof(double), h->stream));
@@ -541,13 +570,13 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       // classes
       std::vector<ClassDev> cdev(pl.classes.size());
       h->class_fast.assign(pl.classes.size(), 0);
-      int fast_chunk_count[2] = {0, 0};
+      int fast_chunk_count[2] = {0, 0}, fast_class_count[2] = {0, 0};
       h->d_pos_of.assign(pl.classes.size(), nullptr);
       for (size_t ci = 0; ci < pl.classes.size(); ci++) {
          const ClassPlan& cp = pl.classes[ci];
          ClassDev& cd = cdev[ci];
          cd.S = cp.S; cd.zdir = cp.zdir; cd.ring = cp.ring; cd.tiles = cp.tiles ? 1 : 0; cd.npatch = cp.npatch;
-         cd.nsteps = cp.nsteps; cd.pad = 0;
+         cd.nsteps = cp.nsteps; cd.gm = gm; cd.nsm = nsm_of(cp); cd.pad = 0; cd.mats_c = nullptr;
          {  // material map in the class's (patch, pipeline step, lane) order
             std::vector<int32_t> ms((size_t)cp.npatch * cp.nsteps * PS, -1);
             for (int64_t sl = 0; sl < cp.S; sl++) {
@@ -586,13 +615,30 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
             int& cnt = fast_chunk_count[cp.zdir >= 0 ? 0 : 1];
             int mine = 0;
             for (size_t c = 0; c < pl.chunks.size(); c++) mine += (pl.chunks[c].cls == (int)ci && chunk_owned[c]);
-            if (cnt + mine > SHEAR_MAX_PER_PASS) h->class_fast[ci] = 0; else cnt += mine;
+            int& ccnt = fast_class_count[cp.zdir >= 0 ? 0 : 1];
+            if (cnt + mine > SHEAR_MAX_PER_PASS || ccnt + 1 > shear_max_classes()) h->class_fast[ci] = 0;
+            else { cnt += mine; ccnt++; }
          }
          if (h->class_fast[ci]) {
             double* d_qs;
-            if (dev_alloc(h, &d_qs, (int64_t)h->G * cp.npatch * cp.nsteps * PS)) return 1;
-            SN_CUDA(h, cudaMemsetAsync(d_qs, 0, (size_t)h->G * cp.npatch * cp.nsteps * PS * sizeof(double), h->stream));
+            const int64_t nq = (int64_t)nblk * cp.npatch * nsm_of(cp) * PS;
+            if (dev_alloc(h, &d_qs, nq)) return 1;
+            SN_CUDA(h, cudaMemsetAsync(d_qs, 0, (size_t)nq * sizeof(double), h->stream));
             cd.q_sheared = d_qs;
+            // material map of the dataflow kernel, cyclic in the pipeline step: the lane at level l
+            // is at layer (step - l) mod nz of some group of its block
+            std::vector<int32_t> mc((size_t)cp.npatch * nz * PS, -1);
+            for (int64_t sl = 0; sl < cp.S; sl++) {
+               if (cp.cell_of[sl] < 0) continue;
+               const int64_t p = sl / PS, lane = sl % PS;
+               for (int kp = 0; kp < nz; kp++) {
+                  const int k = cp.zdir >= 0 ? kp : nz - 1 - kp;
+                  mc[((size_t)p * nz + (kp + cp.lvl[sl]) % nz) * PS + lane] = mats[(size_t)k * Sb + cp.cell_of[sl]];
+               }
+            }
+            int32_t* d_mc;
+            if (dev_upload(h, &d_mc, mc)) return 1;
+            cd.mats_c = d_mc;
          }
          cd.cell_of = d_cell_of; cd.lvl = d_lvl; cd.patch_nlev = d_patch_nlev;
          cd.out_vec = (const double2*)d_out_vec; cd.in_src = d_in_src; cd.in_vec = (const double2*)d_in_vec;
@@ -624,7 +670,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          cd.phi_part = nullptr;
          if (chunk_owned[c] && h->class_fast[ch.cls]) {
             const ClassPlan& cpc = pl.classes[ch.cls];
-            if (dev_alloc(h, &cd.phi_part, (int64_t)h->Gown * cpc.npatch * cpc.nsteps * PS)) return 1;
+            if (dev_alloc(h, &cd.phi_part, (int64_t)nblk * cpc.npatch * nsm_of(cpc) * PS)) return 1;
             fast_chunks.push_back((int32_t)c);
          }
       }
@@ -660,7 +706,8 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
             const size_t first = all.size();
             for (size_t w = 0; w < pl.waves.size(); w++)
                for (const Task& t : pl.waves[w])
-                  if (h->class_fast[pl.chunks[t.chunk].cls] && pl.chunks[t.chunk].nd == dt) all.push_back(t);
+                  if (h->class_fast[pl.chunks[t.chunk].cls] && pl.chunks[t.chunk].nd == dt && h->gloc[t.group] % gm == 0)
+                     all.push_back(Task{t.chunk, h->gloc[t.group] / gm, t.patch, 0});   // group field = block
             if (all.size() > first) {
                if (h->flows.size() >= 16) SN_FAIL(h, "internal: too many dataflow launches");
                FlowLaunch fl{dt, (int64_t)first, (int)(all.size() - first), {}, 0};
@@ -676,7 +723,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
             }
          }
          if (!h->flows.empty()) {
-            h->flow_ctl_count = 16 + (int64_t)pl.chunks.size() * h->Gown * pl.npatch_b;
+            h->flow_ctl_count = 16 + (int64_t)pl.chunks.size() * nblk * pl.npatch_b;
             if (dev_alloc(h, &h->d_flow_ctl, h->flow_ctl_count)) return 1;
          }
       }
@@ -806,7 +853,9 @@ int pampa_sn_iterate_timed(pampa_sn_handle* h, int32_t iterations, double* keff,
    std::vector<cudaEvent_t> ev(2 * (size_t)iterations + 2);
    for (auto& e : ev) SN_CUDA(h, cudaEventCreate(&e));
    int rc = 0;
+   std::vector<cudaEvent_t> kev;
    SN_CUDA(h, cudaStreamSynchronize(h->stream));
+   h->kernel_events = &kev;
    cudaEventRecord(ev[0], h->stream);
    for (int it = 0; it < iterations && !rc; it++) {
       rc = do_source(h);
@@ -816,7 +865,13 @@ int pampa_sn_iterate_timed(pampa_sn_handle* h, int32_t iterations, double* keff,
       if (!rc) rc = do_reduce(h, 1);
    }
    cudaEventRecord(ev[1], h->stream);
+   h->kernel_events = nullptr;
    if (!rc) rc = sync_scalars(h);
+   h->timed_kernel_ms = 0;
+   for (size_t i = 0; i + 1 < kev.size() && !rc; i += 2) {
+      float t = 0; cudaEventElapsedTime(&t, kev[i], kev[i + 1]); h->timed_kernel_ms += t;
+   }
+   for (auto& e : kev) cudaEventDestroy(e);
    if (!rc) {
       float ms = 0, sw = 0, t = 0;
       cudaEventElapsedTime(&ms, ev[0], ev[1]);
@@ -1141,6 +1196,7 @@ int pampa_sn_get_info(pampa_sn_handle* h, pampa_sn_info* info) {
    info->num_classes = (int64_t)pl.classes.size(); info->num_chunks = (int64_t)pl.chunks.size();
    info->tile_classes = pl.tile_classes;
    info->device_bytes = h->device_bytes;
+   info->timed_kernel_ms = h->timed_kernel_ms;
    info->last_sweep_ms = h->last_sweep_ms; info->last_source_ms = h->last_source_ms;
    info->last_reduce_ms = h->last_reduce_ms;
    info->kernel_launches = h->launches;

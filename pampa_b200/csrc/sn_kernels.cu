@@ -71,7 +71,7 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    const int kfirst = zdir >= 0 ? kp0 : nz - 1 - kp0;
    const int NS = cl->nsteps;
    constexpr int kstride_psi = DT * PSX;
-   double* psi_w = ch->psi + ((((int64_t)gl * npatch + tk.patch) * NS + kp0 + (valid ? lv : 0)) * DT) * PSX + t;
+   double* psi_w = ch->psi + ((block_row0(gl, tk.patch, npatch, cl->nsm, cl->gm, nz) + kp0 + (valid ? lv : 0)) * DT) * PSX + t;
    const int32_t* mats_w = cl->mats_s + ((int64_t)tk.patch * NS + kp0 + (valid ? lv : 0)) * PS + t;
 #pragma unroll
    for (int s = 0; s < FIN; s++) {
@@ -82,7 +82,7 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
       const int pay = src[s] & SRC_PAYLOAD;
       gsrc[s] = ch->psi;
       if (src[s] >= 0 && (src[s] >> SRC_KIND_SHIFT) == SRC_GLOBAL)
-         gsrc[s] += ((((int64_t)gl * npatch + (pay >> 8)) * NS + kp0 + cl->lvl[pay]) * DT) * PSX + (pay & (PS - 1));
+         gsrc[s] += ((block_row0(gl, pay >> 8, npatch, cl->nsm, cl->gm, nz) + kp0 + cl->lvl[pay]) * DT) * PSX + (pay & (PS - 1));
    }
    int rout[ROUT_MAX];
    int lsb = -1;
@@ -413,7 +413,6 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
       }
       const int c0 = cl->in_src[slot];
       const int c1 = cl->in_src[S + slot];
-      const double* psi_gl = ch->psi + (int64_t)gl * npatch * NS * ROW;
       if (c0 >= 0) {
          kind0 = c0 >> SRC_KIND_SHIFT;
          const int pay = c0 & SRC_PAYLOAD;
@@ -421,7 +420,7 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
          else {
             off0 = PS + cl->in_hidx[slot];
             if (kind0 == SRC_GLOBAL)
-               g0 = psi_gl + ((int64_t)(pay >> 8) * NS + kp0 + (int)cl->lvl[pay] - lv0) * ROW + PS + cl->eidx[pay];
+               g0 = ch->psi + (block_row0(gl, pay >> 8, npatch, cl->nsm, cl->gm, nz) + kp0 + (int)cl->lvl[pay] - lv0) * ROW + PS + cl->eidx[pay];
             else { ax0 = pay >> SRC_AXIS_SHIFT; rf0 = pay & ((1 << SRC_AXIS_SHIFT) - 1); }
          }
       }
@@ -432,7 +431,7 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
          else {
             off1 = PS + cl->in_hidx[S + slot];
             if (kind1 == SRC_GLOBAL)
-               g1 = psi_gl + ((int64_t)(pay >> 8) * NS + kp0 + (int)cl->lvl[pay] - lv0) * ROW + PS + cl->eidx[pay];
+               g1 = ch->psi + (block_row0(gl, pay >> 8, npatch, cl->nsm, cl->gm, nz) + kp0 + (int)cl->lvl[pay] - lv0) * ROW + PS + cl->eidx[pay];
             else { ax1 = pay >> SRC_AXIS_SHIFT; rf1 = pay & ((1 << SRC_AXIS_SHIFT) - 1); }
          }
       }
@@ -449,11 +448,11 @@ sn_sweep_tile_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
    }
 
    // global rows of pipeline step 0 of this task; step s is s rows further
-   const int64_t prow = (int64_t)tk.patch * NS + kp0;
-   double* psi_row = ch->psi + ((int64_t)gl * npatch * NS + prow) * ROW + t;
-   const int32_t* m_row = cl->mats_s + prow * PS + t;
-   const double* q_row = cl->q_sheared + ((int64_t)g * npatch * NS + prow) * PS + t;
-   double* ph_row = ch->phi_part + ((int64_t)gl * npatch * NS + prow) * PS + t;
+   const int64_t prow = block_row0(gl, tk.patch, npatch, cl->nsm, cl->gm, nz) + kp0;
+   double* psi_row = ch->psi + prow * ROW + t;
+   const int32_t* m_row = cl->mats_s + ((int64_t)tk.patch * NS + kp0) * PS + t;
+   const double* q_row = cl->q_sheared + prow * PS + t;
+   double* ph_row = ch->phi_part + prow * PS + t;
    const int cell = (int)slot;                         // tile classes: class slot == base slot
    const int kdir = zdir >= 0 ? 1 : -1;
    const int kstart = zdir >= 0 ? kp0 : nz - 1 - kp0;
@@ -668,18 +667,21 @@ cudaError_t configure_tile_kernels() {
 // instead of a whole task (246 steps at 216 layers): no wavefront tails on one GPU, and a critical
 // path ~9x shorter when the sweep is sharded over GPUs.
 //
-// Roles (warp specialisation, 288 threads): warps 0-7 are the 256 lanes of the patch and never touch
+// Roles (warp specialisation, 320 threads): warps 0-7 are the 256 lanes of the patch and never touch
 // psi in global memory; warp 8 is the producer:
 //   * its 32 lanes own the 32 halo entries of the patch (values read from another patch's edge
 //     copies, or from the mirrored direction of a reflective face): poll the upwind task's progress
 //     counter (ld.acquire.gpu), then cp.async the DT values PFD steps ahead of their use;
-//   * lane 0 stores the finished psi row -- the shared-memory buffer of the step IS the global row
-//     [DT][256 lanes | 32 edge copies] -- with DT bulk async copies (cp.async.bulk, async proxy) and
-//     publishes the progress counter (st.release.gpu) once the copies of the previous step have landed.
+//   * lane 0 loads the q / material rows of a step with bulk async copies counted on an mbarrier;
+// and one thread of warp 9 is the store thread: it hands the finished psi row -- the shared-memory
+// buffer of the step IS the global row [DT][256 lanes | 32 edge copies] -- to the copy engine (DT
+// cp.async.bulk) and publishes the progress counter (fence.proxy.async + st.release.gpu).  It is tied
+// to the pipeline by two shared-memory counters instead of the per-step barrier, so the fences'
+// latency (they wait for the stores in flight) stays off the lanes' critical path.
 // The LSU pipe was the limiter of the per-lane version (81 % busy: 2 LDS + STS + STG per update, all
 // 64-bit); the row stores and halo loads are ~30 % of its wavefronts.
 constexpr int PSXS = PS + 2 * PEDGE;       // smem row: 256 ring lanes | 32 edge copies (out) | 32 halo (in)
-constexpr int FLOW_THREADS = PS + 32;
+constexpr int FLOW_THREADS = PS + 64;       // 8 lane warps + producer warp + store warp
 constexpr int FLOW_DQ = 8, FLOW_PFQ = 6;    // q / material row ring: depth and prefetch distance (steps)
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -737,7 +739,8 @@ __device__ __forceinline__ int ld_acquire_cta_smem(const int* p) {
 __device__ __forceinline__ void st_release_cta_smem(int* p, int v) {
    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
-__device__ __forceinline__ void lanes_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// barrier of the pipeline warps (lanes + producer); the store warp stays outside
+__device__ __forceinline__ void pipe_barrier() { asm volatile("bar.sync 1, 288;" ::: "memory"); }
 
 struct HaloEntry { int32_t code; int32_t lv; };      // upwind source code and level of the reading lane
 
@@ -753,6 +756,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
    __shared__ int s_task;
    __shared__ HaloEntry s_halo[PEDGE];
    __shared__ __align__(8) uint64_t s_bar[FLOW_DQ];   // q / material rows of a step have landed
+   __shared__ int s_rows_done, s_rows_read;           // rows complete in smem / rows the copy engine has read
    const int t = threadIdx.x;
    if (t == 0) {
       s_task = atomicAdd(ticket, 1);
@@ -761,23 +765,31 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    if (t < PEDGE) s_halo[t] = HaloEntry{-1, 0};
+   if (t == PEDGE) { s_rows_done = 0; s_rows_read = 0; }
    __syncthreads();
    const Task tk = tasks[s_task];
    const ChunkDev* __restrict__ ch = gp.chunks + tk.chunk;
    const ClassDev* __restrict__ cl = gp.classes + ch->cls;
    const int64_t S = cl->S;
-   const int g = tk.group;
-   const int gl = gp.gloc[g];
+   // a flow task sweeps the columns of one patch for every group of one block of owned groups, back
+   // to back: a lane starts the next group the step after it finishes the last layer of the previous
+   // one, so the pipeline is filled and drained once per task instead of once per group
+   const int gb = tk.group;                           // block of owned groups
+   const int gm = gp.gm;
+   const int ngr = min(gm, gp.Gown - gb * gm);        // groups in this block
+   const int nblk = (gp.Gown + gm - 1) / gm;
    const int nz = gp.nz;
+   const int nmat = gp.nmat;
    const int npatch = cl->npatch;
-   const int NS = cl->nsteps;
+   const int NS = cl->nsm;
    const int zdir = cl->zdir;
-   const int kcnt = nz;                               // the flow kernel never splits a column in z
+   const int kcnt = ngr * nz;                         // column updates of a lane (never split in z)
    const int nsteps = cl->patch_nlev[tk.patch] + kcnt - 1;
    const bool lane_thread = t < PS;
    const int64_t slot = (int64_t)tk.patch * PS + (lane_thread ? t : 0);
 
-   // smem: bufs[D][DT][PSXS] | q stage [DQ][PS] | material stage [DQ][PS] (int) | {muz,w}[DT] | mux,muy | idz | sigma_t
+   // smem: bufs[D][DT][PSXS] | q stage [DQ][PS] | material stage [DQ][PS] (int) | {muz,w}[DT] | mux,muy | idz |
+   //       sigma_t [gm][nmat] | group of a block-local index [gm] (int)
    double* bufs = smem;
    double* s_q = smem + D * ROWS;
    int* s_m = (int*)(s_q + DQ * PS);
@@ -786,9 +798,12 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
    double* s_muy = s_mux + DT;
    double* s_idz = s_muy + DT;
    double* s_sigt = s_idz + nz;
+   int* s_g = (int*)(s_sigt + gm * nmat);
    for (int a = t; a < D * ROWS; a += FLOW_THREADS) bufs[a] = 0.0;
    for (int kk = t; kk < nz; kk += FLOW_THREADS) s_idz[kk] = gp.has_z ? gp.inv_dz[kk] : 0.0;
-   for (int m = t; m < gp.nmat; m += FLOW_THREADS) s_sigt[m] = gp.sigma_t[m * gp.G + g];
+   for (int a = t; a < ngr * nmat; a += FLOW_THREADS)
+      s_sigt[a] = gp.sigma_t[(a % nmat) * gp.G + gp.gown[gb * gm + a / nmat]];
+   if (t < ngr) s_g[t] = gp.gown[gb * gm + t];
    if (t < DT) {
       s_mux[t] = ch->mux[t];
       s_muy[t] = ch->muy[t];
@@ -796,16 +811,16 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
    }
    __syncthreads();
 
-   const int64_t prow = (int64_t)tk.patch * NS;       // first row of this patch in the step-major arrays
+   const int64_t prow = ((int64_t)gb * npatch + tk.patch) * NS;   // first row of this (block, patch)
    // psi rows in global memory: [DT][256 lanes | 32 edge copies], or the edge copies alone when the
    // angular flux is not kept (store_psi = 0): only other patches read them
    const int gstr = gp.store_psi ? PSX : PEDGE;       // direction stride of a global row
    const int goff = gp.store_psi ? PS : 0;            // offset of the edge copies in it
    const int rowg = DT * gstr;
-   double* psi_gl = ch->psi + (int64_t)gl * npatch * NS * rowg;
+   double* psi_gl = ch->psi + (int64_t)gb * npatch * NS * rowg;
    const int kdir = zdir >= 0 ? 1 : -1;
    const int kstart = zdir >= 0 ? 0 : nz - 1;
-   int* my_progress = progress + ((int64_t)tk.chunk * gp.Gown + gl) * npatch + tk.patch;
+   int* my_progress = progress + ((int64_t)tk.chunk * nblk + gb) * npatch + tk.patch;
 
    if (lane_thread) {
       // ---------------------------------------------------------------- the 256 lanes of the patch
@@ -852,24 +867,31 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
 #pragma unroll
          for (int r = 0; r < ROUT_MAX; r++) rout[r] = valid ? cl->rout[(size_t)r * S + slot] : -1;
       }
-      double* ph_row = ch->phi_part + ((int64_t)gl * npatch * NS + prow) * PS + t;
+      double* ph_row = ch->phi_part + prow * PS + t;
       const int cell = (int)slot;                      // tile classes: class slot == base slot
 
+      // z-upwind start values of a column: zero (vacuum) or the mirrored direction of the last sweep
       double psiz[DT];
+      auto start_column = [&](int gi) {
 #pragma unroll
-      for (int d = 0; d < DT; d++) psiz[d] = 0.0;
-      if (EXTRAS && gp.has_z && valid) {
-         const int face = zdir > 0 ? 0 : 1;
-         if (face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl) {
+         for (int d = 0; d < DT; d++) psiz[d] = 0.0;
+         if (EXTRAS && gp.has_z && valid && gi < ngr) {
+            const int face = zdir > 0 ? 0 : 1;
+            if (face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl) {
+               const int g = s_g[gi];
 #pragma unroll
-            for (int d = 0; d < DT; d++)
-               psiz[d] = gp.bndz_old[(((int64_t)face * gp.M + ch->mrefl[d][2]) * gp.G + g) * gp.Sb + cell];
+               for (int d = 0; d < DT; d++)
+                  psiz[d] = gp.bndz_old[(((int64_t)face * gp.M + ch->mrefl[d][2]) * gp.G + g) * gp.Sb + cell];
+            }
          }
-      }
-      __syncthreads();                                 // (A) halo table complete -> producer warp
-      __syncthreads();                                 // (B) halo of step 0 staged by the producer warp
+      };
+      start_column(0);
+      pipe_barrier();                                  // (A) halo table complete -> producer warp
+      pipe_barrier();                                  // (B) halo of step 0 staged by the producer warp
 
       int k = kstart;
+      int kk = 0, gi = 0;                              // layers done in the current column, group of the block
+      const double* sigt = s_sigt;                     // sigma_t of the current group
       int tagA = -1, tagB = -1;                        // materials of the two cached reciprocal sets
       bool lastA = false;
       double invA[UNIFORM_DZ ? DT : 1], invB[UNIFORM_DZ ? DT : 1];
@@ -887,7 +909,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
             double ph = 0.0;
             if (UNIFORM_DZ) {
                if (mat != tagA && mat != tagB) {        // miss: rare once both materials of a column are seen
-                  const double st = s_sigt[mat];
+                  const double st = sigt[mat];
                   if (lastA) {
                      tagB = mat;
 #pragma unroll
@@ -912,7 +934,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
                   ph = fma(mw.y, v, ph);
                }
             } else {
-               const double st = s_sigt[mat];
+               const double st = sigt[mat];
                const double idz = s_idz[k];
 #pragma unroll
                for (int d = 0; d < DT; d++) {
@@ -933,6 +955,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
             }
             ph_row[(int64_t)step * PS] = ph;
             if (EXTRAS) {
+               const int g = s_g[gi];
 #pragma unroll
                for (int r = 0; r < ROUT_MAX; r++)
                   if (rout[r] >= 0) {
@@ -940,7 +963,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
                      for (int d = 0; d < DT; d++)
                         gp.bnd_new[(((int64_t)ch->m[d] * gp.G + g) * nz + k) * gp.nrf + rout[r]] = psiz[d];
                   }
-               if (gp.has_z && kl == nz - 1) {
+               if (gp.has_z && kk == nz - 1) {
                   const int face = zdir > 0 ? 1 : 0;
                   if (face == 0 ? gp.bcz_minus_refl : gp.bcz_plus_refl) {
 #pragma unroll
@@ -950,14 +973,19 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
                }
             }
             k += kdir;
+            if (++kk == nz) {                          // next group of the block: a fresh column
+               kk = 0; gi++; k = kstart; sigt += nmat;
+               tagA = -1; tagB = -1; lastA = false;
+               start_column(gi);
+            }
          }
          fence_proxy_async_smem();                     // my row entries -> visible to the bulk store
-         __syncthreads();
+         pipe_barrier();
       }
-   } else {
+   } else if (t < PS + 32) {
       // ---------------------------------------------------------------- producer warp
       const int hl = t - PS;                           // halo entry of this lane
-      __syncthreads();                                 // (A) halo table written by the lanes
+      pipe_barrier();                                  // (A) halo table written by the lanes
       const HaloEntry he = s_halo[hl];
       const int kind = he.code >= 0 ? (he.code >> SRC_KIND_SHIFT) : -1;
       const int pay = he.code & SRC_PAYLOAD;
@@ -970,7 +998,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
          const int up = pay >> 8;
          const int dlv = (int)cl->lvl[pay] - rlv;
          gsrc = psi_gl + ((int64_t)up * NS + dlv) * rowg + goff + cl->eidx[pay];
-         flag = progress + ((int64_t)tk.chunk * gp.Gown + gl) * npatch + up;
+         flag = progress + ((int64_t)tk.chunk * nblk + gb) * npatch + up;
          need0 = dlv + 1;
       } else if (kind == SRC_REFL) {
          ax = pay >> SRC_AXIS_SHIFT; rf = pay & ((1 << SRC_AXIS_SHIFT) - 1);
@@ -982,11 +1010,14 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
          double* dst = bufs + ((st - 1) & (D - 1)) * ROWS + PS + PEDGE + hl;
          if (kind == SRC_GLOBAL) {
             const int need = st + need0;
-            if (!(gp.dbg & 1)) while (seen < need) seen = ld_acquire_gpu(flag);
+            if (gp.dbg & 4) { do { seen = ld_acquire_gpu(flag); } while (seen < need); }
+            else if (!(gp.dbg & 1)) while (seen < need) seen = ld_acquire_gpu(flag);
 #pragma unroll
             for (int d = 0; d < DT; d++) cp_async8(dst + d * PSXS, gsrc + (int64_t)st * rowg + d * gstr);
          } else if (EXTRAS) {
-            const int kk = kstart + klt * kdir;
+            const int gi = klt / nz;
+            const int kk = kstart + (klt - gi * nz) * kdir;
+            const int g = s_g[gi];
 #pragma unroll
             for (int d = 0; d < DT; d++)
                cp_async8(dst + d * PSXS,
@@ -994,14 +1025,14 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
          }
       };
       // q and material rows of a step: two bulk copies (2 KB + 1 KB) counted on the step's mbarrier
-      const double* q_rows = cl->q_sheared + ((int64_t)g * npatch * NS + prow) * PS;
-      const int32_t* m_rows = cl->mats_s + prow * PS;
+      const double* q_rows = cl->q_sheared + prow * PS;
+      const int32_t* m_rows = cl->mats_c + (int64_t)tk.patch * nz * PS;   // cyclic in the step: row st mod nz
       auto stage_rows = [&](int st) {
          if (hl != 0 || st >= nsteps) return;
          uint64_t* bar = &s_bar[st & (DQ - 1)];
          mbar_expect_tx(bar, PS * (sizeof(double) + sizeof(int32_t)));
          bulk_load(s_q + (st & (DQ - 1)) * PS, q_rows + (int64_t)st * PS, PS * sizeof(double), bar);
-         bulk_load(s_m + (st & (DQ - 1)) * PS, m_rows + (int64_t)st * PS, PS * sizeof(int32_t), bar);
+         bulk_load(s_m + (st & (DQ - 1)) * PS, m_rows + (int64_t)(st % nz) * PS, PS * sizeof(int32_t), bar);
       };
 #pragma unroll
       for (int st = 0; st < PFQ; st++) stage_rows(st);
@@ -1012,9 +1043,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       }
       cp_async_wait_group<PFD - 1>();                  // halo of step 0 has landed
       if (hl == 0) mbar_wait(&s_bar[0], 0);            // and its q / material rows
-      __syncthreads();                                 // (B)
-      double* psi_rows = psi_gl + prow * rowg;
-      const int pub = (gp.dbg >> 4) ? (gp.dbg >> 4) : 2;
+      pipe_barrier();                                  // (B)
       for (int step = 0; step < nsteps; step++) {
          stage_rows(step + PFQ);                       // ring slot (step-2)&7: read by the lanes at step - 2
          stage_halo(step + PFD);
@@ -1022,42 +1051,54 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
          cp_async_wait_group<PFD - 1>();               // halo of step + 1 has landed
          if (hl == 0) {
             if (step + 1 < nsteps) mbar_wait(&s_bar[(step + 1) & (DQ - 1)], ((step + 1) / DQ) & 1);
-            bulk_wait_read<D - 2>();                   // buffer (step+1)&3 is free to be rewritten
+            // buffer (step+1)&3 is rewritten in the next step: its row, step - 3, must have left smem
+            while (ld_acquire_cta_smem(&s_rows_read) < step - 2) {}
          }
-         __syncthreads();                              // end of step: row `step` is complete in smem
-         if (hl == 0) {
-            const double* src = bufs + (step & (D - 1)) * ROWS + (PS - goff);
-            double* dst = psi_rows + (int64_t)step * rowg;
-            const unsigned bytes = gstr * sizeof(double);
-#pragma unroll
-            for (int d = 0; d < DT; d++) bulk_store(dst + d * gstr, src + d * PSXS, bytes);
-            bulk_commit();
-            // Publish two rows behind the store, so that the wait finds the copies already landed.
-            // The flag is a relaxed store: wait_group (without .read) returns once the bulk copies
-            // are complete -- written and acknowledged by L2 -- and the flag is issued after that, to the
-            // same point of coherence the reader's ld.acquire.gpu goes to.  A st.release.gpu here
-            // (MEMBAR.GPU under full store load) costs about one pipeline step: 29.1 instead of 24.1 ms
-            // per sweep when publishing every 4th step.
-            if ((step % pub) == pub - 1) {
-               bulk_wait<2>();                         // rows < step - 1 are in global memory
-               asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(my_progress), "r"(step - 1) : "memory");
-            }
-         }
+         pipe_barrier();                               // end of step: row `step` is complete in smem
+         if (hl == 0) st_release_cta_smem(&s_rows_done, step + 1);
          __syncwarp();
       }
-      if (hl == 0) {
-         bulk_wait<0>();
-         fence_proxy_async_all();
-         st_release_gpu(my_progress, nsteps);
+   } else if (t == PS + 32) {
+      // ---------------------------------------------------------------- store thread (warp 9)
+      // Hands every finished row to the copy engine and publishes the progress counter.  Completion
+      // of a bulk group makes its writes visible to the issuing thread only; another SM may read them
+      // after fence.proxy.async (async-proxy writes -> generic proxy) and a gpu-scope release of the
+      // counter.  Those fences wait for the stores still in flight (~1 pipeline step under full store
+      // load), which is why they live in a thread of their own, outside the per-step barrier: the
+      // pipeline only needs rows_read to stay within two steps of it.  (A relaxed counter store right
+      // after wait_group, without the fences, is a race: readers that followed the writer closely saw
+      // rows of the previous sweep.)
+      double* psi_rows = ch->psi + prow * rowg;
+      // publish every 8th row: the fences take longer than the two steps of slack the buffer ring gives
+      // (measured at C4: 22.7 / 19.1 / 17.7 ms per sweep publishing every 2nd / 4th / 8th row)
+      const int pub = ((gp.dbg >> 4) & 0xff) ? ((gp.dbg >> 4) & 0xff) : 8;
+      const unsigned bytes = gstr * sizeof(double);
+      for (int step = 0; step < nsteps; step++) {
+         while (ld_acquire_cta_smem(&s_rows_done) <= step) {}
+         const double* src = bufs + (step & (D - 1)) * ROWS + (PS - goff);
+         double* dst = psi_rows + (int64_t)step * rowg;
+#pragma unroll
+         for (int d = 0; d < DT; d++) bulk_store(dst + d * gstr, src + d * PSXS, bytes);
+         bulk_commit();
+         bulk_wait_read<1>();                          // rows < step have left shared memory
+         st_release_cta_smem(&s_rows_read, step);
+         if ((step % pub) == pub - 1 && step >= 2) {
+            bulk_wait<2>();                            // rows < step - 1 are complete
+            fence_proxy_async_all();
+            st_release_gpu(my_progress, step - 1);
+         }
       }
+      bulk_wait<0>();
+      fence_proxy_async_all();
+      st_release_gpu(my_progress, nsteps);
    }
 }
 
 template <int DT>
 static void launch_flow_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, bool extras, int* ticket,
                            int* progress, const double* mw_host, int nch, cudaStream_t st) {
-   const size_t smem = ((size_t)TILE_D * DT * PSXS + FLOW_DQ * PS + (FLOW_DQ * PS) / 2 + 4 * DT + gp.nz + gp.nmat) *
-                       sizeof(double);
+   const size_t smem = ((size_t)TILE_D * DT * PSXS + FLOW_DQ * PS + (FLOW_DQ * PS) / 2 + 4 * DT + gp.nz +
+                        (size_t)gp.gm * gp.nmat + (gp.gm + 1) / 2) * sizeof(double);
    FlowDirs<DT> dirs;
    std::memset(&dirs, 0, sizeof(dirs));
    for (int c = 0; c < nch && c < FlowDirs<DT>::MAXCH; c++)
@@ -1118,7 +1159,8 @@ cudaError_t configure_flow_kernels() {
 // column in a shared-memory ring and writes, for every class, the entry its level selects.  Every
 // global access is a full 2 KB row.
 constexpr int SHEAR_RING = 32;          // >= local levels of a patch (fast classes: <= 32)
-constexpr int SHEAR_MAXC = 32;          // fast classes / chunks per z direction handled per pass
+constexpr int SHEAR_MAXC = 8;           // fast classes per z direction (4 on Cartesian meshes; checked on the host)
+constexpr int SHEAR_U = 4;              // layers loaded ahead per thread (two batches in flight)
 
 struct ShearSmem {
    double ring[SHEAR_RING][PS];
@@ -1126,6 +1168,7 @@ struct ShearSmem {
    double* base[SHEAR_MAXC];
    int nc, maxlev;
 };
+int shear_max_classes() { return SHEAR_MAXC; }
 
 __global__ void __launch_bounds__(PS)
 sn_shear_q_kernel(const SweepGlobals gp, const ClassDev* __restrict__ classes,
@@ -1144,7 +1187,7 @@ sn_shear_q_kernel(const SweepGlobals gp, const ClassDev* __restrict__ classes,
       for (int c = 0; c < nfast && nc < SHEAR_MAXC; c++) {
          const ClassDev* cl = classes + fast_classes[c];
          if ((cl->zdir >= 0 ? 0 : 1) != zpass) continue;
-         sm.base[nc] = cl->q_sheared + ((int64_t)g * cl->npatch + patch) * cl->nsteps * PS;
+         sm.base[nc] = cl->q_sheared + block_row0(gp.gloc[g], patch, cl->npatch, cl->nsm, cl->gm, nz) * PS;
          maxlev = max(maxlev, cl->patch_nlev[patch]);
          nc++;
       }
@@ -1162,13 +1205,31 @@ sn_shear_q_kernel(const SweepGlobals gp, const ClassDev* __restrict__ classes,
    __syncthreads();
    const int nc = sm.nc;
    if (nc == 0) return;
-   const double* qg = gp.q + (int64_t)g * nz * gp.Sb + slot;
+   // the column of this thread, in sweep order; the loads run SHEAR_U..2*SHEAR_U layers ahead of the
+   // stores (a thread only ever touches its own ring column: no barriers in the loop)
+   const double* qg = gp.q + (int64_t)g * nz * gp.Sb + slot + (zpass == 0 ? 0 : (int64_t)(nz - 1) * gp.Sb);
+   const int64_t kstr = zpass == 0 ? gp.Sb : -gp.Sb;
    const int nrow = nz + sm.maxlev - 1;
-   for (int s = 0; s < nrow; s++) {
-      if (s < nz) sm.ring[s & (SHEAR_RING - 1)][t] = qg[(int64_t)(zpass == 0 ? s : nz - 1 - s) * gp.Sb];
-      for (int c = 0; c < nc; c++) {
-         const int a = s - sm.lv[c][t];
-         if (a >= 0 && a < nz) sm.base[c][(int64_t)s * PS + t] = sm.ring[a & (SHEAR_RING - 1)][t];
+   double nxt[SHEAR_U];
+#pragma unroll
+   for (int u = 0; u < SHEAR_U; u++) nxt[u] = u < nz ? __ldcs(qg + (int64_t)u * kstr) : 0.0;
+   for (int s0 = 0; s0 < nrow; s0 += SHEAR_U) {
+      double cur[SHEAR_U];
+#pragma unroll
+      for (int u = 0; u < SHEAR_U; u++) {
+         cur[u] = nxt[u];
+         const int sn = s0 + SHEAR_U + u;
+         nxt[u] = sn < nz ? __ldcs(qg + (int64_t)sn * kstr) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < SHEAR_U; u++) {
+         const int s = s0 + u;
+         if (s >= nrow) break;
+         if (s < nz) sm.ring[s & (SHEAR_RING - 1)][t] = cur[u];
+         for (int c = 0; c < nc; c++) {
+            const int a = s - sm.lv[c][t];
+            if (a >= 0 && a < nz) __stcs(sm.base[c] + (int64_t)s * PS + t, sm.ring[a & (SHEAR_RING - 1)][t]);
+         }
       }
    }
 }
@@ -1216,7 +1277,7 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
                if ((cl->zdir >= 0 ? 0 : 1) == zpass) {
                   const int l = cl->lvl[slot];
                   lv[j] = l == LVL_EMPTY ? (1 << 20) : l;
-                  base[j] = ch->phi_part + ((int64_t)gl * cl->npatch + patch) * cl->nsteps * PS + t;
+                  base[j] = ch->phi_part + block_row0(gl, patch, cl->npatch, cl->nsm, cl->gm, nz) * PS + t;
                   maxlev = max(maxlev, cl->patch_nlev[patch]);
                   found = 1;
                }
@@ -1545,7 +1606,7 @@ __global__ void sn_ls_rhs_kernel(const SweepGlobals gp, const int32_t* __restric
          {
             const int sl = pos[ls_nbr_slot[e]];       // nz == 1: pipeline step = local level
             acc -= ls_coef[(int64_t)m * nnz + e] *
-                   ch->psi[psi_index(gl, sl, cl->lvl[sl], d, cl->npatch, cl->nsteps, ch->nd)];
+                   ch->psi[psi_index(gl, sl, cl->lvl[sl], d, cl->npatch, cl->nsm, cl->gm, gp.nz, ch->nd)];
          }
    }
    rhs[tid] = acc;
@@ -1626,7 +1687,7 @@ __global__ void sn_export_psi_kernel(const double* __restrict__ psi_block,
    if (gl < 0) return;
    const int sl = pos_of[slot_of_xy[c]];
    const int kp = cl->zdir >= 0 ? k : nz - 1 - k;
-   const double v = scale * psi_block[psi_index(gl, sl, kp + cl->lvl[sl], d, cl->npatch, cl->nsteps, nd)];
+   const double v = scale * psi_block[psi_index(gl, sl, kp + cl->lvl[sl], d, cl->npatch, cl->nsm, cl->gm, nz, nd)];
    out[tid * M + m] = v;
    if (v < 0.0) *minval = v;     // benign race: any negative value flags the error
 }

@@ -13,13 +13,21 @@ constexpr int PS = 256;       // patch slots = sweep CTA size
 constexpr int PEDGE = 32;     // compact copies of the lanes other patches read, behind each psi row
 constexpr int PSX = PS + PEDGE;
 
-// psi of a chunk: [owned group][patch][pipeline step][direction][lane | edge copies] (row = PSX).  The pipeline step of
-// (lane, layer) is kp + lvl(lane), kp = position of the layer in sweep order: the lanes of a CTA
-// work on different layers in the same step (wavefront skew), and storing by step instead of by
-// layer makes every CTA-step one contiguous, fully coalesced block of nd x 256 doubles.
+// Step-major ("sheared") arrays.  The pipeline step of (lane, layer) is kp + lvl(lane), kp = position of
+// the layer in sweep order: the lanes of a CTA work on different layers in the same step (wavefront skew),
+// and storing by step instead of by layer makes every CTA-step one contiguous block.  The owned groups are
+// stored in blocks of gm consecutive groups that share ONE run of rows per patch: group gi of a block
+// starts nz rows after group gi - 1, so that the skewed tail of one group interleaves with the skewed head
+// of the next and a task that sweeps the gm groups back to back (flow kernel) has no padding in between:
+//    rows per (block, patch):  nsm = gm * nz + max local levels - 1
+//    row of (gl, patch, step): ((gl / gm) * npatch + patch) * nsm + (gl % gm) * nz + step
+// psi of a chunk: [block][patch][row][direction][lane | edge copies] (row = PSX doubles per direction).
+__host__ __device__ inline int64_t block_row0(int gl, int patch, int npatch, int nsm, int gm, int nz) {
+   return ((int64_t)(gl / gm) * npatch + patch) * nsm + (int64_t)(gl % gm) * nz;
+}
 __host__ __device__ inline int64_t psi_index(int gl, int64_t slot, int step, int d, int npatch,
-                                             int nsteps, int nd) {
-   return ((((int64_t)gl * npatch + (slot >> 8)) * nsteps + step) * nd + d) * PSX + (slot & (PS - 1));
+                                             int nsm, int gm, int nz, int nd) {
+   return ((block_row0(gl, (int)(slot >> 8), npatch, nsm, gm, nz) + step) * nd + d) * PSX + (slot & (PS - 1));
 }
 
 struct ClassDev {
@@ -28,9 +36,12 @@ struct ClassDev {
    int32_t ring;              // smem ring depth
    int32_t tiles;             // 1: class slot == base slot
    int32_t npatch;
-   int32_t nsteps;            // pipeline steps stored per patch: max local levels + nz - 1
+   int32_t nsteps;            // pipeline steps of one group per patch: max local levels + nz - 1
+   int32_t gm;                // owned groups per block of the step-major arrays
+   int32_t nsm;               // rows per (block, patch) = gm * nz + max local levels - 1
    int32_t pad;
    const int32_t* mats_s;     // [npatch][nsteps][PS] material of (lane, step), -1 outside
+   const int32_t* mats_c;     // [npatch][nz][PS] cyclic: row r holds the material of layer (r - lvl) mod nz
    const int32_t* cell_of;    // [S] base slot or -1
    const uint16_t* lvl;       // [S]
    const int32_t* patch_nlev; // [npatch]
@@ -41,7 +52,7 @@ struct ClassDev {
    const int32_t* ls_of;      // [S] index into the LS cell list or -1 (nullptr: no LS)
    const uint16_t* in_hidx;   // [FIN_MAX][S] halo index of patch-boundary / reflective sources
    const uint8_t* eidx;       // [S] edge index of lanes read by other patches (255: none)
-   double* q_sheared;         // [G][npatch][nsteps][PS] source in this class's step-major order
+   double* q_sheared;         // [block][patch][nsm][PS] source in this class's step-major order
                               // (nullptr: class swept by the generic kernel)
 };
 
@@ -52,8 +63,8 @@ struct ChunkDev {
    int32_t m[DT_MAX];         // quadrature index
    int32_t mrefl[DT_MAX][3];  // mirrored direction about x, y, z
    double mux[DT_MAX], muy[DT_MAX], muz_abs[DT_MAX], w[DT_MAX];
-   double* psi;               // [Gown][npatch][nsteps][nd][PSX]
-   double* phi_part;          // [Gown][npatch][nsteps][PS] sum_d w_d psi_d of this chunk (tile kernel)
+   double* psi;               // [block][patch][nsm][nd][PSX]
+   double* phi_part;          // [block][patch][nsm][PS] sum_d w_d psi_d of this chunk (tile / flow kernels)
    int32_t flow_slot;         // index of this chunk in the direction table of its flow launch
    int32_t pad_;
 };
@@ -62,6 +73,7 @@ struct SweepGlobals {
    const ClassDev* classes;
    const ChunkDev* chunks;
    const int32_t* gloc;       // [G] local index of an owned group or -1
+   const int32_t* gown;       // [Gown] group of a local index
    const double* q;           // [G][nz][Sb]
    double* phi_new;           // [G][nz][Sb] accumulated with atomics
    const int32_t* mats;       // [nz][Sb] (-1 in holes)
@@ -77,6 +89,7 @@ struct SweepGlobals {
    const double* ls_rhs;      // [M][G][nls]
    int64_t Sb;
    int32_t G, Gown, M, nz, Kc, has_z, nrf, nls;
+   int32_t gm;                // owned groups per block (ClassDev::gm, the same for every class)
    int32_t bcz_minus_refl, bcz_plus_refl;   // 1 if that z boundary is reflective
    int32_t store_psi;
    int32_t nmat;
@@ -99,6 +112,7 @@ void launch_sweep(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int d
 cudaError_t configure_sweep_kernels();
 cudaError_t configure_tile_kernels();
 cudaError_t configure_shear_kernels();
+int shear_max_classes();      // fast classes per z direction the shear kernel handles
 constexpr int SHEAR_MAX_PER_PASS = 32;   // fast classes / chunks per z direction the shear kernels handle
 void launch_sweep_tile(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras,
                        cudaStream_t st);

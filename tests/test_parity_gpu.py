@@ -82,7 +82,10 @@ def test_single_sweep_cartesian_3d():
     # generic_only = the general kernel; store_psi = 0 keeps only the patch-edge copies of psi
     for opts in ({}, {"wave_launch": 1}, {"z_chunk": 4}, {"tile_i": 8, "tile_j": 4}, {"generic_only": 1},
                  {"dt_max": 2, "z_chunk": 3}, {"dt_max": 3, "generic_only": 1}, {"dt_max": 4}, {"store_psi": 0},
-                 {"store_psi": 0, "tile_i": 8, "tile_j": 8}):
+                 {"store_psi": 0, "tile_i": 8, "tile_j": 8},
+                 # groups a dataflow task sweeps back to back (default 4 -> one block of 3 here): no merging,
+                 # a ragged last block, and merged rows holding only the edge copies
+                 {"group_merge": 1}, {"group_merge": 2}, {"group_merge": 2, "store_psi": 0, "dt_max": 3}):
         dev = pb.SNDevice(em, xs, quad, **opts)
         dev.set("flux-moments", phi0.reshape(-1))
         dev.source(keff)
@@ -113,7 +116,7 @@ def test_keff_cartesian_3d_reflective():
     em = syn.cartesian_mesh(h, h, np.full(nz, 2.5), mats, bcs)
     mesh, op = _oracle_cart(h, h, np.full(nz, 2.5), mats, bcs, xs, quad, G)
     sol = orc.solve_matrix_free(op)
-    for opts in ({}, {"generic_only": 1}, {"z_chunk": 3, "dt_max": 2}):
+    for opts in ({}, {"group_merge": 1}, {"generic_only": 1}, {"z_chunk": 3, "dt_max": 2}):
         dev, k, it = _solve(em, xs, quad, **opts)
         _check_solution(dev, k, sol.keff, sol.phi, sol.power)
         psi = dev.get("angular-flux").reshape(sol.psi.shape)
