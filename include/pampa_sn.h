@@ -111,7 +111,7 @@ typedef struct {
                                     (0: default 7, < 0: plain power iteration) */
    int32_t wave_launch;          /* 1: sweep the tile classes with one launch per wavefront instead of the
                                     single dataflow launch (A/B testing) */
-   int32_t group_merge;          /* energy groups a dataflow sweep task handles back to back (0: default 4);
+   int32_t group_merge;          /* energy groups a dataflow sweep task handles back to back (0: default 8);
                                     more groups = less pipeline fill/drain padding in the step-major arrays */
 } pampa_sn_options;
 

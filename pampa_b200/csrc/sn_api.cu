@@ -214,7 +214,7 @@ int sync_scalars(pampa_sn_handle* h) {
 
 int do_source(pampa_sn_handle* h) {
    launch_source(h->d_phi, h->d_q, h->d_mats, h->d_sig_s, h->d_chi, h->d_nusf, h->d_sc, h->d_gloc, h->G,
-                 h->plan.nz, h->plan.Sb, h->stream);
+                 h->nmat, h->plan.nz, h->plan.Sb, h->stream);
    h->launches++;
    return 0;
 }
@@ -476,7 +476,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       // tasks: a longer tail at the end of the launch.  The sigma_t table of a block lives in shared memory.
       h->gm = 1;
       if (!h->opts.wave_launch && pl.nzc == 1 && pl.tile_classes > 0) {
-         int gm = h->opts.group_merge > 0 ? h->opts.group_merge : 4;
+         int gm = h->opts.group_merge > 0 ? h->opts.group_merge : 8;
          gm = std::min(gm, std::max(1, 2048 / std::max(1, h->nmat)));
          h->gm = std::max(1, std::min(gm, h->Gown));
       }
@@ -576,7 +576,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          const ClassPlan& cp = pl.classes[ci];
          ClassDev& cd = cdev[ci];
          cd.S = cp.S; cd.zdir = cp.zdir; cd.ring = cp.ring; cd.tiles = cp.tiles ? 1 : 0; cd.npatch = cp.npatch;
-         cd.nsteps = cp.nsteps; cd.gm = gm; cd.nsm = nsm_of(cp); cd.pad = 0; cd.mats_c = nullptr;
+         cd.nsteps = cp.nsteps; cd.gm = gm; cd.nsm = nsm_of(cp); cd.mat_bytes = 4; cd.mats_c = nullptr;
          {  // material map in the class's (patch, pipeline step, lane) order
             std::vector<int32_t> ms((size_t)cp.npatch * cp.nsteps * PS, -1);
             for (int64_t sl = 0; sl < cp.S; sl++) {
@@ -627,17 +627,21 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
             cd.q_sheared = d_qs;
             // material map of the dataflow kernel, cyclic in the pipeline step: the lane at level l
             // is at layer (step - l) mod nz of some group of its block
-            std::vector<int32_t> mc((size_t)cp.npatch * nz * PS, -1);
+            const int mb = h->nmat <= 256 ? 1 : 4;
+            std::vector<uint8_t> mc((size_t)cp.npatch * nz * PS * mb, 0);
             for (int64_t sl = 0; sl < cp.S; sl++) {
                if (cp.cell_of[sl] < 0) continue;
                const int64_t p = sl / PS, lane = sl % PS;
                for (int kp = 0; kp < nz; kp++) {
                   const int k = cp.zdir >= 0 ? kp : nz - 1 - kp;
-                  mc[((size_t)p * nz + (kp + cp.lvl[sl]) % nz) * PS + lane] = mats[(size_t)k * Sb + cp.cell_of[sl]];
+                  const int32_t m = mats[(size_t)k * Sb + cp.cell_of[sl]];
+                  const size_t e = ((size_t)p * nz + (kp + cp.lvl[sl]) % nz) * PS + lane;
+                  if (mb == 1) mc[e] = (uint8_t)m; else std::memcpy(&mc[e * 4], &m, 4);
                }
             }
-            int32_t* d_mc;
+            uint8_t* d_mc;
             if (dev_upload(h, &d_mc, mc)) return 1;
+            cd.mat_bytes = mb;
             cd.mats_c = d_mc;
          }
          cd.cell_of = d_cell_of; cd.lvl = d_lvl; cd.patch_nlev = d_patch_nlev;

@@ -784,6 +784,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
    const int NS = cl->nsm;
    const int zdir = cl->zdir;
    const int kcnt = ngr * nz;                         // column updates of a lane (never split in z)
+   const int mat_bytes = cl->mat_bytes;               // 1: uint8 material rows (<= 256 materials), 4: int32
    const int nsteps = cl->patch_nlev[tk.patch] + kcnt - 1;
    const bool lane_thread = t < PS;
    const int64_t slot = (int64_t)tk.patch * PS + (lane_thread ? t : 0);
@@ -900,7 +901,8 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
          asm volatile("" : "+r"(cslot));               // keep the LDCs in the loop (not 20 hoisted registers)
          const int kl = step - lv0;
          if (kl >= 0 && kl < kcnt) {
-            const int mat = s_m[(step & (DQ - 1)) * PS + t];
+            const int mat = mat_bytes == 1 ? (int)((const uint8_t*)(s_m + (step & (DQ - 1)) * PS))[t]
+                                           : s_m[(step & (DQ - 1)) * PS + t];
             const double qv = s_q[(step & (DQ - 1)) * PS + t];
             const double* rbuf = bufs + ((step - 1) & (D - 1)) * ROWS;
             double* wbuf = bufs + (step & (D - 1)) * ROWS + t;
@@ -1026,13 +1028,16 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       };
       // q and material rows of a step: two bulk copies (2 KB + 1 KB) counted on the step's mbarrier
       const double* q_rows = cl->q_sheared + prow * PS;
-      const int32_t* m_rows = cl->mats_c + (int64_t)tk.patch * nz * PS;   // cyclic in the step: row st mod nz
+      const unsigned mrow_bytes = PS * mat_bytes;
+      const uint8_t* m_rows = cl->mats_c + (int64_t)tk.patch * nz * mrow_bytes;   // cyclic in the step: row st mod nz
+      int mrow = 0;                                    // st mod nz (stage_rows is called for st = 0, 1, 2, ...)
       auto stage_rows = [&](int st) {
          if (hl != 0 || st >= nsteps) return;
          uint64_t* bar = &s_bar[st & (DQ - 1)];
-         mbar_expect_tx(bar, PS * (sizeof(double) + sizeof(int32_t)));
+         mbar_expect_tx(bar, PS * sizeof(double) + mrow_bytes);
          bulk_load(s_q + (st & (DQ - 1)) * PS, q_rows + (int64_t)st * PS, PS * sizeof(double), bar);
-         bulk_load(s_m + (st & (DQ - 1)) * PS, m_rows + (int64_t)(st % nz) * PS, PS * sizeof(int32_t), bar);
+         bulk_load(s_m + (st & (DQ - 1)) * PS, m_rows + (int64_t)mrow * mrow_bytes, mrow_bytes, bar);
+         if (++mrow == nz) mrow = 0;
       };
 #pragma unroll
       for (int st = 0; st < PFQ; st++) stage_rows(st);
@@ -1352,12 +1357,52 @@ sn_source_kernel(const double* __restrict__ phi, double* __restrict__ q,
    }
 }
 
+// Same, with the G flux values of the cell held in registers (G <= GR): all the global loads of a thread are
+// issued together and the cross sections of the (few) materials come from shared memory.
+template <int GR>
+__global__ void __launch_bounds__(256)
+sn_source_reg_kernel(const double* __restrict__ phi, double* __restrict__ q,
+                     const int32_t* __restrict__ mats, const double* __restrict__ sig_s,
+                     const double* __restrict__ chi, const double* __restrict__ nusf,
+                     const ReduceScalars* __restrict__ sc, const int32_t* __restrict__ gloc, int G, int nmat,
+                     int64_t n) {
+   extern __shared__ double s_xs[];                     // [nmat][G][G] sigma_s + chi nu-sigma-f / k, then owned flags
+   const double ik = 1.0 / sc->keff;
+   for (int a = threadIdx.x; a < nmat * G * G; a += blockDim.x) {
+      const int m = a / (G * G), g2 = (a / G) % G, g = a % G;
+      s_xs[a] = sig_s[a] + chi[m * G + g] * nusf[m * G + g2] * ik;
+   }
+   __syncthreads();
+   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (idx >= n) return;
+   const int mat = mats[idx];
+   if (mat < 0) return;
+   double ph[GR];
+#pragma unroll
+   for (int g2 = 0; g2 < GR; g2++) ph[g2] = g2 < G ? __ldcs(phi + (int64_t)g2 * n + idx) : 0.0;
+   const double* xs = s_xs + (size_t)mat * G * G;
+#pragma unroll
+   for (int g = 0; g < GR; g++) {
+      if (g >= G || gloc[g] < 0) continue;
+      double acc = 0.0;
+#pragma unroll
+      for (int g2 = 0; g2 < GR; g2++) if (g2 < G) acc = fma(xs[g2 * G + g], ph[g2], acc);
+      __stcs(q + (int64_t)g * n + idx, acc);
+   }
+}
+
 void launch_source(const double* phi, double* q, const int32_t* mats, const double* sig_s,
                    const double* chi, const double* nusf, const ReduceScalars* sc, const int32_t* gloc,
-                   int G, int nz, int64_t Sb, cudaStream_t st) {
+                   int G, int nmat, int nz, int64_t Sb, cudaStream_t st) {
    const int64_t n = (int64_t)nz * Sb;
    const int nb = (int)((n + 255) / 256);
-   sn_source_kernel<<<nb, 256, 0, st>>>(phi, q, mats, sig_s, chi, nusf, sc, gloc, G, n);
+   const size_t smem = (size_t)nmat * G * G * sizeof(double);
+   if (G <= 8 && smem <= 32 * 1024)
+      sn_source_reg_kernel<8><<<nb, 256, smem, st>>>(phi, q, mats, sig_s, chi, nusf, sc, gloc, G, nmat, n);
+   else if (G <= 16 && smem <= 32 * 1024)
+      sn_source_reg_kernel<16><<<nb, 256, smem, st>>>(phi, q, mats, sig_s, chi, nusf, sc, gloc, G, nmat, n);
+   else
+      sn_source_kernel<<<nb, 256, 0, st>>>(phi, q, mats, sig_s, chi, nusf, sc, gloc, G, n);
 }
 
 // ------------------------------------------------------------------------------------ reduce

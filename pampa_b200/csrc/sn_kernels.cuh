@@ -39,9 +39,10 @@ struct ClassDev {
    int32_t nsteps;            // pipeline steps of one group per patch: max local levels + nz - 1
    int32_t gm;                // owned groups per block of the step-major arrays
    int32_t nsm;               // rows per (block, patch) = gm * nz + max local levels - 1
-   int32_t pad;
+   int32_t mat_bytes;         // element size of mats_c: 1 (uint8, <= 256 materials) or 4 (int32)
    const int32_t* mats_s;     // [npatch][nsteps][PS] material of (lane, step), -1 outside
-   const int32_t* mats_c;     // [npatch][nz][PS] cyclic: row r holds the material of layer (r - lvl) mod nz
+   const uint8_t* mats_c;     // [npatch][nz][PS] x mat_bytes, cyclic: row r holds the material of layer
+                              // (r - lvl) mod nz (dataflow kernel; 0 in holes)
    const int32_t* cell_of;    // [S] base slot or -1
    const uint16_t* lvl;       // [S]
    const int32_t* patch_nlev; // [npatch]
@@ -130,7 +131,7 @@ void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const 
 
 void launch_source(const double* phi, double* q, const int32_t* mats, const double* sig_s,
                    const double* chi, const double* nusf, const ReduceScalars* sc, const int32_t* gloc,
-                   int G, int nz, int64_t Sb, cudaStream_t st);
+                   int G, int nmat, int nz, int64_t Sb, cudaStream_t st);
 
 void launch_reduce(double* phi, double* phi_new, const int32_t* mats, const double* nusf,
                    const double* kapsf, const double* area, const double* dz, int has_z, int G,

@@ -193,3 +193,29 @@ def test_anderson_matches_plain_power_iteration():
     assert it1 < it0, (it1, it0)
     print("iterations: plain %d, Anderson %d" % (it0, it1))
     plain.close(); acc.close()
+
+
+def test_sweep_schedule_independence(monkeypatch):
+    """The sweep result must not depend on how it is scheduled: one launch per wavefront (stream order), the
+    dataflow launch (patches coupled by progress counters) with 1 / 4 / 8 groups per task, publishing the counter
+    every row (PAMPA_SN_DBG = 16: readers follow the writer as closely as possible).  Bit-exact: an unfenced
+    counter store once let readers see rows of the previous sweep on a mesh of this shape."""
+    G = 8
+    mesh, xs = syn.checkerboard_core(64, 64, 96, num_groups=G)
+    quad = syn.level_symmetric(4)
+    ref = None
+    for opts, dbg in (({"wave_launch": 1}, None), ({}, None), ({"group_merge": 8}, None), ({"group_merge": 8}, "16"),
+                      ({"group_merge": 1}, "16"), ({"group_merge": 3, "store_psi": 0}, "16")):
+        if dbg is None:
+            monkeypatch.delenv("PAMPA_SN_DBG", raising=False)
+        else:
+            monkeypatch.setenv("PAMPA_SN_DBG", dbg)
+        dev = pb.SNDevice(mesh, xs, quad, **opts)
+        k = dev.iterate(3)
+        phi = dev.get("flux-moments")
+        dev.close()
+        if ref is None:
+            ref = (k, phi)
+        else:
+            assert k == ref[0], (opts, dbg)
+            assert np.array_equal(phi, ref[1]), (opts, dbg)
