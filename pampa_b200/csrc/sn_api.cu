@@ -111,6 +111,7 @@ struct pampa_sn_handle {
    std::vector<char> class_fast;
    int32_t *d_fast_classes = nullptr, *d_fast_chunks = nullptr;
    int nfast_classes = 0, nfast_chunks = 0;
+   int groups_generic = 0;               // launch groups of the generic kernel (it accumulates into phi_new with atomics)
    int gm = 1;                           // owned groups per block of the step-major arrays (sn_kernels.cuh)
    int32_t* d_gown = nullptr;            // [Gown] group of a local index
 
@@ -269,8 +270,9 @@ int do_sweep(pampa_sn_handle* h) {
       cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); h->kernel_events->push_back(e);
    }
    if (h->nfast_chunks > 0) {
+      // every owned chunk on the tile kernels: nothing else adds to phi_new, the first pass may overwrite it
       launch_unshear_phi(gp, h->d_chunks, h->d_classes, h->d_fast_chunks, h->nfast_chunks, h->plan.npatch_b,
-                         h->stream);
+                         h->groups_generic == 0 ? 1 : 0, h->stream);
       h->launches++;
    }
    h->bnd_cur = 1 - h->bnd_cur;      // what this sweep wrote is what the next one reads
@@ -751,6 +753,8 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          }
          all.insert(all.end(), tasks.begin(), tasks.end());
       }
+      h->groups_generic = 0;
+      for (const LaunchGroup& lg : h->groups) if (lg.kind != 1) h->groups_generic++;
       if (!h->opts.store_psi && !h->groups.empty())
          SN_FAIL(h, "store_psi = 0 needs every ordering class on the dataflow tile kernel (Cartesian mesh, no "
                     "least-squares term, wave_launch = 0)");

@@ -1255,9 +1255,10 @@ constexpr int UNSHEAR_NC = 8;
 __global__ void __launch_bounds__(PS)
 sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks,
                       const ClassDev* __restrict__ classes, const int32_t* __restrict__ fast_chunks,
-                      int nfast, int npatch_b) {
+                      int nfast, int npatch_b, int overwrite_first) {
    extern __shared__ __align__(16) unsigned char shear_raw[];
    double (*ring)[PS] = reinterpret_cast<double (*)[PS]>(shear_raw);      // [SHEAR_RING][PS]
+   bool overwrite = overwrite_first != 0;   // phi_new holds nothing yet: the first pass stores instead of adding
    const int t = threadIdx.x;
    const int patch = blockIdx.x % npatch_b;
    const int g = blockIdx.x / npatch_b;
@@ -1296,8 +1297,16 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
 #pragma unroll
             for (int j = 0; j < UNSHEAR_NC; j++) {
                const int a0 = s - lv[j], a1 = s + 1 - lv[j];
-               v0[j] = (a0 >= 0 && a0 < nz) ? base[j][(int64_t)s * PS] : 0.0;
-               v1[j] = (a1 >= 0 && a1 < nz) ? base[j][(int64_t)(s + 1) * PS] : 0.0;
+               v0[j] = (a0 >= 0 && a0 < nz) ? __ldcs(base[j] + (int64_t)s * PS) : 0.0;
+               v1[j] = (a1 >= 0 && a1 < nz) ? __ldcs(base[j] + (int64_t)(s + 1) * PS) : 0.0;
+            }
+            // the (up to two) layers this pair of steps completes: their current phi_new values are
+            // loaded with the chunk rows, not after them (nothing to load in the pass that overwrites)
+            double old[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+               const int ad = s + u - (maxlev - 1);
+               old[u] = (!overwrite && ad >= 0 && ad < nz) ? pg[(int64_t)(zpass == 0 ? ad : nz - 1 - ad) * gp.Sb] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 2; u++) {
@@ -1309,20 +1318,21 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
                const int ad = s + u - (maxlev - 1);      // complete for every chunk and lane
                if (ad >= 0 && ad < nz) {
                   const int k = zpass == 0 ? ad : nz - 1 - ad;
-                  pg[(int64_t)k * gp.Sb] += ring[ad & (SHEAR_RING - 1)][t];
+                  pg[(int64_t)k * gp.Sb] = old[u] + ring[ad & (SHEAR_RING - 1)][t];
                   ring[ad & (SHEAR_RING - 1)][t] = 0.0;
                }
             }
          }
+         overwrite = false;
       }
    }
 }
 
 void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
-                        const int32_t* d_fast_chunks, int nfast, int npatch_b, cudaStream_t st) {
+                        const int32_t* d_fast_chunks, int nfast, int npatch_b, int overwrite_first, cudaStream_t st) {
    if (nfast <= 0) return;
    sn_unshear_phi_kernel<<<npatch_b * gp.G, PS, SHEAR_RING * PS * sizeof(double), st>>>(
-      gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b);
+      gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first);
 }
 
 cudaError_t configure_shear_kernels() {

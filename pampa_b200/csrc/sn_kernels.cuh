@@ -127,7 +127,7 @@ cudaError_t configure_flow_kernels();
 void launch_shear_q(const SweepGlobals& gp, const ClassDev* d_classes, const int32_t* d_fast_classes,
                     int nfast, int npatch_b, cudaStream_t st);
 void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
-                        const int32_t* d_fast_chunks, int nfast, int npatch_b, cudaStream_t st);
+                        const int32_t* d_fast_chunks, int nfast, int npatch_b, int overwrite_first, cudaStream_t st);
 
 void launch_source(const double* phi, double* q, const int32_t* mats, const double* sig_s,
                    const double* chi, const double* nusf, const ReduceScalars* sc, const int32_t* gloc,
