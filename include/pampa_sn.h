@@ -113,6 +113,10 @@ typedef struct {
                                     single dataflow launch (A/B testing) */
    int32_t group_merge;          /* energy groups a dataflow sweep task handles back to back (0: default 8);
                                     more groups = less pipeline fill/drain padding in the step-major arrays */
+   int32_t inline_edges;         /* 1: structured tiles numbered perimeter first and the dataflow sweep reads the
+                                    perimeter lanes of the neighbouring patch's psi rows directly instead of
+                                    compact edge copies behind each row (6 GB less written per sweep at C4, but
+                                    no faster: measured 22.35 vs 21.90 ms per iteration); 0: default */
 } pampa_sn_options;
 
 void pampa_sn_default_options(pampa_sn_options* opts);

@@ -363,6 +363,7 @@ void pampa_sn_default_options(pampa_sn_options* o) {
    std::memset(o, 0, sizeof(*o));
    o->store_psi = 1;
    o->group_merge = 0;
+   o->inline_edges = 0;
    o->num_ranks = 1;
 }
 
@@ -517,7 +518,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          if (chunk_owned[c]) {
             psi_off[c] = psi_doubles;
             const ClassPlan& cpc = pl.classes[pl.chunks[c].cls];
-            psi_doubles += (int64_t)pl.chunks[c].nd * nblk * cpc.npatch * nsm_of(cpc) * (h->opts.store_psi ? PSX : PEDGE);
+            psi_doubles += (int64_t)pl.chunks[c].nd * nblk * cpc.npatch * nsm_of(cpc) * (h->opts.store_psi ? PSX : PERIM_MAX);
          }
       if (dev_alloc(h, &h->d_psi, psi_doubles)) return 1;
       SN_CUDA(h, cudaMemsetAsync(h->d_psi, 0, (size_t)psi_doubles * sizeof(double), h->stream));
@@ -650,7 +651,6 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          cd.out_vec = (const double2*)d_out_vec; cd.in_src = d_in_src; cd.in_vec = (const double2*)d_in_vec;
          cd.rout = d_rout; cd.ls_of = d_ls_of;
       }
-      if (dev_upload(h, &h->d_classes, cdev)) return 1;
       if (dev_upload(h, &h->d_class_pos_of, h->d_pos_of.data(), (int64_t)h->d_pos_of.size())) return 1;
 
       // chunks
@@ -758,6 +758,13 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       if (!h->opts.store_psi && !h->groups.empty())
          SN_FAIL(h, "store_psi = 0 needs every ordering class on the dataflow tile kernel (Cartesian mesh, no "
                     "least-squares term, wave_launch = 0)");
+      // dataflow classes on structured tiles: neighbouring patches read the perimeter lanes of the psi rows
+      // themselves (no edge copies); the wavefront-launched kernels keep the copies
+      for (size_t ci = 0; ci < pl.classes.size(); ci++) {
+         cdev[ci].inline_edges = (use_flow && h->class_fast[ci] && pl.classes[ci].inline_ok && h->opts.inline_edges) ? 1 : 0;
+         cdev[ci].pstride = cdev[ci].inline_edges ? PS : PSX;
+      }
+      if (dev_upload(h, &h->d_classes, cdev)) return 1;
       if (dev_upload(h, &h->d_chunks, chdev)) return 1;
       if (dev_upload(h, &h->d_tasks, all)) return 1;
       // reflective / LS problems read what another class wrote in the previous sweep only, so classes

@@ -815,8 +815,15 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
    const int64_t prow = ((int64_t)gb * npatch + tk.patch) * NS;   // first row of this (block, patch)
    // psi rows in global memory: [DT][256 lanes | 32 edge copies], or the edge copies alone when the
    // angular flux is not kept (store_psi = 0): only other patches read them
-   const int gstr = gp.store_psi ? PSX : PEDGE;       // direction stride of a global row
-   const int goff = gp.store_psi ? PS : 0;            // offset of the edge copies in it
+   // Two ways a neighbouring patch gets the lanes it reads.  Edge copies: 32 compact duplicates behind the
+   // 256 lanes of a row.  Inline (perimeter-first lane order, sn_plan.hpp): the lanes other patches read are
+   // among the first PERIM_MAX lanes of the row itself, so nothing is duplicated.  With store_psi = 0 only
+   // the part of a row other patches read is stored at all.
+   const bool inl = cl->inline_edges != 0;
+   const int gstr = gp.store_psi ? cl->pstride : (inl ? PERIM_MAX : PEDGE);   // direction stride of a global row
+   const int goff = inl ? 0 : (gp.store_psi ? PS : 0);               // offset of the edge copies in it
+   const int src_off = (inl || gp.store_psi) ? 0 : PS;               // first smem column the row store takes
+   const int row_cols = gp.store_psi ? (inl ? PS : PSX) : gstr;      // columns stored per direction
    const int rowg = DT * gstr;
    double* psi_gl = ch->psi + (int64_t)gb * npatch * NS * rowg;
    const int kdir = zdir >= 0 ? 1 : -1;
@@ -862,7 +869,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
 #pragma unroll
          for (int d = 0; d < DT; d++) { so[d] = 0.0; a0[d] = 0.0; a1[d] = 0.0; }
       }
-      const int ex = valid ? (int)cl->eidx[slot] : 255;   // my compact edge index, if another patch reads me
+      const int ex = (valid && !inl) ? (int)cl->eidx[slot] : 255;   // my compact edge index, if another patch reads me
       int rout[ROUT_MAX];
       if (EXTRAS) {
 #pragma unroll
@@ -999,7 +1006,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       if (kind == SRC_GLOBAL) {
          const int up = pay >> 8;
          const int dlv = (int)cl->lvl[pay] - rlv;
-         gsrc = psi_gl + ((int64_t)up * NS + dlv) * rowg + goff + cl->eidx[pay];
+         gsrc = psi_gl + ((int64_t)up * NS + dlv) * rowg + (inl ? (pay & (PS - 1)) : goff + (int)cl->eidx[pay]);
          flag = progress + ((int64_t)tk.chunk * nblk + gb) * npatch + up;
          need0 = dlv + 1;
       } else if (kind == SRC_REFL) {
@@ -1077,10 +1084,10 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       // publish every 8th row: the fences take longer than the two steps of slack the buffer ring gives
       // (measured at C4: 22.7 / 19.1 / 17.7 ms per sweep publishing every 2nd / 4th / 8th row)
       const int pub = ((gp.dbg >> 4) & 0xff) ? ((gp.dbg >> 4) & 0xff) : 8;
-      const unsigned bytes = gstr * sizeof(double);
+      const unsigned bytes = row_cols * sizeof(double);
       for (int step = 0; step < nsteps; step++) {
          while (ld_acquire_cta_smem(&s_rows_done) <= step) {}
-         const double* src = bufs + (step & (D - 1)) * ROWS + (PS - goff);
+         const double* src = bufs + (step & (D - 1)) * ROWS + src_off;
          double* dst = psi_rows + (int64_t)step * rowg;
 #pragma unroll
          for (int d = 0; d < DT; d++) bulk_store(dst + d * gstr, src + d * PSXS, bytes);
@@ -1661,7 +1668,7 @@ __global__ void sn_ls_rhs_kernel(const SweepGlobals gp, const int32_t* __restric
          {
             const int sl = pos[ls_nbr_slot[e]];       // nz == 1: pipeline step = local level
             acc -= ls_coef[(int64_t)m * nnz + e] *
-                   ch->psi[psi_index(gl, sl, cl->lvl[sl], d, cl->npatch, cl->nsm, cl->gm, gp.nz, ch->nd)];
+                   ch->psi[psi_index(gl, sl, cl->lvl[sl], d, cl->npatch, cl->nsm, cl->gm, gp.nz, ch->nd, cl->pstride)];
          }
    }
    rhs[tid] = acc;
@@ -1742,7 +1749,7 @@ __global__ void sn_export_psi_kernel(const double* __restrict__ psi_block,
    if (gl < 0) return;
    const int sl = pos_of[slot_of_xy[c]];
    const int kp = cl->zdir >= 0 ? k : nz - 1 - k;
-   const double v = scale * psi_block[psi_index(gl, sl, kp + cl->lvl[sl], d, cl->npatch, cl->nsm, cl->gm, nz, nd)];
+   const double v = scale * psi_block[psi_index(gl, sl, kp + cl->lvl[sl], d, cl->npatch, cl->nsm, cl->gm, nz, nd, cl->pstride)];
    out[tid * M + m] = v;
    if (v < 0.0) *minval = v;     // benign race: any negative value flags the error
 }

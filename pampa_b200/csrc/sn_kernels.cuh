@@ -26,8 +26,8 @@ __host__ __device__ inline int64_t block_row0(int gl, int patch, int npatch, int
    return ((int64_t)(gl / gm) * npatch + patch) * nsm + (int64_t)(gl % gm) * nz;
 }
 __host__ __device__ inline int64_t psi_index(int gl, int64_t slot, int step, int d, int npatch,
-                                             int nsm, int gm, int nz, int nd) {
-   return ((block_row0(gl, (int)(slot >> 8), npatch, nsm, gm, nz) + step) * nd + d) * PSX + (slot & (PS - 1));
+                                             int nsm, int gm, int nz, int nd, int pstride) {
+   return ((block_row0(gl, (int)(slot >> 8), npatch, nsm, gm, nz) + step) * nd + d) * pstride + (slot & (PS - 1));
 }
 
 struct ClassDev {
@@ -40,6 +40,9 @@ struct ClassDev {
    int32_t gm;                // owned groups per block of the step-major arrays
    int32_t nsm;               // rows per (block, patch) = gm * nz + max local levels - 1
    int32_t mat_bytes;         // element size of mats_c: 1 (uint8, <= 256 materials) or 4 (int32)
+   int32_t inline_edges;      // 1: dataflow kernel, neighbouring patches read the first PERIM_MAX lanes of a psi
+   int32_t pstride;           //    row directly (perimeter-first lane order) instead of edge copies;
+                              // pstride: doubles per direction of a psi row (PSX with edge copies, PS inline)
    const int32_t* mats_s;     // [npatch][nsteps][PS] material of (lane, step), -1 outside
    const uint8_t* mats_c;     // [npatch][nz][PS] x mat_bytes, cyclic: row r holds the material of layer
                               // (r - lvl) mod nz (dataflow kernel; 0 in holes)

@@ -38,6 +38,7 @@ constexpr int DT_MAX = 10;         // directions per sweep chunk (register-resid
 constexpr int DT_DEFAULT = 5;      // measured best on B200 (registers -> 2 CTAs/SM without spills)
 constexpr int RING_MAX = 4;        // smem ring depth for in-patch upwind values
 constexpr uint16_t LVL_EMPTY = 0xFFFF;
+constexpr int PERIM_MAX = 64;           // perimeter lanes of a structured tile (16x16: 60)
 
 // upwind source codes
 constexpr int32_t SRC_NONE = -1;
@@ -71,6 +72,7 @@ struct ClassPlan {
    std::vector<uint8_t> eidx;           // [S] compact index of a lane other patches read from (255: none)
    int max_export = 0;
    bool fast = false;                   // eligible for the staged tile kernel
+   bool inline_ok = false;              // every lane another patch reads is one of the first PERIM_MAX lanes
 };
 
 struct Chunk {
@@ -100,6 +102,7 @@ struct Plan {
    std::vector<int32_t> rface_axis;     // [num_rfaces]
    int64_t owned_updates = 0;
    int tile_classes = 0;
+   int nperim = 0;                      // structured tiles: lanes 0 .. nperim-1 are the tile perimeter (0: row-major)
 };
 
 namespace detail {
@@ -195,10 +198,28 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
          if (tile_id[t] < 0) tile_id[t] = 0;
       }
       for (int t = 0; t < ntx * nty; t++) if (tile_id[t] == 0) tile_id[t] = np++;
+      // Lane order inside a tile: the perimeter first, walked as a ring (bottom row, right column, top row
+      // backwards, left column downwards), then the interior row by row.  Only perimeter lanes are read by
+      // other patches, and the two sides a sweep direction exports are adjacent on the ring, so a neighbouring
+      // patch can read them straight from the psi rows as one or two contiguous segments of the first
+      // PERIM_MAX lanes (no edge copies).  Thin tiles (a side < 3) keep the row-major order.
+      std::vector<int> lane_of_pos(ti * tj);
+      std::iota(lane_of_pos.begin(), lane_of_pos.end(), 0);
+      pl.nperim = 0;
+      if (in.opts.inline_edges && ti >= 3 && tj >= 3 && 2 * (ti + tj) - 4 <= PERIM_MAX) {
+         int n = 0;
+         for (int i = 0; i < ti; i++) lane_of_pos[i] = n++;                                  // j = 0
+         for (int j = 1; j < tj; j++) lane_of_pos[j * ti + ti - 1] = n++;                    // i = ti - 1
+         for (int i = ti - 2; i >= 0; i--) lane_of_pos[(tj - 1) * ti + i] = n++;             // j = tj - 1
+         for (int j = tj - 2; j >= 1; j--) lane_of_pos[j * ti] = n++;                        // i = 0
+         pl.nperim = n;
+         for (int j = 1; j < tj - 1; j++)
+            for (int i = 1; i < ti - 1; i++) lane_of_pos[j * ti + i] = n++;
+      }
       for (int c = 0; c < nxy; c++) {
          int i = ms.xy_ij[2*c], j = ms.xy_ij[2*c+1];
          int t = (j / tj) * ntx + i / ti;
-         pl.slot_of_xy[c] = tile_id[t] * P + (j % tj) * ti + (i % ti);   // ti*tj <= P lanes used
+         pl.slot_of_xy[c] = tile_id[t] * P + lane_of_pos[(j % tj) * ti + (i % ti)];   // ti*tj <= P lanes used
       }
       pl.npatch_b = np;
    } else {
@@ -421,6 +442,8 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
                if (exported[(int64_t)p * P + l]) { cp.eidx[(int64_t)p * P + l] = (uint8_t)std::min(254, n); n++; }
             cp.max_export = std::max(cp.max_export, n);
          }
+         cp.inline_ok = pl.nperim > 0;
+         for (int64_t sl = 0; sl < S; sl++) if (exported[sl] && (sl % P) >= PERIM_MAX) cp.inline_ok = false;
          // the staged tile kernel: shared tiles, <= 2 incoming faces, double-buffered ring, and a
          // halo that fits the 256-wide staging rows
          cp.fast = cp.tiles && cp.fin <= 2 && cp.ring == 2 && cp.max_halo <= 32 && cp.max_export <= 32 &&

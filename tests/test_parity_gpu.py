@@ -85,7 +85,9 @@ def test_single_sweep_cartesian_3d():
                  {"store_psi": 0, "tile_i": 8, "tile_j": 8},
                  # groups a dataflow task sweeps back to back (default 4 -> one block of 3 here): no merging,
                  # a ragged last block, and merged rows holding only the edge copies
-                 {"group_merge": 1}, {"group_merge": 2}, {"group_merge": 2, "store_psi": 0, "dt_max": 3}):
+                 {"group_merge": 1}, {"group_merge": 2}, {"group_merge": 2, "store_psi": 0, "dt_max": 3},
+                 # perimeter-first lane order: neighbouring patches read the psi rows themselves, no edge copies
+                 {"inline_edges": 1}, {"inline_edges": 1, "store_psi": 0}, {"inline_edges": 1, "tile_i": 8, "tile_j": 4}):
         dev = pb.SNDevice(em, xs, quad, **opts)
         dev.set("flux-moments", phi0.reshape(-1))
         dev.source(keff)
@@ -205,7 +207,8 @@ def test_sweep_schedule_independence(monkeypatch):
     quad = syn.level_symmetric(4)
     ref = None
     for opts, dbg in (({"wave_launch": 1}, None), ({}, None), ({"group_merge": 8}, None), ({"group_merge": 8}, "16"),
-                      ({"group_merge": 1}, "16"), ({"group_merge": 3, "store_psi": 0}, "16")):
+                      ({"group_merge": 1}, "16"), ({"group_merge": 3, "store_psi": 0}, "16"),
+                      ({"inline_edges": 1}, "16")):
         if dbg is None:
             monkeypatch.delenv("PAMPA_SN_DBG", raising=False)
         else:
