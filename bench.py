@@ -37,6 +37,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, nargs=3, default=[216, 216, 216])
+    ap.add_argument("--mesh", default="cartesian", choices=["cartesian", "hex"],
+                    help="hex: synthetic unstructured extruded hexagonal core (BASELINE config 5 family); "
+                         "informational, the bench line of record is the Cartesian default")
+    ap.add_argument("--rings", type=int, default=120, help="hex mesh: rings of hexagons around the centre")
     ap.add_argument("--groups", type=int, default=8)
     ap.add_argument("--order", type=int, default=8)
     ap.add_argument("--cpu-scale", type=int, default=2, help="CPU sample: mesh edge divided by this")
@@ -48,6 +52,10 @@ def parse():
 
 
 def workload_name(a):
+    if a.mesh == "hex":
+        nxy = 3 * a.rings * (a.rings + 1) + 1
+        return "synthetic 3D unstructured extruded hex core %d hexagons x %d layers = %d cells, S%d, %d groups" % (
+            nxy, a.size[2], nxy * a.size[2], a.order, a.groups)
     return "synthetic 3D extruded Cartesian core %dx%dx%d=%d cells, S%d, %d groups" % (
         a.size[0], a.size[1], a.size[2], a.size[0] * a.size[1] * a.size[2], a.order, a.groups)
 
@@ -154,7 +162,11 @@ def run_b200(a, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     nx, ny, nz = a.size
-    mesh, xs = syn.checkerboard_core(nx, ny, nz, num_groups=a.groups)
+    if a.mesh == "hex":
+        mesh, xs, _ = syn.hex_core(a.rings, nz, pitch=1.0, dz=1.0, num_groups=a.groups, seed=54321)
+        a.no_cpu_baseline = True          # the oracle's C port is Cartesian only
+    else:
+        mesh, xs = syn.checkerboard_core(nx, ny, nz, num_groups=a.groups)
     quad = syn.level_symmetric(a.order)
     M = len(quad.weights)
     # sharding: by energy group when the groups divide evenly over the ranks (allgather of the group
@@ -220,7 +232,8 @@ def run_b200(a, rank, world, local_rank):
         if per_update:
             traffic = per_update * U_own / max(1, info0["sweep_launches"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "sn_sweep_flow_kernel",
+                "traffic": traffic if a.mesh == "cartesian" else None,
+                "kernel": "sn_sweep_flow_kernel" if info0["tile_classes"] > 0 else "sn_sweep_kernel (generic)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_update": b_alg, "launches_per_step": info0["sweep_launches"],
                 "algorithmic_bytes_per_launch": b_alg * U_own / max(1, info0["sweep_launches"]),

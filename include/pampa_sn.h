@@ -117,6 +117,8 @@ typedef struct {
                                     perimeter lanes of the neighbouring patch's psi rows directly instead of
                                     compact edge copies behind each row (6 GB less written per sweep at C4, but
                                     no faster: measured 22.35 vs 21.90 ms per iteration); 0: default */
+   int32_t no_graph;             /* 1: never replay the sweep's launch sequence from a CUDA graph (plans with >= 32
+                                    launches per sweep are captured once and replayed; A/B testing) */
 } pampa_sn_options;
 
 void pampa_sn_default_options(pampa_sn_options* opts);

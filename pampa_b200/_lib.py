@@ -43,7 +43,7 @@ class Options(C.Structure):
     _fields_ = [("device", i32), ("store_psi", i32), ("patch_cells", i32), ("tile_i", i32), ("tile_j", i32),
                 ("z_chunk", i32), ("rank", i32), ("num_ranks", i32), ("shard_mode", i32), ("verbose", i32),
                 ("dt_max", i32), ("generic_only", i32), ("single_stream", i32),
-                ("anderson_depth", i32), ("wave_launch", i32), ("group_merge", i32), ("inline_edges", i32)]
+                ("anderson_depth", i32), ("wave_launch", i32), ("group_merge", i32), ("inline_edges", i32), ("no_graph", i32)]
 
 
 class Info(C.Structure):

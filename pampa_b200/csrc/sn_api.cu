@@ -111,6 +111,9 @@ struct pampa_sn_handle {
    std::vector<char> class_fast;
    int32_t *d_fast_classes = nullptr, *d_fast_chunks = nullptr;
    int nfast_classes = 0, nfast_chunks = 0;
+   bool use_graph = false, graph_failed = false;
+   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // one per parity of the alternating boundary buffers
+   int64_t launches_per_sweep = 0;
    int groups_generic = 0;               // launch groups of the generic kernel (it accumulates into phi_new with atomics)
    int gm = 1;                           // owned groups per block of the step-major arrays (sn_kernels.cuh)
    int32_t* d_gown = nullptr;            // [Gown] group of a local index
@@ -220,7 +223,8 @@ int do_source(pampa_sn_handle* h) {
    return 0;
 }
 
-int do_sweep(pampa_sn_handle* h) {
+// the launch sequence of one sweep (issued directly, or captured once into a CUDA graph)
+int sweep_launches(pampa_sn_handle* h) {
    SweepGlobals gp = h->globals();
    if (h->nls > 0) {
       launch_ls_rhs(gp, h->d_ls_ptr, h->d_ls_nbr, h->d_ls_coef, h->ls_nnz, h->d_dir_chunk, h->d_dir_d,
@@ -274,6 +278,50 @@ int do_sweep(pampa_sn_handle* h) {
       launch_unshear_phi(gp, h->d_chunks, h->d_classes, h->d_fast_chunks, h->nfast_chunks, h->plan.npatch_b,
                          h->groups_generic == 0 ? 1 : 0, h->stream);
       h->launches++;
+   }
+   return 0;
+}
+
+// One sweep.  Plans with many small launches (unstructured meshes: one launch per wavefront, ordering class
+// and kernel variant, thousands per sweep) are launch-bound, so their sequence -- fixed for the life of the
+// handle but for the two boundary buffers that alternate -- is captured once per buffer parity into a CUDA
+// graph, fork / join over the class streams included, and replayed.
+int do_sweep(pampa_sn_handle* h) {
+   const bool graphed = h->use_graph && !h->graph_failed;
+   if (!graphed) {
+      if (sweep_launches(h)) return 1;
+   } else {
+      const int par = h->bnd_cur;
+      if (!h->graph_exec[par]) {
+         const int64_t l0 = h->launches;
+         cudaGraph_t graph = nullptr;
+         cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+         int rc = 0;
+         if (e == cudaSuccess) {
+            std::vector<cudaEvent_t>* kev = h->kernel_events;
+            h->kernel_events = nullptr;                  // timing events cannot be recorded inside a capture
+            rc = sweep_launches(h);
+            h->kernel_events = kev;
+            e = cudaStreamEndCapture(h->stream, &graph);
+         }
+         if (e == cudaSuccess && !rc) e = cudaGraphInstantiate(&h->graph_exec[par], graph, 0);
+         if (graph) cudaGraphDestroy(graph);
+         h->launches_per_sweep = h->launches - l0;
+         h->launches = l0;
+         if (rc) return 1;
+         if (e != cudaSuccess) {                         // fall back to direct launches, loudly in verbose mode
+            cudaGetLastError();
+            h->graph_failed = true; h->graph_exec[par] = nullptr;
+            if (h->opts.verbose) std::printf("pampa_sn: sweep graph capture failed (%s), launching directly\n", cudaGetErrorString(e));
+            if (sweep_launches(h)) return 1;
+            h->bnd_cur = 1 - h->bnd_cur;
+            return 0;
+         }
+      }
+      if (h->kernel_events) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, h->stream); h->kernel_events->push_back(ev); }
+      SN_CUDA(h, cudaGraphLaunch(h->graph_exec[par], h->stream));
+      if (h->kernel_events) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, h->stream); h->kernel_events->push_back(ev); }
+      h->launches += h->launches_per_sweep;
    }
    h->bnd_cur = 1 - h->bnd_cur;      // what this sweep wrote is what the next one reads
    return 0;
@@ -364,6 +412,7 @@ void pampa_sn_default_options(pampa_sn_options* o) {
    o->store_psi = 1;
    o->group_merge = 0;
    o->inline_edges = 0;
+   o->no_graph = 0;
    o->num_ranks = 1;
 }
 
@@ -755,6 +804,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       }
       h->groups_generic = 0;
       for (const LaunchGroup& lg : h->groups) if (lg.kind != 1) h->groups_generic++;
+      h->use_graph = h->groups.size() >= 32 && !h->opts.no_graph;
       if (!h->opts.store_psi && !h->groups.empty())
          SN_FAIL(h, "store_psi = 0 needs every ordering class on the dataflow tile kernel (Cartesian mesh, no "
                     "least-squares term, wave_launch = 0)");
@@ -803,6 +853,7 @@ int pampa_sn_destroy(pampa_sn_handle* h) {
       if (h->cls_stream[i]) { cudaStreamSynchronize(h->cls_stream[i]); cudaStreamDestroy(h->cls_stream[i]); }
       if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
    }
+   for (int i = 0; i < 2; i++) if (h->graph_exec[i]) cudaGraphExecDestroy(h->graph_exec[i]);
    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
    if (h->ev0) cudaEventDestroy(h->ev0);
    if (h->ev1) cudaEventDestroy(h->ev1);

@@ -471,7 +471,10 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
    // ---- z chunks and the launch schedule ---------------------------------------------------
    int Kc = pl.nz;
    if (in.opts.z_chunk > 0) Kc = std::min(pl.nz, in.opts.z_chunk);
-   else if (pl.has_z && pl.tile_classes < (int)pl.classes.size()) Kc = std::min(pl.nz, 32);
+   // level-chunk patches (unstructured meshes) form a chain per ordering class: the sweep time goes like
+   // (patches + z chunks) x (layers per chunk + local levels), and the local levels are few -- short z chunks
+   // win (measured on a 43 561-hexagon x 100-layer core, S8: 63 / 47 / 44 / 47 ms per sweep at 32 / 16 / 8 / 4)
+   else if (pl.has_z && pl.tile_classes < (int)pl.classes.size()) Kc = std::min(pl.nz, 8);
    else if (pl.has_z && in.opts.num_ranks > 2 && in.opts.wave_launch) {
       // sharded over many GPUs a rank owns too few sweeps to fill its SMs wavefront by wavefront:
       // pipeline in z as well (tasks x nzc, critical path ~ (patch levels + nzc) x (levels + nz/nzc))

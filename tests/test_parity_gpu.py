@@ -149,23 +149,26 @@ def test_single_sweep_hex_3d():
     qd = np.einsum("nfg,nf->ng", op.sig_s, phi0) + op.chi * np.sum(op.nusf * phi0, axis=1)[:, None]
     b = np.repeat((qd * op.vol[:, None]).reshape(N * G), M)
     psi = spla.splu(op.T.tocsc()).solve(b).reshape(N, G, M)
-    for opts in ({}, {"patch_cells": 32}, {"patch_cells": 64, "z_chunk": 2}):
+    # small patches / z chunks: >= 32 launches per sweep, replayed from a CUDA graph unless no_graph is set
+    for opts in ({}, {"patch_cells": 32}, {"patch_cells": 64, "z_chunk": 2}, {"patch_cells": 32, "no_graph": 1}):
         dev = pb.SNDevice(em, xs, quad, **opts)
-        dev.set("flux-moments", phi0.reshape(-1))
-        dev.source(1.0)
-        dev.sweep()
-        dev.reduce()
-        got_psi = dev.get("angular-flux").reshape(N, G, M)
-        assert util.rel_l2(got_psi, psi) < 1e-12
+        for _ in range(3):                      # the graph is captured in the first sweep of each buffer parity
+            dev.set("flux-moments", phi0.reshape(-1))
+            dev.source(1.0)
+            dev.sweep()
+            dev.reduce()
+            got_psi = dev.get("angular-flux").reshape(N, G, M)
+            assert util.rel_l2(got_psi, psi) < 1e-12
         dev.close()
 
 
 def test_keff_hex_3d():
     em, xs, quad, op = _hex_problem(5, 6, 2, 4, seed=4)
     sol = orc.solve_matrix_free(op)
-    dev, k, it = _solve(em, xs, quad, patch_cells=64)
-    _check_solution(dev, k, sol.keff, sol.phi, sol.power)
-    dev.close()
+    for opts in ({"patch_cells": 64}, {"patch_cells": 64, "no_graph": 1}):
+        dev, k, it = _solve(em, xs, quad, **opts)
+        _check_solution(dev, k, sol.keff, sol.phi, sol.power)
+        dev.close()
 
 
 def test_errors_are_loud():
