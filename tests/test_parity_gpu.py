@@ -225,3 +225,30 @@ def test_sweep_schedule_independence(monkeypatch):
         else:
             assert k == ref[0], (opts, dbg)
             assert np.array_equal(phi, ref[1]), (opts, dbg)
+
+
+def test_full_size_properties():
+    """BASELINE config 4 at its own size (216^3 cells, S8, 8 groups; the oracle cannot run there): properties that
+    do not depend on the size.  The checkerboard core, its vacuum boundaries and the level-symmetric quadrature are
+    invariant under x <-> y, x <-> z and the three reflections, so the flux moments of any number of source
+    iterations from a flat start must be too (every octant's sweep maps onto another one's); they are positive;
+    and the dataflow sweep must reproduce the stream-ordered wavefront sweep bit for bit."""
+    n, G = 216, 8
+    mesh, xs = syn.checkerboard_core(n, n, n, num_groups=G)
+    quad = syn.level_symmetric(8)
+    dev = pb.SNDevice(mesh, xs, quad)
+    assert dev.info()["updates_per_sweep"] == n ** 3 * 80 * G
+    k = dev.iterate(2)
+    phi = dev.get("flux-moments").reshape(n, n, n, G)       # [z][y][x][g]
+    dev.close()
+    assert phi.min() > 0.0
+    scale = np.abs(phi).max()
+    for name, other in (("x<->y", phi.transpose(0, 2, 1, 3)), ("x<->z", phi.transpose(2, 1, 0, 3)),
+                        ("-x", phi[:, :, ::-1]), ("-y", phi[:, ::-1]), ("-z", phi[::-1])):
+        assert np.abs(phi - other).max() < 1e-12 * scale, name
+    dev = pb.SNDevice(mesh, xs, quad, wave_launch=1)
+    k2 = dev.iterate(2)
+    phi2 = dev.get("flux-moments").reshape(n, n, n, G)
+    dev.close()
+    assert k2 == k
+    assert np.array_equal(phi2, phi)
