@@ -1,5 +1,6 @@
 // capi.cpp -- the reference's C API (src/pampa.cxx:8-113) over a global Driver.
 #include <cstdio>
+#include "vtk.hpp"
 #include <cstdlib>
 
 #include "../../include/pampa.h"
@@ -94,6 +95,27 @@ int pampa_debug_describe(const char* deck, double* out) {
             for (int g2 = 0; g2 < G; g2++) out[12] += (1 + g + 2 * g2) * mat->sigmaScattering(g, g2, 0.0);
          }
       }
+   }
+   delete mesh;
+   for (auto* m : materials) delete m;
+   for (auto* s : solvers) delete s;
+   return rc;
+}
+
+/* Test hook (no GPU needed): parse a deck and write its mesh to <prefix>.vtk in the reference's format
+ * (src/vtk.cxx:28-121), whatever the deck's own `vtk` switch says. */
+int pampa_debug_write_mesh_vtk(const char* deck, const char* prefix) {
+   pampa::Mesh* mesh = nullptr;
+   std::vector<pampa::Material*> materials;
+   std::vector<pampa::Solver*> solvers;
+   std::vector<double> dt;
+   pampa::Parser parser;
+   int rc = parser.read(std::string(deck), &mesh, materials, solvers, dt);
+   if (!rc && mesh) {
+      const bool on = pampa::vtk::on;
+      pampa::vtk::on = true;
+      rc = mesh->writeVTK(std::string(prefix), -1);
+      pampa::vtk::on = on;
    }
    delete mesh;
    for (auto* m : materials) delete m;

@@ -1,8 +1,15 @@
 #include "mesh.hpp"
+#include "vtk.hpp"
 
 #include <algorithm>
 
 namespace pampa {
+
+int Mesh::writeVTK(const std::string& prefix, int n) const {
+   PAMPA_CHECK(vtk::write(prefix, n, points, getNumPoints(), cell_point_ptr, cell_points, num_cells, cells.materials),
+               "unable to write the mesh");
+   return 0;
+}
 
 int Mesh::findBoundary(const std::string& name) const {
    for (size_t i = 0; i < boundaries.size(); i++) if (boundaries[i] == name) return (int)i;
@@ -104,6 +111,31 @@ int CartesianMesh::build() {
       return k * num_xy_cells + xy_id[(size_t)j * nx + i];
    };
 
+   // mesh points (x fastest, then y, then z) and cell point lists in the gmsh order of the reference
+   points.clear(); cell_point_ptr.assign(1, 0); cell_points.clear();
+   for (int k = 0; k < nz + 1; k++)
+      for (int j = 0; j < ny + 1; j++)
+         for (int i = 0; i < nx + 1; i++) points.insert(points.end(), {x[i], y[j], z[k]});
+   for (int k = 0; k < nzz; k++)
+      for (int j = 0; j < nyy; j++)
+         for (int i = 0; i < nx; i++) {
+            if (at(k, j, i) == -1) continue;
+            const int sx = nx + 1, sxy = (nx + 1) * (ny + 1);
+            cell_points.push_back(i + j * sx + k * sxy);
+            cell_points.push_back((i + 1) + j * sx + k * sxy);
+            if (ny > 0) {
+               cell_points.push_back((i + 1) + (j + 1) * sx + k * sxy);
+               cell_points.push_back(i + (j + 1) * sx + k * sxy);
+               if (nz > 0) {
+                  cell_points.push_back(i + j * sx + (k + 1) * sxy);
+                  cell_points.push_back((i + 1) + j * sx + (k + 1) * sxy);
+                  cell_points.push_back((i + 1) + (j + 1) * sx + (k + 1) * sxy);
+                  cell_points.push_back(i + (j + 1) * sx + (k + 1) * sxy);
+               }
+            }
+            cell_point_ptr.push_back((int)cell_points.size());
+         }
+
    cells.volumes.clear(); cells.centroids.clear(); cells.materials.clear(); cells.global_indices.clear();
    faces = Faces();
    faces.ptr.push_back(0);
@@ -203,6 +235,19 @@ int UnstructuredExtrudedMesh::build() {
    num_cells = nxy * nzz;
    auto px = [&](int p) { return xy_points[2 * (size_t)p]; };
    auto py = [&](int p) { return xy_points[2 * (size_t)p + 1]; };
+
+   // mesh points (the xy points repeated for every z level) and cell point lists: bottom polygon, then top
+   points.clear(); cell_point_ptr.assign(1, 0); cell_points.clear();
+   for (int k = 0; k < nz + 1; k++)
+      for (int p = 0; p < num_xy_points; p++) points.insert(points.end(), {px(p), py(p), z[k]});
+   for (int k = 0; k < nzz; k++)
+      for (int i = 0; i < nxy; i++) {
+         for (int a = xy_cell_ptr[i]; a < xy_cell_ptr[i + 1]; a++) cell_points.push_back(xy_cell_points[a] + k * num_xy_points);
+         if (nz > 0)
+            for (int a = xy_cell_ptr[i]; a < xy_cell_ptr[i + 1]; a++)
+               cell_points.push_back(xy_cell_points[a] + (k + 1) * num_xy_points);
+         cell_point_ptr.push_back((int)cell_points.size());
+      }
 
    // polygon areas and centroids (shoelace)
    std::vector<double> area(nxy), ccx(nxy), ccy(nxy);

@@ -42,6 +42,13 @@ class Mesh {
    const std::vector<std::string>& getBoundaries() const { return boundaries; }
    const std::vector<BoundaryCondition>& getBoundaryConditions() const { return bcs; }
    int findBoundary(const std::string& name) const;
+   // points and per-cell point lists in the reference's numbering (src/CartesianMesh.cxx:157-231,
+   // src/UnstructuredExtrudedMesh.cxx:160-207), kept for the .vtk output (src/Mesh.cxx:397-405)
+   int getNumPoints() const { return (int)(points.size() / 3); }
+   const std::vector<double>& getPoints() const { return points; }
+   const std::vector<int>& getCellPointPtr() const { return cell_point_ptr; }
+   const std::vector<int>& getCellPoints() const { return cell_points; }
+   int PAMPA_WARN_UNUSED writeVTK(const std::string& prefix, int n) const;
    void addBoundary(const std::string& name) { boundaries.push_back(name); }
 
    // extruded structure (read-only accessors the reference keeps private:
@@ -62,6 +69,8 @@ class Mesh {
    bool has_z_faces = false;
    std::vector<double> dz;
    std::vector<int> xy_ij;
+   std::vector<double> points;            // [np][3]
+   std::vector<int> cell_point_ptr, cell_points;
    int PAMPA_WARN_UNUSED readBC(const std::vector<std::string>& line, std::ifstream& file);
 };
 

@@ -1,4 +1,5 @@
 #include "parser.hpp"
+#include "vtk.hpp"
 
 namespace pampa {
 
@@ -43,6 +44,8 @@ int Parser::read(const std::string& filename, Mesh** mesh, std::vector<Material*
          PAMPA_CHECK(input::read_axis(dt, nt, line[1], file), "wrong dt data");
       } else if (k == "vtk") {
          PAMPA_CHECK(line.size() < 2 || line.size() > 3, "wrong number of arguments for keyword '" + k + "'");
+         PAMPA_CHECK(input::read(vtk::on, line[1]), "wrong switch for .vtk output");
+         if (line.size() == 3) PAMPA_CHECK(input::read(vtk::dn, 1, INT_MAX, line[2]), "wrong .vtk output interval");
       } else if (k == "petsc") {
          // PETSc / SLEPc options of the reference's linear algebra: there is none here
          PAMPA_CHECK(line.size() != 3, "wrong number of arguments for keyword '" + k + "'");

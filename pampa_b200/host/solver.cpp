@@ -1,4 +1,5 @@
 #include "solver.hpp"
+#include "vtk.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -48,8 +49,9 @@ int PhysicsSolver::initialize(bool transient) {
    return 0;
 }
 
-int PhysicsSolver::output(const std::string& path, int n, bool) const {
+int PhysicsSolver::output(const std::string& path, int n, bool write_mesh) const {
    PAMPA_CHECK(printLog(n), "unable to print the solution summary to standard output");
+   if (write_mesh) PAMPA_CHECK(mesh->writeVTK(path + "/output", n), "unable to write the mesh in .vtk format");
    PAMPA_CHECK(writeVTK(path, n), "unable to write the solution in .vtk format");
    return 0;
 }
@@ -388,7 +390,19 @@ long SNSolver::getFieldSize(const std::string& fname) const {
    return Solver::getFieldSize(fname);
 }
 
-int SNSolver::writeVTK(const std::string&, int) const { return 0; }
+// scalar flux, angular flux and thermal power appended to the mesh file (src/SNSolver.cxx:754-770); the angular
+// flux (cells x groups x directions) is fetched from the device only when .vtk output is switched on
+int SNSolver::writeVTK(const std::string& path, int n) const {
+   if (!vtk::on || (n % vtk::dn != 0)) return 0;
+   PAMPA_CHECK(vtk::write(path + "/output", n, "flux", phi.data(), num_cells, num_energy_groups),
+               "unable to write the scalar flux");
+   std::vector<double> angular((size_t)num_cells * num_energy_groups * num_directions);
+   PAMPA_CHECK(getField(angular.data(), "angular-flux"), "unable to get the angular flux");
+   PAMPA_CHECK(vtk::write(path + "/output", n, "flux", angular.data(), num_cells, num_energy_groups, num_directions),
+               "unable to write the angular flux");
+   PAMPA_CHECK(vtk::write(path + "/output", n, "power", q.data(), num_cells), "unable to write the thermal power");
+   return 0;
+}
 
 int SNSolver::finalize() {
    if (device) { PAMPA_CHECK(pampa_sn_destroy(device), "unable to destroy the device solver"); device = nullptr; }

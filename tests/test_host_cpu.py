@@ -180,6 +180,35 @@ def test_host_reads_the_reference_decks(decks, ref):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("case", ["slab_s2", "pwr_cartesian_s2", "pwr_unstructured_s2"])
+def test_host_mesh_vtk(decks, case, tmp_path):
+    """Mesh::writeVTK in the reference's format (src/vtk.cxx:28-121, src/CartesianMesh.cxx:157-231,
+    src/UnstructuredExtrudedMesh.cxx:160-207): point / cell counts, VTK cell types, 1-based materials, and the
+    point lists really are the corners of the oracle's cells (their mean is the cell centroid on these meshes)."""
+    lib = _host_lib()
+    path = os.path.join(decks, case, "input.pmp")
+    prefix = str(tmp_path / "mesh_data")
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(path))
+    try:
+        assert lib.pampa_debug_write_mesh_vtk(b"input.pmp", prefix.encode()) == 0
+    finally:
+        os.chdir(cwd)
+    v = util.read_vtk(prefix + ".vtk")
+    m = orc.read_deck(path).mesh
+    assert len(v["cells"]) == m.num_cells == v["num_cell_data"]
+    npts = {len(c) for c in v["cells"]}
+    want_type = {2: 3, 3: 5, 4: 9, 6: 13, 8: 12, 12: 16}
+    assert all(t == want_type[len(c)] for t, c in zip(v["types"], v["cells"]))
+    assert npts <= ({2} if m.num_dims == 1 else {3, 4, 5, 6} if m.num_dims == 2 else {6, 8, 12})
+    assert max(max(c) for c in v["cells"]) < len(v["points"])
+    name, mats = v["scalars"][0]
+    assert name == "materials" and len(v["scalars"]) == 1
+    assert np.array_equal(mats.astype(int), m.materials + 1)
+    cen = np.array([v["points"][c].mean(axis=0) for c in v["cells"]])
+    assert np.allclose(cen[:, :m.num_dims], m.centroids[:, :m.num_dims], atol=1e-5)   # files carry 7 digits
+
+
 def test_host_c_api_exports():
     hdr = open(os.path.join(ROOT, "include", "pampa.h")).read()
     lib = _host_lib()

@@ -87,3 +87,37 @@ def test_fields_through_the_c_api(decks):
         lib.pampa_finalize_steady_state(ctypes.byref(err)); assert err.value == 0
     finally:
         os.chdir(cwd)
+
+
+def test_vtk_output(decks, tmp_path):
+    """`vtk 1` in the main input: output_0.vtk = the mesh followed by flux_<g>, flux_<g>_<m> and power blocks in the
+    reference's order (src/PhysicsSolver.cxx:19-28, src/SNSolver.cxx:754-770, src/vtk.cxx:123-170), holding the same
+    numbers pampa_get_field returns (to the 7 digits the file carries)."""
+    import shutil
+    case = tmp_path / "case"
+    shutil.copytree(os.path.join(decks, "pwr_cartesian_s2"), case)
+    with open(case / "input.pmp", "a") as f:
+        f.write("\nvtk 1\n")
+    exe = os.path.join(ROOT, "pampa_b200", "bin", "pampa")
+    r = subprocess.run([exe, "input.pmp"], cwd=case, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    v = util.read_vtk(str(case / "output_0.vtk"))
+    z = np.load(os.path.join(util.GOLDEN, "pwr_cartesian_s2.npz"))
+    N, G = z["phi"].shape
+    M = 8
+    names = [n for n, _ in v["scalars"]]
+    assert names == (["materials"] + ["flux_%d" % (g + 1) for g in range(G)] +
+                     ["flux_%d_%d" % (g + 1, m + 1) for g in range(G) for m in range(M)] + ["power"])
+    assert len(v["cells"]) == N
+    vals = dict(v["scalars"])
+    for g in range(G):
+        assert util.rel_l2(vals["flux_%d" % (g + 1)], z["phi"][:, g]) < 1e-5
+    assert util.rel_l2(vals["power"], z["power"]) < 1e-5
+    # after the two normalisations (phi = 4 pi sum w psi scaled to the power, src/SNSolver.cxx:288 and
+    # src/NeutronicSolver.cxx:63; psi scaled to the power without the 4 pi, src/SNSolver.cxx:324) the fields
+    # satisfy sum_m w_m psi_m = phi; level-symmetric S2 has equal weights 1/8
+    for g in range(G):
+        s = sum(vals["flux_%d_%d" % (g + 1, m + 1)] for m in range(M)) / M
+        assert util.rel_l2(s, vals["flux_%d" % (g + 1)]) < 1e-5
+    # without the switch nothing is written
+    assert not os.path.exists(os.path.join(decks, "pwr_cartesian_s2", "output_0.vtk"))

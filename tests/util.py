@@ -146,3 +146,42 @@ def load_golden(name):
     if "ls_cell" in z:
         ls = pb.LSCorrection(z["ls_cell"], z["ls_ptr"], z["ls_nbr"], z["ls_omega"], z["ls_nvec"])
     return em, xs, quad, ls, z
+
+
+def read_vtk(path):
+    """Parse a legacy ASCII .vtk file as the reference writes it (src/vtk.cxx): points, ragged cells, cell types
+    and the ordered list of (name, values) SCALARS blocks."""
+    tok = open(path).read().split("\n")
+    assert tok[0] == "# vtk DataFile Version 3.0" and tok[2] == "ASCII" and tok[3] == "DATASET UNSTRUCTURED_GRID"
+    i = 4
+    out = {"scalars": []}
+    while i < len(tok):
+        line = tok[i].split()
+        i += 1
+        if not line:
+            continue
+        if line[0] == "POINTS":
+            n = int(line[1])
+            out["points"] = np.array([[float(x) for x in tok[i + a].split()] for a in range(n)])
+            i += n
+        elif line[0] == "CELLS":
+            n = int(line[1])
+            rows = [[int(x) for x in tok[i + a].split()] for a in range(n)]
+            assert sum(len(r) for r in rows) == int(line[2])
+            assert all(r[0] == len(r) - 1 for r in rows)
+            out["cells"] = [r[1:] for r in rows]
+            i += n
+        elif line[0] == "CELL_TYPES":
+            n = int(line[1])
+            out["types"] = np.array([int(tok[i + a]) for a in range(n)])
+            i += n
+        elif line[0] == "CELL_DATA":
+            out["num_cell_data"] = int(line[1])
+        elif line[0] == "SCALARS":
+            assert line[2:] == ["double", "1"] and tok[i] == "LOOKUP_TABLE default"
+            n = out["num_cell_data"]
+            out["scalars"].append((line[1], np.array([float(tok[i + 1 + a]) for a in range(n)])))
+            i += 1 + n
+        else:
+            raise AssertionError("unexpected line in %s: %r" % (path, tok[i - 1]))
+    return out
