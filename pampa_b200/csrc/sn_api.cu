@@ -1259,6 +1259,7 @@ int pampa_sn_get_info(pampa_sn_handle* h, pampa_sn_info* info) {
    info->updates_per_sweep = pl.owned_updates;
    info->sweep_launches = (int64_t)(h->groups.size() + h->flows.size());
    for (auto& g : h->groups) info->sweep_tasks += g.count;
+   for (auto& f : h->flows) info->sweep_tasks += f.count;
    info->num_classes = (int64_t)pl.classes.size(); info->num_chunks = (int64_t)pl.chunks.size();
    info->tile_classes = pl.tile_classes;
    info->device_bytes = h->device_bytes;
