@@ -251,6 +251,11 @@ def run_b200(a, rank, world, local_rank):
         host_phi = torch.empty(n_phi, dtype=torch.float64, pin_memory=True).numpy()
         host_pow = torch.empty(mesh.num_cells, dtype=torch.float64, pin_memory=True).numpy()
         host_in[:] = 1.0
+        # untimed warm-up of the same call sequence (first use allocates the device staging buffer)
+        dev.set("flux-moments", host_in)
+        dev.iterate(1)
+        dev.get("scalar-flux", out=host_phi)
+        dev.get("power", out=host_pow)
         barrier()
         t0 = time.perf_counter()
         dev.update_xs(xs)

@@ -1081,9 +1081,10 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       // after wait_group, without the fences, is a race: readers that followed the writer closely saw
       // rows of the previous sweep.)
       double* psi_rows = ch->psi + prow * rowg;
-      // publish every 8th row: the fences take longer than the two steps of slack the buffer ring gives
-      // (measured at C4: 22.7 / 19.1 / 17.7 ms per sweep publishing every 2nd / 4th / 8th row)
-      const int pub = ((gp.dbg >> 4) & 0xff) ? ((gp.dbg >> 4) & 0xff) : 8;
+      // publish every 16th row: the fences take longer than the two steps of slack the buffer ring gives
+      // (measured at C4: 22.7 / 19.1 / 17.15 / 16.85 / 16.71 / 16.65 ms per sweep publishing every 2nd / 4th /
+      // 8th / 12th / 16th / 24th row; one rank of an 8-way sharded run: 2.73 / 2.55 / 2.51 ms at 4 / 8 / 16)
+      const int pub = ((gp.dbg >> 4) & 0xff) ? ((gp.dbg >> 4) & 0xff) : 16;
       const unsigned bytes = row_cols * sizeof(double);
       for (int step = 0; step < nsteps; step++) {
          while (ld_acquire_cta_smem(&s_rows_done) <= step) {}
