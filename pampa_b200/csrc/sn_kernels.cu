@@ -1523,39 +1523,54 @@ void launch_update_k(const double* sums, ReduceScalars* sc, int update_k, cudaSt
 constexpr int AA_MAX = 8;
 struct AAHist { double* f[AA_MAX]; double* g[AA_MAX]; };
 
+// Streams the flat [G][n] arrays two doubles per thread with every load of a step issued before its stores
+// (9 x 16 B in flight per thread at full depth): bandwidth-bound, ~12 x 0.645 GB per call at C4.  Holes need no
+// test: phi and phi_new are zero there, so g, f and the dot products get zeros.
 __global__ void __launch_bounds__(256)
-sn_aa_store_kernel(const double* __restrict__ phi, double* __restrict__ phi_new, const int32_t* __restrict__ mats,
+sn_aa_store_kernel(const double* __restrict__ phi, double* __restrict__ phi_new,
                    const int32_t* __restrict__ gloc, int owned_only, int G, int64_t n, double inv_prod,
                    AAHist hist, int cur, int nhist, double* __restrict__ partials) {
    double dots[AA_MAX];
 #pragma unroll
    for (int j = 0; j < AA_MAX; j++) dots[j] = 0.0;
-   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-        idx += (int64_t)gridDim.x * blockDim.x) {
-      if (mats[idx] < 0) continue;
-      for (int g = 0; g < G; g++) {
-         if (owned_only && gloc[g] < 0) continue;
-         const int64_t a = (int64_t)g * n + idx;
-         const double xg = phi_new[a] * inv_prod;
-         const double f = xg - phi[a];
-         phi_new[a] = 0.0;
-         hist.g[cur][a] = xg;
-         hist.f[cur][a] = f;
+   double* __restrict__ fc = hist.f[0];
+   double* __restrict__ gc = hist.g[0];
 #pragma unroll
-         for (int j = 0; j < AA_MAX; j++)
-            if (j < nhist) dots[j] = fma(f, j == cur ? f : hist.f[j][a], dots[j]);
+   for (int j = 1; j < AA_MAX; j++) if (j == cur) { fc = hist.f[j]; gc = hist.g[j]; }
+   const int64_t total = (int64_t)G * n;                 // n = layers x (patches x 256): even
+   for (int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; a < total;
+        a += (int64_t)gridDim.x * blockDim.x * 2) {
+      if (owned_only && gloc[a / n] < 0) continue;
+      const double2 p = *reinterpret_cast<const double2*>(phi_new + a);
+      const double2 x = *reinterpret_cast<const double2*>(phi + a);
+      double2 hf[AA_MAX];
+#pragma unroll
+      for (int j = 0; j < AA_MAX; j++)
+         hf[j] = (j < nhist && j != cur) ? *reinterpret_cast<const double2*>(hist.f[j] + a) : make_double2(0.0, 0.0);
+      const double2 xg = make_double2(p.x * inv_prod, p.y * inv_prod);
+      const double2 f = make_double2(xg.x - x.x, xg.y - x.y);
+      *reinterpret_cast<double2*>(phi_new + a) = make_double2(0.0, 0.0);
+      *reinterpret_cast<double2*>(gc + a) = xg;
+      *reinterpret_cast<double2*>(fc + a) = f;
+#pragma unroll
+      for (int j = 0; j < AA_MAX; j++) {
+         const double2 o = (j == cur) ? f : hf[j];
+         dots[j] = fma(f.x, o.x, fma(f.y, o.y, dots[j]));
       }
    }
-   __shared__ double sh[256];
-   for (int j = 0; j < nhist; j++) {
-      sh[threadIdx.x] = dots[j];
-      __syncthreads();
-      for (int off = 128; off > 0; off >>= 1) {
-         if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
-         __syncthreads();
-      }
-      if (threadIdx.x == 0) partials[(size_t)j * gridDim.x + blockIdx.x] = sh[0];
-      __syncthreads();
+   __shared__ double sh[AA_MAX][8];
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+   for (int j = 0; j < AA_MAX; j++) {
+      double v = dots[j];
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) sh[j][warp] = v;
+   }
+   __syncthreads();
+   if ((int)threadIdx.x < nhist) {
+      double v = 0.0;
+      for (int w = 0; w < 8; w++) v += sh[threadIdx.x][w];
+      partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
    }
 }
 
@@ -1628,8 +1643,8 @@ void launch_aa_store(const double* phi, double* phi_new, const int32_t* mats, co
                      cudaStream_t st) {
    AAHist h{};
    for (int j = 0; j < AA_MAX; j++) { h.f[j] = hist_f[j]; h.g[j] = hist_g[j]; }
-   sn_aa_store_kernel<<<nblocks, 256, 0, st>>>(phi, phi_new, mats, gloc, owned_only, G, n, inv_prod, h, cur, nhist,
-                                               partials);
+   (void)mats;
+   sn_aa_store_kernel<<<nblocks, 256, 0, st>>>(phi, phi_new, gloc, owned_only, G, n, inv_prod, h, cur, nhist, partials);
    sn_aa_dots_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, nhist, dots);
 }
 
