@@ -286,12 +286,16 @@ def run_b200(a, rank, world, local_rank):
     # source iteration to |dk| < 1e-7 and a relative flux change < 1e-7)
     keff_solve = None
     if not a.no_solve:
+        # cold start: flat flux, k = 1 (the timed steps above leave a settled k estimate behind, which saves
+        # ~40 of ~200 accelerated iterations)
         dev.set("flux-moments", np.ones(mesh.num_cells * a.groups))
+        dev.set("keff", np.ones(1))
         barrier()
         t0 = time.perf_counter()
         ks, its = dev.solve_keff(tol_k=1e-7, tol_phi=1e-7, max_it=20000)
         torch.cuda.synchronize()
-        keff_solve = {"wall_s": time.perf_counter() - t0, "iterations": its, "keff": ks, "tol_k": 1e-7, "tol_phi": 1e-7}
+        keff_solve = {"wall_s": time.perf_counter() - t0, "iterations": its, "keff": ks, "tol_k": 1e-7, "tol_phi": 1e-7,
+                      "start": "flat flux, k = 1"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

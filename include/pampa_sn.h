@@ -154,7 +154,8 @@ int pampa_sn_iterate_timed(pampa_sn_handle* h, int32_t iterations, double* keff,
 /* Fields in the reference layouts (src/SNSolver.cxx:721-747):
  *   "scalar-flux" [i][g], "angular-flux" [i][g][m], "power" [i], "production-rate" [i],
  *   "delayed-source" [i]  (get);   "temperature" [i], "delayed-source" [i] (set, stored only);
- *   "flux-moments" [i][g] (get/set): the raw iteration state sum_m w_m psi, un-normalised.
+ *   "flux-moments" [i][g] (get/set): the raw iteration state sum_m w_m psi, un-normalised;
+ *   "keff" [1] (get/set): the current eigenvalue estimate / the one the next iteration starts from.
  * Normalised as the reference does after the eigen-solve (src/NeutronicSolver.cxx:46-78,
  * src/SNSolver.cxx:302-341) by the last pampa_sn_solve_keff. */
 int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out);

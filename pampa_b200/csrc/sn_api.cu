@@ -1117,6 +1117,7 @@ int64_t pampa_sn_field_size(const pampa_sn_handle* h, const char* name) {
    if (s == "scalar-flux" || s == "flux-moments") return N * h->G;
    if (s == "angular-flux") return N * h->G * h->M;
    if (s == "power" || s == "production-rate" || s == "temperature" || s == "delayed-source") return N;
+   if (s == "keff") return 1;
    return -1;
 }
 
@@ -1128,6 +1129,11 @@ int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
    const int64_t count = pampa_sn_field_size(h, name);
    if (count < 0) SN_FAIL(h, "unable to find field '" + s + "'");
    if (s == "angular-flux" && !h->opts.store_psi) SN_FAIL(h, "the angular flux is not kept in memory (store_psi = 0)");
+   if (s == "keff") {
+      if (sync_scalars(h)) return 1;
+      out[0] = h->sc.keff;
+      return 0;
+   }
    if (s == "temperature" || s == "delayed-source") {
       std::vector<double>& v = s == "temperature" ? h->h_temperature : h->h_delayed;
       if (s == "delayed-source" && h->solved) {
@@ -1204,6 +1210,14 @@ int pampa_sn_set(pampa_sn_handle* h, const char* name, const double* in) {
    const int64_t N = (int64_t)h->plan.nxy * h->plan.nz;
    if (s == "temperature") { h->h_temperature.assign(in, in + N); return 0; }
    if (s == "delayed-source") { h->h_delayed.assign(in, in + N); return 0; }
+   if (s == "keff") {              // eigenvalue estimate the next iteration starts from (1 value)
+      SN_CUDA(h, cudaSetDevice(h->device));
+      if (!(in[0] > 0.0)) SN_FAIL(h, "the eigenvalue estimate must be positive");
+      SN_CUDA(h, cudaMemcpyAsync(&h->d_sc->keff, in, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      SN_CUDA(h, cudaStreamSynchronize(h->stream));
+      h->sc.keff = in[0]; h->keff = in[0];
+      return 0;
+   }
    if (s == "flux-moments") {      // iteration state / initial guess, layout [i][g]
       SN_CUDA(h, cudaSetDevice(h->device));
       const int64_t count = N * h->G;
