@@ -123,6 +123,15 @@ int pampa_debug_write_mesh_vtk(const char* deck, const char* prefix) {
    return rc;
 }
 
+/* Test hook: write `count` doubles as <prefix>_<n>.ptc whatever the `petsc dump` switch says. */
+int pampa_debug_write_ptc(const char* prefix, int n, const double* v, long count) {
+   const bool on = pampa::ptc::dump;
+   pampa::ptc::dump = true;
+   const int rc = pampa::ptc::write(std::string(prefix), n, v, count);
+   pampa::ptc::dump = on;
+   return rc;
+}
+
 double pampa_get_keff(int* error) {
    const double k = pampa_driver.getKeff();
    *error = k < 0.0 ? 1 : 0;

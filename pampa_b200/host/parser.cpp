@@ -47,8 +47,11 @@ int Parser::read(const std::string& filename, Mesh** mesh, std::vector<Material*
          PAMPA_CHECK(input::read(vtk::on, line[1]), "wrong switch for .vtk output");
          if (line.size() == 3) PAMPA_CHECK(input::read(vtk::dn, 1, INT_MAX, line[2]), "wrong .vtk output interval");
       } else if (k == "petsc") {
-         // PETSc / SLEPc options of the reference's linear algebra: there is none here
+         // `petsc dump <0|1>` switches the .ptc output of the solution; the other options address the
+         // reference's PETSc / SLEPc linear algebra, of which there is none here: accepted and ignored
          PAMPA_CHECK(line.size() != 3, "wrong number of arguments for keyword '" + k + "'");
+         if (line[1] == "dump")
+            PAMPA_CHECK(input::read(ptc::dump, line[2]), "wrong switch to write the solution in PETSc format");
       } else if (k == "include") {
          PAMPA_CHECK(line.size() != 2, "wrong number of arguments for keyword '" + k + "'");
          PAMPA_CHECK(read(line[1], mesh, materials, solvers, dt), "unable to parse " + line[1]);

@@ -53,6 +53,7 @@ int PhysicsSolver::output(const std::string& path, int n, bool write_mesh) const
    PAMPA_CHECK(printLog(n), "unable to print the solution summary to standard output");
    if (write_mesh) PAMPA_CHECK(mesh->writeVTK(path + "/output", n), "unable to write the mesh in .vtk format");
    PAMPA_CHECK(writeVTK(path, n), "unable to write the solution in .vtk format");
+   PAMPA_CHECK(writePETSc(n), "unable to write the solution in PETSc format");
    return 0;
 }
 
@@ -401,6 +402,15 @@ int SNSolver::writeVTK(const std::string& path, int n) const {
    PAMPA_CHECK(vtk::write(path + "/output", n, "flux", angular.data(), num_cells, num_energy_groups, num_directions),
                "unable to write the angular flux");
    PAMPA_CHECK(vtk::write(path + "/output", n, "power", q.data(), num_cells), "unable to write the thermal power");
+   return 0;
+}
+
+// angular flux in PETSc's binary Vec format (src/SNSolver.cxx:773-780), fetched only when `petsc dump 1` is set
+int SNSolver::writePETSc(int n) const {
+   if (!ptc::dump) return 0;
+   std::vector<double> angular((size_t)num_cells * num_energy_groups * num_directions);
+   PAMPA_CHECK(getField(angular.data(), "angular-flux"), "unable to get the angular flux");
+   PAMPA_CHECK(ptc::write("angular_flux", n, angular.data(), (long)angular.size()), "unable to write the angular flux");
    return 0;
 }
 

@@ -69,6 +69,7 @@ class PhysicsSolver : public Solver {
    virtual int PAMPA_WARN_UNUSED build() = 0;
    virtual int PAMPA_WARN_UNUSED printLog(int n = 0) const = 0;
    virtual int PAMPA_WARN_UNUSED writeVTK(const std::string& path, int n = 0) const = 0;
+   virtual int PAMPA_WARN_UNUSED writePETSc(int n = 0) const = 0;
 };
 
 class NeutronicSolver : public PhysicsSolver {
@@ -122,6 +123,7 @@ class SNSolver : public NeutronicSolver {
    int PAMPA_WARN_UNUSED buildMatrices(int n, double dt, double t) override;
    int PAMPA_WARN_UNUSED getSolution(int n = 0) override;
    int PAMPA_WARN_UNUSED writeVTK(const std::string& path, int n = 0) const override;
+   int PAMPA_WARN_UNUSED writePETSc(int n = 0) const override;
    int PAMPA_WARN_UNUSED packCrossSections(std::vector<double>& st, std::vector<double>& ss, std::vector<double>& nsf,
                                            std::vector<double>& ksf, std::vector<double>& chi, std::vector<double>& beta,
                                            std::vector<int>& cell_material) const;

@@ -1,5 +1,9 @@
 #include "vtk.hpp"
 
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+
 namespace pampa {
 namespace vtk {
 
@@ -73,4 +77,39 @@ int write(const std::string& prefix, int n, const std::string& name, const doubl
 }
 
 }   // namespace vtk
+
+namespace ptc {
+
+bool dump = false;
+
+namespace {
+void put_be32(std::ofstream& f, uint32_t x) {
+   const unsigned char b[4] = {(unsigned char)(x >> 24), (unsigned char)(x >> 16), (unsigned char)(x >> 8), (unsigned char)x};
+   f.write((const char*)b, 4);
+}
+}   // namespace
+
+int write(const std::string& prefix, int n, const double* v, long count) {
+   if (!dump) return 0;
+   PAMPA_CHECK(count < 0 || count > INT_MAX, "vector too long for the PETSc binary format with 32-bit indices");
+   const std::string filename = prefix + "_" + std::to_string(n) + ".ptc";
+   std::ofstream file(filename, std::ios_base::out | std::ios_base::binary);
+   PAMPA_CHECK(!file.is_open(), "unable to open " + filename);
+   put_be32(file, 1211214u);                  // VEC_FILE_CLASSID
+   put_be32(file, (uint32_t)count);
+   std::vector<unsigned char> buf((size_t)std::min<long>(count, 1 << 16) * 8);
+   for (long i0 = 0; i0 < count; i0 += 1 << 16) {
+      const long m = std::min<long>(1 << 16, count - i0);
+      for (long i = 0; i < m; i++) {
+         uint64_t bits;
+         std::memcpy(&bits, v + i0 + i, 8);
+         for (int b = 0; b < 8; b++) buf[(size_t)i * 8 + b] = (unsigned char)(bits >> (56 - 8 * b));
+      }
+      file.write((const char*)buf.data(), m * 8);
+   }
+   PAMPA_CHECK(!file.good(), "unable to write " + filename);
+   return 0;
+}
+
+}   // namespace ptc
 }   // namespace pampa

@@ -23,4 +23,12 @@ int PAMPA_WARN_UNUSED write(const std::string& prefix, int n, const std::string&
                             int num_cells, int num_groups = 1, int num_directions = 1);
 
 }   // namespace vtk
+
+// `petsc dump 1` (src/Parser.cxx:231-234): solution vectors in PETSc's binary Vec format, <prefix>_<n>.ptc
+// (src/petsc.cxx:491-511 -> VecView on a binary viewer): big-endian int32 class id 1211214, int32 length, then
+// the values as big-endian float64 -- readable by PetscBinaryIO / VecLoad.  No PETSc is involved here.
+namespace ptc {
+extern bool dump;
+int PAMPA_WARN_UNUSED write(const std::string& prefix, int n, const double* v, long count);
+}   // namespace ptc
 }   // namespace pampa

@@ -209,6 +209,20 @@ def test_host_mesh_vtk(decks, case, tmp_path):
     assert np.allclose(cen[:, :m.num_dims], m.centroids[:, :m.num_dims], atol=1e-5)   # files carry 7 digits
 
 
+def test_host_ptc_writer(tmp_path):
+    """`petsc dump 1`: PETSc binary Vec files (big-endian class id 1211214, length, float64 values) as
+    VecView writes them on a binary viewer (src/petsc.cxx:491-511)."""
+    lib = _host_lib()
+    v = np.random.default_rng(3).normal(size=70001)
+    prefix = str(tmp_path / "angular_flux")
+    lib.pampa_debug_write_ptc.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_long]
+    assert lib.pampa_debug_write_ptc(prefix.encode(), 0, v.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), v.size) == 0
+    raw = open(prefix + "_0.ptc", "rb").read()
+    head = np.frombuffer(raw[:8], dtype=">i4")
+    assert head[0] == 1211214 and head[1] == v.size and len(raw) == 8 + 8 * v.size
+    assert np.array_equal(np.frombuffer(raw[8:], dtype=">f8"), v)
+
+
 def test_host_c_api_exports():
     hdr = open(os.path.join(ROOT, "include", "pampa.h")).read()
     lib = _host_lib()
