@@ -93,3 +93,20 @@ def test_c_port_matches_oracle():
     ph = phi.reshape(G, -1).T
     ph = ph / np.sum(ph * op.kapsf * op.vol[:, None])
     assert util.rel_l2(ph, sol.phi) < 1e-7
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the
+    contract's keys, produced by the oracle's C port on the host cores, no GPU involved."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--size", "48", "48", "48"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "updates/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "Cartesian core 48x48x48" in line["config"]["workload"]
