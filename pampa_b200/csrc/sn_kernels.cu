@@ -1019,8 +1019,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
          double* dst = bufs + ((st - 1) & (D - 1)) * ROWS + PS + PEDGE + hl;
          if (kind == SRC_GLOBAL) {
             const int need = st + need0;
-            if (gp.dbg & 4) { do { seen = ld_acquire_gpu(flag); } while (seen < need); }
-            else if (!(gp.dbg & 1)) while (seen < need) seen = ld_acquire_gpu(flag);
+            while (seen < need) seen = ld_acquire_gpu(flag);
 #pragma unroll
             for (int d = 0; d < DT; d++) cp_async8(dst + d * PSXS, gsrc + (int64_t)st * rowg + d * gstr);
          } else if (EXTRAS) {

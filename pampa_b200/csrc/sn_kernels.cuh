@@ -98,7 +98,8 @@ struct SweepGlobals {
    int32_t store_psi;
    int32_t nmat;
    int32_t uniform_dz;        // 1: every layer has the same thickness (or the mesh has no z faces)
-   int32_t dbg;               // development knobs of the flow kernel (PAMPA_SN_DBG), 0 in production
+   int32_t dbg;               // PAMPA_SN_DBG: (dbg >> 4) & 0xff = rows between two publishes of a dataflow task's
+                              // progress counter (0: default 16; the stress test uses 1); no other bits are read
 };
 
 struct ReduceScalars {        // device-resident iteration state
