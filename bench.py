@@ -11,7 +11,10 @@ iteration: scattering + fission source, transport sweep of every direction and g
 k-eff reduction (and the NCCL allreduce of the flux moments when sharded over N GPUs).
 
 metric = cell*angle*group updates per second = cells * directions * groups * steps / time.
-The sweep is sharded over the ranks by angle set; the total work is fixed => scaling "strong".
+Sharded over N ranks by energy group when G divides by N (peer-to-peer exchange of the group slabs of the
+flux moments, sharded source / reduction), else by angle set (allreduce of the flux moments); the total work
+is fixed => scaling "strong".  Before the timed region a sharded run solves a small problem on every rank
+and compares k-eff and the scalar flux with a one-GPU solve of rank 0 ("sharded_parity" in the line).
 """
 import argparse
 import json
@@ -47,6 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded-vs-one-GPU check of multi-GPU runs")
     ap.add_argument("--opts", default="{}", help="JSON of pampa_sn_options overrides")
     return ap.parse_args()
 
@@ -94,6 +98,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_problem(a, scale):
     from oracle import sweep_cpu
     from pampa_b200 import synthetic as syn
@@ -101,10 +112,15 @@ def cpu_problem(a, scale):
     mesh, xs = syn.checkerboard_core(n[0], n[1], n[2], num_groups=a.groups)
     quad = syn.level_symmetric(a.order)
     mats = mesh.materials.reshape(n[2], n[1], n[0])
+    # every host core this process may use (torch.distributed.run exports OMP_NUM_THREADS=1: not inherited), and
+    # the angular flux is stored, as in the GPU arm (store_psi = 1), when it fits a bounded share of host memory
+    ncell = n[0] * n[1] * n[2]
+    psi_bytes = ncell * len(quad.weights) * a.groups * 8
+    store_psi = psi_bytes <= 16e9
     cpu = sweep_cpu.SweepCPU(np.ones(n[0]), np.ones(n[1]), np.ones(n[2]), mats, xs.sigma_total,
                              xs.sigma_scattering, xs.nu_sigma_fission, xs.chi_effective, quad.directions,
-                             quad.weights)
-    updates = n[0] * n[1] * n[2] * len(quad.weights) * a.groups
+                             quad.weights, threads=host_threads(), store_psi=store_psi)
+    updates = ncell * len(quad.weights) * a.groups
     return cpu, updates, n
 
 
@@ -118,9 +134,33 @@ def cpu_time_steps(a, scale, steps, warmup):
     for _ in range(steps):
         k = cpu.iterate(phi, k, 1)
     dt = time.perf_counter() - t0
-    sample = "%dx%dx%d sub-core of the same workload (1/%d of the cells), %d source iterations, fp64" % (
-        n[0], n[1], n[2], scale ** 3, steps)
+    sample = "%dx%dx%d sub-core of the same workload (1/%d of the cells), %d source iterations, fp64, psi %s" % (
+        n[0], n[1], n[2], scale ** 3, steps, "stored" if cpu.psi is not None else "not stored")
     return updates * steps / dt, dt / steps * 1e3, cpu.threads, sample
+
+
+def reference_algorithm_timing():
+    """SURVEY 8(d) baseline 1: the reference's own algorithm -- monolithic R, sparse LU, Arnoldi on R^-1 F
+    (src/petsc.cxx:193-197) -- restated with scipy (oracle.solve_monolithic) on the reference's slab cases,
+    rebuilt from the committed fixtures.  Real PETSc / SLEPc cannot be installed here; one process, wall time."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    from oracle import pampa_oracle as orc
+    out = []
+    for name in ("slabs_s2", "slabs_s4"):
+        em, xs, quad, ls, z = util.load_golden(name)
+        obcs = [0, orc.VACUUM, orc.VACUUM]
+        mesh = orc.build_cartesian_mesh(em.xy_area, None, None, em.materials, ["-x", "+x"], obcs)
+        t0 = time.perf_counter()
+        op = orc.build_operator(mesh, util.xs_to_oracle(xs), xs.num_groups, int(z["order"]), 1.0,
+                                "literal_zero_init", obcs)
+        sol = orc.solve_monolithic(op)
+        dt = time.perf_counter() - t0
+        n = op.N * op.G * op.M
+        out.append({"case": name, "unknowns": n, "wall_s": dt, "keff": sol.keff,
+                    "golden_keff": float(z["golden_keff"]), "unknowns_per_s": n / dt})
+    return {"kind": "restatement of reference algorithm (scipy SuperLU + ARPACK, 1 process)", "cores": 1,
+            "note": "assembly + LU + eigen-solve of the monolithic system; C4 has 6.4e9 unknowns", "cases": out}
 
 
 def run_reference(a, rank):
@@ -142,7 +182,8 @@ def run_reference(a, rank):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "cpu_sample": sample},
+            "config": {"workload": workload_name(a), "cpu_sample": sample, "same_config": scale == 1,
+                       "sample_fraction_of_cells": 1.0 / scale ** 3},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -150,6 +191,51 @@ def run_reference(a, rank):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+def comm_setup(dev, dist, rank):
+    import torch
+    from pampa_b200 import problem as pb
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(pb.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    dev.comm_init(bytes(uid.cpu().numpy().tobytes()))
+
+
+def sharded_parity(a, dist, rank, world, local_rank, shard_opts):
+    """Sharded-versus-single-GPU check carried by every multi-GPU bench line: a reduced copy of the workload
+    (48^3 cells, same generator, same order and groups, reflective -x / -y so that the boundary-flux exchange is
+    exercised too) is solved to 1e-10 on rank 0 alone and then by all ranks with the run's sharding."""
+    import torch
+    from pampa_b200 import problem as pb, synthetic as syn
+    n = 48
+    bcs = {"-x": pb.BC_REFLECTIVE, "-y": pb.BC_REFLECTIVE}
+    mesh, xs = syn.checkerboard_core(n, n, n, num_groups=a.groups, bcs=bcs)
+    quad = syn.level_symmetric(a.order)
+    ref = None
+    if rank == 0:
+        one = pb.SNDevice(mesh, xs, quad, device=local_rank)
+        k1, it1 = one.solve_keff(tol_k=1e-10, tol_phi=1e-9)
+        ref = (k1, one.get("scalar-flux"), it1)
+        one.close()
+    dev = pb.SNDevice(mesh, xs, quad, device=local_rank, rank=rank, num_ranks=world, **shard_opts)
+    comm_setup(dev, dist, rank)
+    k, it = dev.solve_keff(tol_k=1e-10, tol_phi=1e-9)
+    phi = dev.get("scalar-flux")
+    dev.close()
+    ks = torch.tensor([k, -k], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ks, op=dist.ReduceOp.MAX)
+    spread = float(ks[0] + ks[1])                       # max k - min k over the ranks
+    out = None
+    if rank == 0:
+        l2 = float(np.linalg.norm(phi - ref[1]) / np.linalg.norm(ref[1]))
+        mx = float(np.max(np.abs(phi - ref[1]) / np.abs(ref[1])))
+        out = {"problem": "%d^3 cells, S%d, %d groups, reflective -x/-y" % (n, a.order, a.groups),
+               "keff_1gpu": ref[0], "keff_sharded": k, "keff_diff": k - ref[0], "keff_spread_over_ranks": spread,
+               "phi_rel_l2": l2, "phi_max_rel": mx, "iterations": [ref[2], it],
+               "ok": bool(abs(k - ref[0]) < 1e-7 and l2 < 1e-6 and mx < 1e-5 and spread < 1e-12)}
+    return out
+
+
 def run_b200(a, rank, world, local_rank):
     import torch
     from pampa_b200 import problem as pb, synthetic as syn
@@ -174,13 +260,13 @@ def run_b200(a, rank, world, local_rank):
     opts = dict(device=local_rank, rank=rank, num_ranks=world,
                 shard_mode=1 if (world > 1 and a.groups % world == 0) else 0)
     opts.update(json.loads(a.opts))
+    parity = None
+    if world > 1 and not a.no_parity:
+        parity = sharded_parity(a, dist, rank, world, local_rank,
+                                {k: v for k, v in opts.items() if k not in ("device", "rank", "num_ranks")})
     dev = pb.SNDevice(mesh, xs, quad, **opts)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(pb.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        dev.comm_init(bytes(uid.cpu().numpy().tobytes()))
+        comm_setup(dev, dist, rank)
 
     info0 = dev.info()
     U_total = mesh.num_cells * M * a.groups          # whole-job updates per step
@@ -224,15 +310,20 @@ def run_b200(a, rank, world, local_rank):
         kernel_ms = float(t[0])
     achieved = U_own * a.steps * b_alg / (kernel_ms * 1e-3) / 1e9
     achieved_sweep = U_own * a.steps * b_alg / (sweep_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes per launch from the committed ncu --set full capture of this very configuration (one GPU, default
+    # options, Cartesian workload); it cannot be measured inside an un-profiled run, and it is NOT extrapolated to
+    # sharded runs or other options, whose padding and task shapes differ: null there
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
-    if os.path.exists(tpath):
-        # DRAM bytes per update from the committed ncu --set full capture, scaled to the average launch
-        per_update = json.load(open(tpath)).get("dram_bytes_per_update")
+    if os.path.exists(tpath) and world == 1 and a.mesh == "cartesian" and not json.loads(a.opts) \
+            and list(a.size) == [216, 216, 216] and a.order == 8 and a.groups == 8:
+        tj = json.load(open(tpath))
+        per_update = tj.get("dram_bytes_per_update")
         if per_update:
             traffic = per_update * U_own / max(1, info0["sweep_launches"])
+            traffic_src = "ncu capture %s (dram__bytes_read.sum + dram__bytes_write.sum per launch)" % tj.get("source", "profiles/")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic if a.mesh == "cartesian" else None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "sn_sweep_flow_kernel" if info0["tile_classes"] > 0 else "sn_sweep_kernel (generic)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_update": b_alg, "launches_per_step": info0["sweep_launches"],
@@ -303,7 +394,12 @@ def run_b200(a, rank, world, local_rank):
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         v, ms, threads, sample = cpu_time_steps(a, max(a.cpu_scale, 2), 2, 1)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                        "same_config": False}
+        try:
+            cpu_baseline["reference_algorithm"] = reference_algorithm_timing()
+        except Exception as e:           # informational: never lose the bench line over it
+            cpu_baseline["reference_algorithm"] = {"error": str(e)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
@@ -313,6 +409,7 @@ def run_b200(a, rank, world, local_rank):
                            "l2_policy": "working set (%.1f GB) far exceeds the 126 MB L2" % (info0["device_bytes"] / 1e9),
                            "keff_after_steps": k, "options": json.loads(a.opts)},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "keff_solve": keff_solve,
+                "sharded_parity": parity,
                 "gpu_launches": launches,
                 "clocks": clocks}
         print(json.dumps(line), flush=True)

@@ -22,7 +22,12 @@ void pampa_set_field(const double* v, const char name[], int* error);
  * host code can allocate field buffers without knowing the mesh. */
 long pampa_get_field_size(const char name[], int* error);
 double pampa_get_keff(int* error);
-int pampa_debug_describe(const char* deck, double* out16);   /* host-only digest for the CPU tests */
+/* Host-only entry points used by the CPU test-suite (no device needed): a digest of a parsed deck, the mesh of
+ * a deck in the reference's .vtk format (src/Mesh.cxx writeVTK), and a vector in PETSc's binary Vec format
+ * (src/petsc.cxx:491-511). */
+int pampa_debug_describe(const char* deck, double* out16);
+int pampa_debug_write_mesh_vtk(const char* deck, const char* prefix);
+int pampa_debug_write_ptc(const char* prefix, int n, const double* v, long count);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,17 @@ typedef struct {
    int32_t bc_plus_z;
    int32_t num_bcs;
    const int32_t* bc_types;      /* [1 + num_bcs], entry 0 unused; PAMPA_SN_BC_* */
+   /* mixed-face-interpolation delta < 1 (src/SNSolver.hxx:16 default 0.1, weights src/SNSolver.cxx:193-198):
+    * the face flux is a blend of the upwind value and the linear interpolation between the two cell centres.
+    * The sweep inverts the delta = 1 (upwind) part; the remainder
+    *    (T_delta - T_1) psi |_i = sum_f |Omega.n_f| A_f / V_i * kappa_f * (psi_nbr - psi_i),
+    *    kappa_f = (1-delta) r_if / r_ii2 on outgoing faces, (1-delta) r_i2f / r_ii2 on incoming faces,
+    * is applied to the angular flux of the previous sweep and moved to the right-hand side (a deferred
+    * correction that converges with the source iteration to the eigenpair of the reference's matrix).
+    * NULL / 1.0: pure upwind.  The z faces use the same formula with the layer thicknesses. */
+   const double*  xy_face_kout;  /* [num_xy_cells*max_xy_faces] (1-delta) r_if / r_ii2, 0 on boundary faces */
+   const double*  xy_face_kin;   /* [num_xy_cells*max_xy_faces] (1-delta) r_i2f / r_ii2, 0 on boundary faces */
+   double face_interpolation_delta;   /* delta in (0, 1]; 0 is read as 1 (structs zeroed by older callers) */
 } pampa_sn_mesh;
 
 /* Multigroup cross sections per material (src/Material.hxx:130-169). */
@@ -156,6 +167,8 @@ int pampa_sn_iterate_timed(pampa_sn_handle* h, int32_t iterations, double* keff,
  *   "delayed-source" [i]  (get);   "temperature" [i], "delayed-source" [i] (set, stored only);
  *   "flux-moments" [i][g] (get/set): the raw iteration state sum_m w_m psi, un-normalised;
  *   "keff" [1] (get/set): the current eigenvalue estimate / the one the next iteration starts from.
+ *   "angular-flux-min" [1] (get): smallest stored angular-flux value (the reference fails the solve when it is
+ *   negative, src/SNSolver.cxx:329; possible only with delta < 1 or the least-squares boundary term).
  * Normalised as the reference does after the eigen-solve (src/NeutronicSolver.cxx:46-78,
  * src/SNSolver.cxx:302-341) by the last pampa_sn_solve_keff. */
 int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out);

@@ -13,7 +13,8 @@
  * Parity: checked against oracle/pampa_oracle.py (itself pinned to the reference's goldens) by
  * tests/test_oracle.py::test_c_port_matches_oracle.
  *
- * Layouts: phi, q [g][k][j][i]; materials [k][j][i]; psi is not stored (per-direction planes).
+ * Layouts: phi, q [g][k][j][i]; materials [k][j][i]; psi [g][m][k][j][i] is stored only when the caller
+ * passes a buffer (the bench does, so that the CPU arm moves the bytes the GPU arm's store_psi = 1 moves).
  */
 #include <math.h>
 #include <stdint.h>
@@ -29,7 +30,18 @@ typedef struct {
    const int32_t* mats;                 /* [nz][ny][nx] */
    const double *sigma_t, *sigma_s, *nusf, *chi;   /* [mat][g], [mat][g_from][g_to], ... */
    const double *dirs, *w;              /* [M][3], [M] */
+   double* psi;                         /* optional [G][M][nz][ny][nx] angular-flux store (NULL: not kept) */
 } sweep_problem;
+
+/* Thread count used by the parallel regions.  The bench sets it explicitly: under torch.distributed.run the
+ * environment carries OMP_NUM_THREADS=1, which would silently time one core. */
+void sweep_cpu_set_threads(int n) {
+#ifdef _OPENMP
+   if (n > 0) omp_set_num_threads(n);
+#else
+   (void)n;
+#endif
+}
 
 int sweep_cpu_threads(void) {
 #ifdef _OPENMP
@@ -57,16 +69,29 @@ static void source(const sweep_problem* p, const double* phi, double keff, doubl
    }
 }
 
-/* phi_new[g] = sum_m w_m psi_m[g].  Groups in turn; the M directions of a group are independent
- * sweeps spread over the threads, each accumulating into a private buffer that is then summed
- * in a fixed order (deterministic, no atomics). */
+/* phi_new[g] = sum_m w_m psi_m[g].  The (group, direction) sweeps are independent given q.  Groups are taken in
+ * batches of gb so that the gb * M sweeps of a batch divide evenly over the threads (80 directions over 32 threads
+ * would leave the last round half empty); each thread accumulates into a private buffer that is then summed in a
+ * fixed order (deterministic, no atomics). */
+static int group_batch(int G, int M, int nt) {
+   int best = 1;
+   double best_eff = 0.0;
+   for (int gb = 1; gb <= G && gb <= 4; gb++) {
+      const int tasks = gb * M, rounds = (tasks + nt - 1) / nt;
+      const double eff = (double)tasks / ((double)rounds * nt);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = gb; }
+   }
+   return best;
+}
+
 static void sweep_all(const sweep_problem* p, const double* q, double* phi_new) {
    const int nx = p->nx, ny = p->ny, nz = p->nz, G = p->G, M = p->M;
    const int64_t n = (int64_t)nx * ny * nz;
    const int nt = sweep_cpu_threads();
-   double* priv = (double*)malloc(sizeof(double) * n * nt);
-   for (int g = 0; g < G; g++) {
-      const double* qg = q + (int64_t)g * n;
+   const int gb = group_batch(G, M, nt);
+   double* priv = (double*)malloc(sizeof(double) * n * nt * gb);
+   for (int g0 = 0; g0 < G; g0 += gb) {
+      const int ng = (G - g0 < gb) ? G - g0 : gb;
 #pragma omp parallel
       {
 #ifdef _OPENMP
@@ -74,12 +99,16 @@ static void sweep_all(const sweep_problem* p, const double* q, double* phi_new) 
 #else
          const int tid = 0;
 #endif
-         double* acc = priv + (int64_t)tid * n;
-         memset(acc, 0, sizeof(double) * n);
+         double* acc0 = priv + (int64_t)tid * n * gb;
+         memset(acc0, 0, sizeof(double) * n * ng);
          double* plane = (double*)malloc(sizeof(double) * nx * ny);   /* psi of the previous layer */
          double* row = (double*)malloc(sizeof(double) * nx);          /* psi of the previous row */
-#pragma omp for schedule(dynamic, 1)
-         for (int m = 0; m < M; m++) {
+#pragma omp for schedule(static, 1)
+         for (int task = 0; task < ng * M; task++) {
+            const int g = g0 + task / M, m = task % M;
+            const double* qg = q + (int64_t)g * n;
+            double* acc = acc0 + (int64_t)(g - g0) * n;
+            double* psi_out = p->psi ? p->psi + ((int64_t)g * M + m) * n : NULL;
             const double ox = p->dirs[3 * m], oy = p->dirs[3 * m + 1], oz = p->dirs[3 * m + 2];
             const double ax = fabs(ox), ay = fabs(oy), az = fabs(oz), wm = p->w[m];
             const int sx = ox > 0 ? 1 : -1, sy = oy > 0 ? 1 : -1, sz = oz > 0 ? 1 : -1;
@@ -101,17 +130,20 @@ static void sweep_all(const sweep_problem* p, const double* q, double* phi_new) 
                      const double psi = (qg[c] + cx * up_x + cy * up_y + cz * up_z) / (st + cx + cy + cz);
                      up_x = psi; row[i] = psi; plane[j * nx + i] = psi;
                      acc[c] += wm * psi;
+                     if (psi_out) psi_out[c] = psi;
                   }
                }
             }
          }
          free(plane); free(row);
 #pragma omp barrier
+         for (int gi = 0; gi < ng; gi++) {
 #pragma omp for schedule(static)
-         for (int64_t c = 0; c < n; c++) {
-            double sum = 0.0;
-            for (int t2 = 0; t2 < nt; t2++) sum += priv[(int64_t)t2 * n + c];
-            phi_new[(int64_t)g * n + c] = sum;
+            for (int64_t c = 0; c < n; c++) {
+               double sum = 0.0;
+               for (int t2 = 0; t2 < nt; t2++) sum += priv[((int64_t)t2 * gb + gi) * n + c];
+               phi_new[(int64_t)(g0 + gi) * n + c] = sum;
+            }
          }
       }
    }

@@ -21,7 +21,8 @@ class Mesh(C.Structure):
                 ("xy_num_faces", p_i32), ("xy_neighbor", p_i32), ("xy_face_fx", p_f64), ("xy_face_fy", p_f64),
                 ("xy_face_cf", p_f64), ("xy_area", p_f64), ("xy_cx", p_f64), ("xy_cy", p_f64),
                 ("xy_ij", p_i32), ("dz", p_f64), ("materials", p_i32), ("bc_minus_z", i32),
-                ("bc_plus_z", i32), ("num_bcs", i32), ("bc_types", p_i32)]
+                ("bc_plus_z", i32), ("num_bcs", i32), ("bc_types", p_i32), ("xy_face_kout", p_f64),
+                ("xy_face_kin", p_f64), ("face_interpolation_delta", f64)]
 
 
 class XS(C.Structure):

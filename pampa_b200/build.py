@@ -43,7 +43,7 @@ def build_cuda(force=False):
     cu = _sources(CSRC, (".cu",))
     deps = cu + _sources(CSRC, (".cuh", ".hpp")) + _sources(os.path.join(ROOT, "include"), (".h",))
     if force or _newer(out, deps):
-        _run(["nvcc"] + NVCC_FLAGS + cu + ["-o", out, "-ldl"])
+        _run(["nvcc"] + NVCC_FLAGS + ["--threads", str(max(1, len(cu)))] + cu + ["-o", out, "-ldl"])
     return out
 
 

@@ -105,6 +105,14 @@ struct pampa_sn_handle {
    int32_t *d_ls_ptr = nullptr, *d_ls_nbr = nullptr, *d_dir_chunk = nullptr, *d_dir_d = nullptr;
    double *d_ls_coef = nullptr, *d_ls_dD = nullptr, *d_ls_rhs = nullptr;
    std::vector<int> dir_chunk, dir_d;
+   std::vector<double*> chunk_psi;       // host copy of ChunkDev::psi (field export)
+   // mixed-face-interpolation delta < 1: deferred correction (sn_delta_corr_kernel)
+   double delta = 1.0;
+   double* d_corr = nullptr;             // same size and layout as d_psi
+   int64_t psi_count = 0;
+   int32_t* d_fnb = nullptr;             // [Sb][F] base slot of the neighbour across lateral face f, -1: boundary
+   double *d_fvx = nullptr, *d_fvy = nullptr, *d_fkout = nullptr, *d_fkin = nullptr;   // [Sb][F]
+   int F = 0;
    bool extras = false;
    bool multi_stream = false;
    // staged tile kernel
@@ -148,6 +156,7 @@ struct pampa_sn_handle {
       gp.store_psi = opts.store_psi ? 1 : 0;
       gp.nmat = nmat;
       gp.uniform_dz = uniform_dz;
+      gp.corr_off = d_corr ? (int64_t)(d_corr - d_psi) : 0;
       { const char* e = std::getenv("PAMPA_SN_DBG"); gp.dbg = e ? std::atoi(e) : 0; }
       return gp;
    }
@@ -237,6 +246,17 @@ int sweep_launches(pampa_sn_handle* h) {
       if (gp.bnd_new) cudaMemsetAsync(gp.bnd_new, 0, (size_t)h->bnd_count * sizeof(double), h->stream);
       if (gp.bndz_new) cudaMemsetAsync(gp.bndz_new, 0, (size_t)h->bndz_count * sizeof(double), h->stream);
    }
+   if (h->d_corr) {
+      // delta < 1: (T_delta - T_1) applied to the angular flux of the previous sweep, chunk by chunk
+      for (size_t c = 0; c < h->plan.chunks.size(); c++) {
+         if (!h->chunk_psi[c]) continue;
+         const int cls = h->plan.chunks[c].cls;
+         launch_delta_corr(gp, (int)c, h->plan.classes[cls].npatch, h->d_pos_of[cls], h->d_fnb, h->d_fvx, h->d_fvy,
+                           h->d_fkout, h->d_fkin, h->F, 1.0 - h->delta, h->d_dz, h->d_corr + (h->chunk_psi[c] - h->d_psi),
+                           h->stream);
+         h->launches++;
+      }
+   }
    if (h->nfast_classes > 0) {
       launch_shear_q(gp, h->d_classes, h->d_fast_classes, h->nfast_classes, h->plan.npatch_b, h->stream);
       h->launches++;
@@ -256,8 +276,9 @@ int sweep_launches(pampa_sn_handle* h) {
    for (size_t f = 0; f < h->flows.size(); f++) {
       const FlowLaunch& fl = h->flows[f];
       cudaStream_t st = ns ? h->cls_stream[f % ns] : h->stream;
-      launch_sweep_flow(gp, h->d_tasks + fl.offset, fl.count, fl.dt, h->extras, h->d_flow_ctl + f, h->d_flow_ctl + 16,
-                        fl.mw.data(), fl.nch, st);
+      if (launch_sweep_flow(gp, h->d_tasks + fl.offset, fl.count, fl.dt, h->extras, h->d_flow_ctl + f, h->d_flow_ctl + 16,
+                            fl.mw.data(), fl.nch, st))
+         SN_FAIL(h, "internal: more chunks in a dataflow launch than its direction table holds");
       h->launches++;
    }
    for (const LaunchGroup& lg : h->groups) {
@@ -485,6 +506,13 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       h->err = "least-squares boundary interpolation is only supported on 1-D and 2-D meshes"; return fail(1);
    }
 
+   h->delta = mesh->face_interpolation_delta > 0.0 ? mesh->face_interpolation_delta : 1.0;
+   if (h->delta > 1.0) { h->err = "wrong weight between upwind and linear interpolation"; return fail(1); }
+   if (h->delta < 1.0) {
+      if (!mesh->xy_face_kout || !mesh->xy_face_kin) { h->err = "mixed-face-interpolation < 1 needs the xy_face_kout / xy_face_kin weights"; return fail(1); }
+      if (!h->opts.store_psi) { h->err = "mixed-face-interpolation < 1 needs the angular flux in memory (store_psi = 1)"; return fail(1); }
+   }
+
    int ndev = 0;
    cudaError_t e = cudaGetDeviceCount(&ndev);
    if (e != cudaSuccess || ndev == 0) {
@@ -571,9 +599,29 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          }
       if (dev_alloc(h, &h->d_psi, psi_doubles)) return 1;
       SN_CUDA(h, cudaMemsetAsync(h->d_psi, 0, (size_t)psi_doubles * sizeof(double), h->stream));
+      h->psi_count = psi_doubles;
+      if (h->delta < 1.0) {
+         if (dev_alloc(h, &h->d_corr, psi_doubles)) return 1;
+         SN_CUDA(h, cudaMemsetAsync(h->d_corr, 0, (size_t)psi_doubles * sizeof(double), h->stream));
+         const int F = mesh->max_xy_faces;
+         h->F = F;
+         std::vector<int32_t> fnb((size_t)Sb * F, -1);
+         std::vector<double> fvx((size_t)Sb * F, 0.0), fvy((size_t)Sb * F, 0.0), fko((size_t)Sb * F, 0.0), fki((size_t)Sb * F, 0.0);
+         for (int c = 0; c < pl.nxy; c++)
+            for (int f = 0; f < mesh->xy_num_faces[c]; f++) {
+               const size_t a = (size_t)c * F + f, b = (size_t)pl.slot_of_xy[c] * F + f;
+               const int nb = mesh->xy_neighbor[a];
+               if (nb < 0) continue;
+               fnb[b] = pl.slot_of_xy[nb];
+               fvx[b] = mesh->xy_face_fx[a] / mesh->xy_area[c]; fvy[b] = mesh->xy_face_fy[a] / mesh->xy_area[c];
+               fko[b] = mesh->xy_face_kout[a]; fki[b] = mesh->xy_face_kin[a];
+            }
+         if (dev_upload(h, &h->d_fnb, fnb) || dev_upload(h, &h->d_fvx, fvx) || dev_upload(h, &h->d_fvy, fvy) ||
+             dev_upload(h, &h->d_fkout, fko) || dev_upload(h, &h->d_fkin, fki)) return 1;
+      }
 
       // reflective boundary buffers
-      h->extras = false;
+      h->extras = h->delta < 1.0;       // the deferred correction is read on the kernels' EXTRAS path
       if (pl.num_rfaces > 0) {
          h->bnd_count = (int64_t)h->M * h->G * nz * pl.num_rfaces;
          for (int b = 0; b < 2; b++) {
@@ -657,7 +705,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          if (dev_upload(h, &d_eidx, cp.eidx)) return 1;
          cd.eidx = d_eidx;
          cd.q_sheared = nullptr;
-         h->class_fast[ci] = cp.fast && h->nls == 0 && h->nmat <= 4096 && !h->opts.generic_only;
+         h->class_fast[ci] = cp.fast && h->nls == 0 && h->delta == 1.0 && h->nmat <= 4096 && !h->opts.generic_only;
          if (h->class_fast[ci]) {
             bool any_owned = false;
             for (size_t c = 0; c < pl.chunks.size(); c++) any_owned |= (pl.chunks[c].cls == (int)ci && chunk_owned[c]);
@@ -722,6 +770,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
             }
          }
          cd.psi = chunk_owned[c] ? h->d_psi + psi_off[c] : nullptr;
+         h->chunk_psi.push_back(cd.psi);
          cd.phi_part = nullptr;
          if (chunk_owned[c] && h->class_fast[ch.cls]) {
             const ClassPlan& cpc = pl.classes[ch.cls];
@@ -992,6 +1041,8 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
    // the lagged LS boundary term depends on the angular flux of the previous sweep, which is not
    // part of the mixed state: keep the history short there (1-D / 2-D problems only)
    if (h->nls > 0 && depth > 3) depth = 3;
+   // same for the deferred correction of delta < 1, which is formed from the previous sweep's angular flux
+   if (h->d_corr && depth > 3) depth = 3;
    int it = 0;
    bool converged = false;
    h->psi_scale_factor = 1.0;
@@ -1117,7 +1168,7 @@ int64_t pampa_sn_field_size(const pampa_sn_handle* h, const char* name) {
    if (s == "scalar-flux" || s == "flux-moments") return N * h->G;
    if (s == "angular-flux") return N * h->G * h->M;
    if (s == "power" || s == "production-rate" || s == "temperature" || s == "delayed-source") return N;
-   if (s == "keff") return 1;
+   if (s == "keff" || s == "angular-flux-min") return 1;
    return -1;
 }
 
@@ -1132,6 +1183,18 @@ int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
    if (s == "keff") {
       if (sync_scalars(h)) return 1;
       out[0] = h->sc.keff;
+      return 0;
+   }
+   if (s == "angular-flux-min") {
+      double* d_min = nullptr;
+      SN_CUDA(h, cudaMalloc(&d_min, sizeof(double)));
+      cudaMemsetAsync(d_min, 0, sizeof(double), h->stream);
+      launch_min(h->d_psi, h->psi_count, d_min, h->stream);
+      cudaError_t e = cudaMemcpyAsync(out, d_min, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      cudaFree(d_min);
+      if (e != cudaSuccess) SN_FAIL(h, std::string("CUDA error in the angular-flux minimum: ") + cudaGetErrorString(e));
+      out[0] *= h->scale * h->psi_scale_factor;
       return 0;
    }
    if (s == "temperature" || s == "delayed-source") {
@@ -1178,17 +1241,14 @@ int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
    } else {   // angular-flux
       cudaMemsetAsync(d_out, 0, (size_t)count * sizeof(double), h->stream);
       double* d_min = nullptr;
-      cudaMalloc(&d_min, sizeof(double));
+      SN_CUDA(h, cudaMalloc(&d_min, sizeof(double)));
       cudaMemsetAsync(d_min, 0, sizeof(double), h->stream);
       for (int m = 0; m < h->M; m++) {
          const int c = h->dir_chunk[m];
          if (c < 0) continue;
          const Chunk& ch = pl.chunks[c];
          const ClassPlan& cp = pl.classes[ch.cls];
-         ChunkDev cd;
-         cudaMemcpyAsync(&cd, h->d_chunks + c, sizeof(ChunkDev), cudaMemcpyDeviceToHost, h->stream);
-         cudaStreamSynchronize(h->stream);
-         launch_export_psi(cd.psi, h->d_classes + ch.cls, h->d_pos_of[ch.cls], h->d_slot_of_xy, h->dir_d[m],
+         launch_export_psi(h->chunk_psi[c], h->d_classes + ch.cls, h->d_pos_of[ch.cls], h->d_slot_of_xy, h->dir_d[m],
                            ch.nd, m, h->d_gloc, h->scale * h->psi_scale_factor, h->G, h->M, pl.nz, pl.nxy, d_out, d_min,
                            h->stream);
       }
@@ -1231,9 +1291,9 @@ int pampa_sn_set(pampa_sn_handle* h, const char* name, const double* in) {
       cudaMemcpyAsync(d_in, in, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->stream);
       cudaMemsetAsync(h->d_phi, 0, (size_t)h->G * h->plan.nz * h->plan.Sb * sizeof(double), h->stream);
       launch_import_phi(h->d_phi_new, h->d_slot_of_xy, h->G, h->plan.nz, h->plan.nxy, h->plan.Sb, d_in, h->stream);
-      do_reduce(h, 0);
-      int rc = sync_scalars(h);
-      return rc ? 1 : check_async(h, "field import");
+      if (do_reduce(h, 0)) return 1;
+      if (sync_scalars(h)) return 1;
+      return check_async(h, "field import");
    }
    SN_FAIL(h, "unable to find field '" + s + "'");
 }

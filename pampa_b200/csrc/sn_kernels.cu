@@ -170,6 +170,10 @@ sn_sweep_kernel(const SweepGlobals gp, const Task* __restrict__ tasks) {
                for (int d = 0; d < DT; d++)
                   acc[d] += gp.ls_rhs[((int64_t)ch->m[d] * gp.G + g) * gp.nls + lsb];
             }
+            if (gp.corr_off != 0) {                     // delta < 1: lagged (T_delta - T_1) psi, same address as psi
+#pragma unroll
+               for (int d = 0; d < DT; d++) acc[d] += ldcg_f64(psi_w + gp.corr_off + d * PSX);
+            }
          }
 #pragma unroll
          for (int s = 0; s < FIN; s++) {
@@ -1107,13 +1111,14 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
 }
 
 template <int DT>
-static void launch_flow_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, bool extras, int* ticket,
+static int launch_flow_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, bool extras, int* ticket,
                            int* progress, const double* mw_host, int nch, cudaStream_t st) {
    const size_t smem = ((size_t)TILE_D * DT * PSXS + FLOW_DQ * PS + (FLOW_DQ * PS) / 2 + 4 * DT + gp.nz +
                         (size_t)gp.gm * gp.nmat + (gp.gm + 1) / 2) * sizeof(double);
    FlowDirs<DT> dirs;
    std::memset(&dirs, 0, sizeof(dirs));
-   for (int c = 0; c < nch && c < FlowDirs<DT>::MAXCH; c++)
+   if (nch > FlowDirs<DT>::MAXCH) return 1;   // checked at plan time too; never truncate the direction table silently
+   for (int c = 0; c < nch; c++)
       for (int d = 0; d < DT; d++) dirs.mw[c][d] = make_double2(mw_host[(c * DT_MAX + d) * 2], mw_host[(c * DT_MAX + d) * 2 + 1]);
    if (gp.uniform_dz) {
       if (extras) sn_sweep_flow_kernel<DT, true, true><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
@@ -1122,23 +1127,24 @@ static void launch_flow_dt(const SweepGlobals& gp, const Task* d_tasks, int ntas
       if (extras) sn_sweep_flow_kernel<DT, true, false><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
       else        sn_sweep_flow_kernel<DT, false, false><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
    }
+   return 0;
 }
 
 // mw_host: [nch][DT_MAX][2] = {|mu_z| (/dz when uniform), weight} of the launch's chunks, by ChunkDev::flow_slot
-void launch_sweep_flow(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras, int* ticket,
-                       int* progress, const double* mw_host, int nch, cudaStream_t st) {
-   if (ntasks <= 0) return;
+int launch_sweep_flow(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras, int* ticket,
+                      int* progress, const double* mw_host, int nch, cudaStream_t st) {
+   if (ntasks <= 0) return 0;
    switch (dt) {
-      case 1: launch_flow_dt<1>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
-      case 2: launch_flow_dt<2>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
-      case 3: launch_flow_dt<3>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
-      case 4: launch_flow_dt<4>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
-      case 5: launch_flow_dt<5>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
-      case 6: launch_flow_dt<6>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
-      case 7: launch_flow_dt<7>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
-      case 8: launch_flow_dt<8>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
-      case 9: launch_flow_dt<9>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
-      default: launch_flow_dt<10>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st); break;
+      case 1: return launch_flow_dt<1>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
+      case 2: return launch_flow_dt<2>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
+      case 3: return launch_flow_dt<3>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
+      case 4: return launch_flow_dt<4>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
+      case 5: return launch_flow_dt<5>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
+      case 6: return launch_flow_dt<6>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
+      case 7: return launch_flow_dt<7>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
+      case 8: return launch_flow_dt<8>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
+      case 9: return launch_flow_dt<9>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
+      default: return launch_flow_dt<10>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
    }
 }
 
@@ -1697,6 +1703,91 @@ void launch_ls_rhs(const SweepGlobals& gp, const int32_t* ls_ptr, const int32_t*
    sn_ls_rhs_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(
       gp, ls_ptr, ls_nbr_slot, ls_coef, nnz, dir_chunk, dir_d, class_pos_of,
       const_cast<double*>(gp.ls_rhs));
+}
+
+// ------------------------------------------------------------------------------------ delta < 1
+// Deferred correction of mixed-face-interpolation delta < 1 (reference src/SNSolver.cxx:193-198, :574-597): the
+// sweep inverts the upwind (delta = 1) operator T_1; the rest of the reference's operator,
+//    ((T_delta - T_1) psi)_i = sum over interior faces f of |Omega.n_f| A_f / V_i * kappa_f * (psi_nbr - psi_i),
+// kappa_f = (1-delta) r_if / r_ii2 (outgoing) or (1-delta) r_i2f / r_ii2 (incoming), is evaluated on the angular
+// flux of the previous sweep and subtracted from the source: corr = sum_f coef_f (psi_i - psi_nbr), stored in the
+// layout of the chunk's psi block so that the sweep reads it at the address it writes psi to.
+__global__ void __launch_bounds__(PS)
+sn_delta_corr_kernel(const SweepGlobals gp, int chunk, const int32_t* __restrict__ pos_of,
+                     const int32_t* __restrict__ fnb, const double* __restrict__ fvx, const double* __restrict__ fvy,
+                     const double* __restrict__ fkout, const double* __restrict__ fkin, int F, double omd,
+                     const double* __restrict__ dz, double* __restrict__ corr) {
+   const ChunkDev* __restrict__ ch = gp.chunks + chunk;
+   const ClassDev* __restrict__ cl = gp.classes + ch->cls;
+   const int t = threadIdx.x, patch = blockIdx.x, kp = blockIdx.y, gl = blockIdx.z;
+   const int64_t slot = (int64_t)patch * PS + t;
+   const int lv = cl->lvl[slot];
+   if (lv == LVL_EMPTY) return;
+   const int nz = gp.nz, nd = ch->nd, ps = cl->pstride;
+   const int cell = cl->tiles ? (int)slot : cl->cell_of[slot];
+   const int k = cl->zdir >= 0 ? kp : nz - 1 - kp;
+   const int64_t row = block_row0(gl, patch, cl->npatch, cl->nsm, cl->gm, nz) + kp + lv;
+   const double* __restrict__ psi = ch->psi;
+   const int64_t self = row * nd * ps + t;
+   double me[DT_MAX], acc[DT_MAX];
+   for (int d = 0; d < nd; d++) { me[d] = psi[self + (int64_t)d * ps]; acc[d] = 0.0; }
+   for (int f = 0; f < F; f++) {
+      const int nb = fnb[(int64_t)cell * F + f];
+      if (nb < 0) continue;
+      const int sl2 = pos_of[nb];
+      const int64_t row2 = block_row0(gl, sl2 >> 8, cl->npatch, cl->nsm, cl->gm, nz) + kp + cl->lvl[sl2];
+      const int64_t other = row2 * nd * ps + (sl2 & (PS - 1));
+      const double vx = fvx[(int64_t)cell * F + f], vy = fvy[(int64_t)cell * F + f];
+      const double ko = fkout[(int64_t)cell * F + f], ki = fkin[(int64_t)cell * F + f];
+      for (int d = 0; d < nd; d++) {
+         const double w = ch->mux[d] * vx + ch->muy[d] * vy;
+         const double coef = w > 0.0 ? w * ko : -w * ki;
+         acc[d] = fma(coef, me[d] - psi[other + (int64_t)d * ps], acc[d]);
+      }
+   }
+   if (gp.has_z) {
+      const int kdir = cl->zdir >= 0 ? 1 : -1;
+      if (kp + 1 < nz) {            // downstream layer: outgoing z face, kappa = (1-delta) dz_k / (dz_k + dz_k2)
+         const double c = omd / (dz[k] + dz[k + kdir]);
+         const int64_t other = self + (int64_t)nd * ps;
+         for (int d = 0; d < nd; d++) acc[d] = fma(c * ch->muz_abs[d], me[d] - psi[other + (int64_t)d * ps], acc[d]);
+      }
+      if (kp > 0) {                 // upstream layer: incoming z face, kappa = (1-delta) dz_k2 / (dz_k + dz_k2)
+         const double c = omd * dz[k - kdir] / (dz[k] * (dz[k] + dz[k - kdir]));
+         const int64_t other = self - (int64_t)nd * ps;
+         for (int d = 0; d < nd; d++) acc[d] = fma(c * ch->muz_abs[d], me[d] - psi[other + (int64_t)d * ps], acc[d]);
+      }
+   }
+   for (int d = 0; d < nd; d++) corr[self + (int64_t)d * ps] = acc[d];
+}
+
+void launch_delta_corr(const SweepGlobals& gp, int chunk, int npatch, const int32_t* pos_of, const int32_t* fnb,
+                       const double* fvx, const double* fvy, const double* fkout, const double* fkin, int F,
+                       double one_minus_delta, const double* dz, double* corr, cudaStream_t st) {
+   dim3 grid(npatch, gp.nz, gp.Gown);
+   sn_delta_corr_kernel<<<grid, PS, 0, st>>>(gp, chunk, pos_of, fnb, fvx, fvy, fkout, fkin, F, one_minus_delta, dz, corr);
+}
+
+// smallest value of a buffer (negative angular fluxes fail the solve, reference src/SNSolver.cxx:329)
+__global__ void sn_min_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ out) {
+   double mn = 0.0;
+   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      mn = fmin(mn, p[i]);
+   for (int off = 16; off > 0; off >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+   if ((threadIdx.x & 31) == 0 && mn < 0.0) {
+      // atomic min of a negative double through its ordered integer image
+      unsigned long long* a = reinterpret_cast<unsigned long long*>(out);
+      unsigned long long old = *a, assumed;
+      do {
+         assumed = old;
+         if (__longlong_as_double((long long)assumed) <= mn) break;
+         old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(mn));
+      } while (old != assumed);
+   }
+}
+void launch_min(const double* p, int64_t n, double* out, cudaStream_t st) {
+   if (n <= 0) return;
+   sn_min_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(p, n, out);
 }
 
 // ------------------------------------------------------------------------------------ fields

@@ -98,6 +98,7 @@ struct SweepGlobals {
    int32_t store_psi;
    int32_t nmat;
    int32_t uniform_dz;        // 1: every layer has the same thickness (or the mesh has no z faces)
+   int64_t corr_off;          // delta < 1: offset (doubles) from a psi entry to its deferred-correction entry (0: none)
    int32_t dbg;               // PAMPA_SN_DBG: (dbg >> 4) & 0xff = rows between two publishes of a dataflow task's
                               // progress counter (0: default 16; the stress test uses 1); no other bits are read
 };
@@ -123,8 +124,8 @@ void launch_sweep_tile(const SweepGlobals& gp, const Task* d_tasks, int ntasks, 
                        cudaStream_t st);
 // dataflow version of the tile kernel: one launch, tasks taken by ticket in topological order,
 // patch-to-patch dependencies through progress counters (see sn_kernels.cu)
-void launch_sweep_flow(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras, int* ticket,
-                       int* progress, const double* mw_host, int nch, cudaStream_t st);
+int launch_sweep_flow(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras, int* ticket,
+                      int* progress, const double* mw_host, int nch, cudaStream_t st);   // 1: direction table overflow
 int flow_max_chunks(int dt);
 cudaError_t configure_flow_kernels();
 // base [g][k][slot] <-> step-major [g][patch][step][lane] transforms for the tile kernel
@@ -157,6 +158,12 @@ void launch_update_k(const double* sums, ReduceScalars* sc, int update_k, cudaSt
 void launch_ls_rhs(const SweepGlobals& gp, const int32_t* ls_ptr, const int32_t* ls_nbr_slot,
                    const double* ls_coef, int64_t nnz, const int32_t* dir_chunk,
                    const int32_t* dir_d, const int32_t* const* class_pos_of, cudaStream_t st);
+
+// delta < 1: deferred correction (T_delta - T_1) psi of one chunk into `corr` (layout of the chunk's psi block)
+void launch_delta_corr(const SweepGlobals& gp, int chunk, int npatch, const int32_t* pos_of, const int32_t* fnb,
+                       const double* fvx, const double* fvy, const double* fkout, const double* fkin, int F,
+                       double one_minus_delta, const double* dz, double* corr, cudaStream_t st);
+void launch_min(const double* p, int64_t n, double* out, cudaStream_t st);   // *out = min(*out, min p), *out <= 0
 
 // field export (reference layouts)
 void launch_export_phi(const double* phi, const int32_t* slot_of_xy, double scale, int G, int nz,

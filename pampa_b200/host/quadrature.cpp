@@ -9,6 +9,11 @@ namespace pampa {
 namespace {
 struct Table { std::vector<double> mu; std::map<std::array<int, 3>, double> weight_of_class; bool renormalise; };
 
+// S2..S8: the 7-digit constants of src/AngularQuadratureSet.cxx:15-140.  S12 (the reference stops at S8,
+// :153; BASELINE config 5 asks for it): the standard LQ12 set, 7 digits like the others and used the same way
+// (no renormalisation).  The constants are pinned by their defining equations, not by memory: mu_i^2 =
+// mu_1^2 + (i-1) * 2 (1 - 3 mu_1^2) / (N-2) to 1e-7, and every even moment sum w mu^n = 1/(n+1), n = 2..12,
+// to 6e-8 (tests/test_oracle.py::test_quadrature_tables).
 // weight classes are keyed by the sorted triplet of direction-cosine indices (i <= j <= k,
 // i + j + k = N/2 - 1); the point order inside an octant follows the reference's tables
 const std::map<int, Table>& tables() {
@@ -20,7 +25,7 @@ const std::map<int, Table>& tables() {
            {{{0, 0, 3}, 0.1209877}, {{0, 1, 2}, 0.0907407}, {{1, 1, 1}, 0.0925926}}, false}},
       {12, {{0.1672126, 0.4595476, 0.6280191, 0.7600210, 0.8722706, 0.9716377},
             {{{0, 0, 5}, 0.0707626}, {{0, 1, 4}, 0.0558811}, {{0, 2, 3}, 0.0373377}, {{1, 1, 3}, 0.0502819},
-             {{1, 2, 2}, 0.0258513}}, true}},
+             {{1, 2, 2}, 0.0258513}}, false}},
    };
    return t;
 }

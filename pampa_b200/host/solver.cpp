@@ -228,9 +228,10 @@ int SNSolver::buildLSCorrection(std::vector<int>& cell, std::vector<int>& ptr, s
 
 int SNSolver::build() {
    PAMPA_CHECK(num_energy_groups < 1, "missing number of energy groups");
-   PAMPA_CHECK(face_interpolation_delta != 1.0,
-               "mixed-face-interpolation < 1 couples every face both ways and has no sweep ordering: only the pure "
-               "upwind scheme (mixed-face-interpolation 1.0) is supported by the sweep solver");
+   // mixed-face-interpolation < 1 (the reference's default is 0.1, src/SNSolver.hxx:16) couples every face both
+   // ways: the device layer sweeps the upwind part and treats the rest as a deferred correction (pampa_sn.h)
+   PAMPA_CHECK(face_interpolation_delta <= 0.0,
+               "mixed-face-interpolation 0 (pure linear interpolation) has no upwind part to sweep: use a value in (0, 1]");
    if (bcs.empty()) bcs = mesh->getBoundaryConditions();
    quadrature = AngularQuadratureSet(order);
    PAMPA_CHECK(quadrature.build(), "unable to build the angular quadrature set");
@@ -263,6 +264,7 @@ int SNSolver::build() {
    const double h0 = mesh->hasZFaces() ? mesh->getDz()[0] : 1.0;
    std::vector<int> nb((size_t)nxy * F, 0);
    std::vector<double> fx((size_t)nxy * F, 0.0), fy((size_t)nxy * F, 0.0), cf((size_t)nxy * F, 1.0);
+   std::vector<double> kout((size_t)nxy * F, 0.0), kin((size_t)nxy * F, 0.0);   // delta < 1 (src/SNSolver.cxx:193-198)
    std::vector<double> area(nxy), cx(nxy), cy(nxy);
    auto dist = [](const double* a, const double* b) {
       return std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
@@ -283,6 +285,8 @@ int SNSolver::build() {
             const double* xf = &faces.centroids[3 * gf];
             const double* c2 = &cells.centroids[3 * (size_t)i2];
             cf[s] = (dist(xf, ci) + dist(xf, c2)) / dist(ci, c2);
+            kout[s] = (1.0 - face_interpolation_delta) * dist(xf, ci) / dist(ci, c2);
+            kin[s] = (1.0 - face_interpolation_delta) * dist(xf, c2) / dist(ci, c2);
          }
       }
    }
@@ -306,6 +310,8 @@ int SNSolver::build() {
    ms.bc_minus_z = mesh->hasZFaces() ? mesh->findBoundary("-z") + 1 : 0;
    ms.bc_plus_z = mesh->hasZFaces() ? mesh->findBoundary("+z") + 1 : 0;
    ms.num_bcs = (int)bc_types.size() - 1; ms.bc_types = bc_types.data();
+   ms.face_interpolation_delta = face_interpolation_delta;
+   ms.xy_face_kout = kout.data(); ms.xy_face_kin = kin.data();
 
    pampa_sn_xs xs;
    xs.num_materials = (int)beta.size(); xs.num_groups = num_energy_groups;
@@ -366,6 +372,13 @@ int SNSolver::getSolution(int n) {
    PAMPA_CHECK(pampa_sn_get(device, "delayed-source", S.data()), pampa_sn_last_error(device));
    psi.clear();                                          // fetched on demand (cells x groups x directions)
    for (double x : phi) PAMPA_CHECK(x < 0.0, "negative values in the scalar-flux solution");
+   if (face_interpolation_delta < 1.0 || boundary_interpolation_ls) {
+      // SNSolver::normalizeAngularFlux fails the solve on a negative angular flux (src/SNSolver.cxx:329); only the
+      // non-monotone terms (linear face interpolation, LS boundary gradient) can produce one
+      double psi_min = 0.0;
+      PAMPA_CHECK(pampa_sn_get(device, "angular-flux-min", &psi_min), pampa_sn_last_error(device));
+      PAMPA_CHECK(psi_min < 0.0, "negative values in the angular-flux solution");
+   }
    power = 0.0;
    for (double x : q) power += x;
    return 0;

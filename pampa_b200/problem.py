@@ -42,6 +42,10 @@ class ExtrudedMesh:
     bc_minus_z: int = 0
     bc_plus_z: int = 0
     xy_ij: np.ndarray | None = None  # [nxy,2]
+    # mixed-face-interpolation delta < 1: deferred-correction weights of the lateral faces (include/pampa_sn.h)
+    delta: float = 1.0
+    xy_face_kout: np.ndarray | None = None   # [nxy,F]
+    xy_face_kin: np.ndarray | None = None
 
     @property
     def num_xy_cells(self):
@@ -127,6 +131,9 @@ def pack_mesh(m: ExtrudedMesh, pk: _Packed) -> _lib.Mesh:
     cm.bc_minus_z, cm.bc_plus_z = int(m.bc_minus_z), int(m.bc_plus_z)
     cm.num_bcs = len(m.bc_types) - 1
     cm.bc_types = pk.i32(m.bc_types)
+    cm.face_interpolation_delta = float(m.delta)
+    cm.xy_face_kout = pk.f64(m.xy_face_kout) if m.xy_face_kout is not None else None
+    cm.xy_face_kin = pk.f64(m.xy_face_kin) if m.xy_face_kin is not None else None
     return cm
 
 

@@ -15,8 +15,10 @@ from .problem import BC_REFLECTIVE, BC_VACUUM, CrossSections, ExtrudedMesh, Quad
 
 # ------------------------------------------------------------------------------ quadrature
 # first-octant level-symmetric tables: (mu values, index triplets, point weights summing to 1).
-# S2..S8 carry the 7-digit constants of src/AngularQuadratureSet.cxx:15-140; S12 and S16 are the
-# standard LQn tables (the reference stops at S8, src/AngularQuadratureSet.cxx:153).
+# S2..S8 carry the 7-digit constants of src/AngularQuadratureSet.cxx:15-140; S12 is the standard LQ12
+# table (the reference stops at S8, src/AngularQuadratureSet.cxx:153), 7 digits and used as they are,
+# like the others; its constants are pinned by the level-symmetric defining equations (even moments
+# 2..12 exact to 6e-8, tests/test_oracle.py::test_quadrature_tables).
 _LQ = {
     2: ([1.0 / math.sqrt(3.0)], [(0, 0, 0)], [1.0]),
     4: ([0.3500212, 0.8688903], [(0, 0, 1), (0, 1, 0), (1, 0, 0)], [1.0 / 3.0] * 3),
@@ -55,20 +57,16 @@ def level_symmetric(order: int) -> Quadrature:
         raise ValueError("SN order not implemented")
     mu, idx, w = _LQ[order]
     per = len(idx)
-    wsum = float(sum(w))
     M = 8 * per
     d = np.zeros((M, 3)); wt = np.zeros(M)
     for o in range(8):
         for m in range(per):
             v = [mu[idx[m][0]], mu[idx[m][1]], mu[idx[m][2]]]
-            if order > 8:                      # added tables: renormalise to unit vectors exactly
-                nrm = math.sqrt(v[0] ** 2 + v[1] ** 2 + v[2] ** 2)
-                v = [c / nrm for c in v]
             if o & 1: v[0] = -v[0]
             if o & 2: v[1] = -v[1]
             if o & 4: v[2] = -v[2]
             d[o * per + m] = v
-            wt[o * per + m] = (w[m] / wsum if order > 8 else w[m]) / 8.0
+            wt[o * per + m] = w[m] / 8.0
     refl = np.zeros((M, 3), dtype=np.int32)
     for o in range(8):
         for m in range(per):
@@ -81,9 +79,10 @@ def level_symmetric(order: int) -> Quadrature:
 CART_BOUNDARIES = ["-x", "+x", "-y", "+y", "-z", "+z"]
 
 
-def cartesian_mesh(dx, dy=None, dz=None, materials=None, bcs=None) -> ExtrudedMesh:
+def cartesian_mesh(dx, dy=None, dz=None, materials=None, bcs=None, delta=1.0) -> ExtrudedMesh:
     """Rectilinear mesh; `materials` is [nz,ny,nx] 0-based with -1 = void (the same xy pattern
-    in every layer); `bcs` maps "-x".."+z" to BC_VACUUM / BC_REFLECTIVE (default vacuum)."""
+    in every layer); `bcs` maps "-x".."+z" to BC_VACUUM / BC_REFLECTIVE (default vacuum); `delta` < 1:
+    mixed-face-interpolation weights (src/SNSolver.cxx:193-198) for the deferred correction."""
     dx = np.asarray(dx, dtype=float)
     nx = len(dx)
     ny = 0 if dy is None else len(dy)
@@ -128,18 +127,30 @@ def cartesian_mesh(dx, dy=None, dz=None, materials=None, bcs=None) -> ExtrudedMe
     y0 = np.concatenate([[0.0], np.cumsum(dyv)]) if ny else np.zeros(2)
     cx = x0[ii] + 0.5 * dx[ii]
     cy = (y0[jj] + 0.5 * dyv[jj]) if ny else np.zeros(nxy)
+    kout = kin = None
+    if delta < 1.0:
+        # r_if = half the cell width across the face, r_i2f = half the neighbour's, r_ii2 = their sum
+        hx, hy = dx[ii], dyv[jj]
+        mine = np.stack([hy, hx, hy, hx], axis=1) if ny else np.stack([hx, hx], axis=1)
+        theirs = np.zeros_like(mine)
+        ok = nb >= 0
+        nbc = np.where(ok, nb, 0)
+        theirs = np.stack([hy[nbc[:, 0]], hx[nbc[:, 1]], hy[nbc[:, 2]], hx[nbc[:, 3]]], axis=1) if ny \
+            else np.stack([hx[nbc[:, 0]], hx[nbc[:, 1]]], axis=1)
+        kout = np.where(ok, (1.0 - delta) * mine / (mine + theirs), 0.0)
+        kin = np.where(ok, (1.0 - delta) * theirs / (mine + theirs), 0.0)
     return ExtrudedMesh(
         xy_num_faces=np.full(nxy, F, dtype=np.int32), xy_neighbor=nb.astype(np.int32),
         xy_face_fx=fx, xy_face_fy=fy, xy_face_cf=np.ones((nxy, F)), xy_area=area, xy_cx=cx, xy_cy=cy,
         materials=mats[:, phys].reshape(-1).astype(np.int32), bc_types=bc_types,
         dz=np.asarray(dz, dtype=float) if nz else None,
         bc_minus_z=bidx.get("-z", 0), bc_plus_z=bidx.get("+z", 0),
-        xy_ij=np.stack([ii, jj], axis=1).astype(np.int32))
+        xy_ij=np.stack([ii, jj], axis=1).astype(np.int32), delta=delta, xy_face_kout=kout, xy_face_kin=kin)
 
 
 # ------------------------------------------------------------------------------ polygons
 def polygon_mesh(points, cells, dz=None, materials=None, boundary_points=None, bc_of_boundary=None,
-                 bc_z=(BC_VACUUM, BC_VACUUM)) -> ExtrudedMesh:
+                 bc_z=(BC_VACUUM, BC_VACUUM), delta=1.0) -> ExtrudedMesh:
     """Extruded 2-D polygon mesh (CCW point lists).  `boundary_points` maps a boundary name to
     the set of points on it; an edge whose two points lie on a boundary gets that boundary,
     other unmatched edges get the default boundary ("exterior", listed first)."""
@@ -163,6 +174,7 @@ def polygon_mesh(points, cells, dz=None, materials=None, boundary_points=None, b
     default_b = next((n for n, p in (boundary_points or {"exterior": None}).items() if p is None), None)
     nb = np.full((nxy, F), 0, dtype=np.int32)
     fx = np.zeros((nxy, F)); fy = np.zeros((nxy, F)); cf = np.ones((nxy, F))
+    kout = np.zeros((nxy, F)); kin = np.zeros((nxy, F))
     fcx = np.zeros((nxy, F)); fcy = np.zeros((nxy, F))
     area = np.zeros(nxy); cx = np.zeros(nxy); cy = np.zeros(nxy)
     nf = np.zeros(nxy, dtype=np.int32)
@@ -194,13 +206,17 @@ def polygon_mesh(points, cells, dz=None, materials=None, boundary_points=None, b
             if j >= 0:
                 r1 = math.hypot(fcx[i, f] - cx[i], fcy[i, f] - cy[i])
                 r2 = math.hypot(fcx[i, f] - cx[j], fcy[i, f] - cy[j])
-                cf[i, f] = (r1 + r2) / math.hypot(cx[i] - cx[j], cy[i] - cy[j])
+                r12 = math.hypot(cx[i] - cx[j], cy[i] - cy[j])
+                cf[i, f] = (r1 + r2) / r12
+                kout[i, f] = (1.0 - delta) * r1 / r12
+                kin[i, f] = (1.0 - delta) * r2 / r12
     mats = np.zeros(nxy * max(nz, 1), dtype=np.int32) if materials is None else np.asarray(materials, dtype=np.int32)
     return ExtrudedMesh(xy_num_faces=nf, xy_neighbor=nb, xy_face_fx=fx, xy_face_fy=fy, xy_face_cf=cf,
                         xy_area=area, xy_cx=cx, xy_cy=cy, materials=mats, bc_types=bc_types,
                         dz=np.asarray(dz, dtype=float) if nz else None,
                         bc_minus_z=names.index("-z") + 1 if nz else 0,
-                        bc_plus_z=names.index("+z") + 1 if nz else 0)
+                        bc_plus_z=names.index("+z") + 1 if nz else 0, delta=delta,
+                        xy_face_kout=kout if delta < 1.0 else None, xy_face_kin=kin if delta < 1.0 else None)
 
 
 def hex_lattice(nrings: int, pitch: float = 1.0):
@@ -261,12 +277,12 @@ def checkerboard_core(nx, ny, nz, h=1.0, assembly=8, num_groups=8, seed=12345, b
     return mesh, synthetic_xs(num_groups, seed)
 
 
-def hex_core(nrings, nz, pitch=1.0, dz=1.0, num_groups=16, seed=54321):
+def hex_core(nrings, nz, pitch=1.0, dz=1.0, num_groups=16, seed=54321, delta=1.0):
     """Synthetic hexagonal-prism core: fuel / moderator alternating by ring and axial block."""
     points, cells, ring = hex_lattice(nrings, pitch)
     nxy = len(cells)
     mats = np.zeros((nz, nxy), dtype=np.int32)
     for kk in range(nz):
         mats[kk] = (ring // 4 + kk // 8) % 2
-    mesh = polygon_mesh(points, cells, np.full(nz, dz), mats.reshape(-1))
+    mesh = polygon_mesh(points, cells, np.full(nz, dz), mats.reshape(-1), delta=delta)
     return mesh, synthetic_xs(num_groups, seed), (points, cells)

@@ -30,6 +30,8 @@ CASES = {
     # same decks, variants without a reference-run golden (oracle is the sole authority)
     "pwr_cartesian_s2_lsoff": ("pwr-iaea-benchmark/cartesian-sn/input.pmp", None, None, "off", None),
     "pwr_cartesian_s8_lsoff": ("pwr-iaea-benchmark/cartesian-sn/input.pmp", None, None, "off", 8),
+    # BASELINE config 2 as named: the shipped deck (LS boundary interpolation on) at S8
+    "pwr_cartesian_s8": ("pwr-iaea-benchmark/cartesian-sn/input.pmp", None, None, "reference_effective", 8),
 }
 
 
@@ -50,11 +52,14 @@ def hex_core_deck(groups):
 def main(only=None):
     ref_lines = open(os.path.join(REF, "check_ref.txt")).read().split("\n")
     cases = dict(CASES)
-    cases["hex_core_s8_2g"] = ("hex-core", None, None, "off", None)
+    cases["hex_core_s8_2g"] = ("hex-core:2", None, None, "off", None)
+    # BASELINE config 3 with the reference's own 11-group graphite-moderated data (upscatter, c ~ 0.95)
+    cases["hex_core_s8_11g"] = ("hex-core:11", None, None, "off", None)
     for name, (deck_path, line, gold, ls_mode, order) in cases.items():
         if only and name not in only:
             continue
-        deck = hex_core_deck(2) if deck_path == "hex-core" else orc.read_deck(os.path.join(REF, deck_path))
+        deck = (hex_core_deck(int(deck_path.split(":")[1])) if deck_path.startswith("hex-core")
+                else orc.read_deck(os.path.join(REF, deck_path)))
         if order is not None:
             deck.order = order
         op = orc.build_operator(deck.mesh, deck.xs, deck.G, deck.order, deck.delta, ls_mode, deck.bcs)

@@ -74,17 +74,12 @@ def test_plan_rejects_bad_input():
 
 
 def test_level_symmetric_matches_oracle_tables():
-    for order in (2, 4, 6, 8):
+    for order in (2, 4, 6, 8, 12):                    # S12: added table, pinned in test_oracle.py
         q = syn.level_symmetric(order)
         d, w, r = orc.quadrature(order)
         assert np.array_equal(q.directions, d) and np.array_equal(q.weights, w)
         assert np.array_equal(q.reflected, r)
-    q12 = syn.level_symmetric(12)                     # added table: check the LQn moment conditions
-    assert len(q12.weights) == 168
-    assert abs(q12.weights.sum() - 1.0) < 1e-12
-    for ax in range(3):
-        assert abs((q12.weights * q12.directions[:, ax] ** 2).sum() - 1.0 / 3.0) < 1e-6
-        assert abs((q12.weights * q12.directions[:, ax] ** 4).sum() - 1.0 / 5.0) < 1e-6
+    assert len(syn.level_symmetric(12).weights) == 168
 
 
 def test_builders_agree_with_oracle_geometry():

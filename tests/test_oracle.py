@@ -57,7 +57,7 @@ def test_oracle_on_reference_decks(case, gold):
 
 
 def test_quadrature_tables():
-    for order in (2, 4, 6, 8):
+    for order in (2, 4, 6, 8, 12):
         d, w, refl = orc.quadrature(order)
         assert len(w) == order * (order + 2)
         assert abs(w.sum() - 1.0) < 1e-6
@@ -67,7 +67,22 @@ def test_quadrature_tables():
                 r = d[m].copy(); r[ax] = -r[ax]
                 assert np.allclose(d[refl[m, ax]], r)
     with pytest.raises(ValueError):
-        orc.quadrature(12)
+        orc.quadrature(16)
+    # S12 is not in the reference (it stops at S8): its constants are pinned by the equations that define a
+    # level-symmetric set.  (1) mu_i^2 is an arithmetic progression fixed by mu_1; (2) the quadrature integrates
+    # every even moment through order 12 (7-digit constants: 6e-8), and not order 14 -- a wrong digit in any
+    # of the five weights would show at the 1e-6 level.
+    d, w, _ = orc.quadrature(12)
+    mu = np.unique(np.round(np.abs(d[:, 0]), 7))
+    assert len(mu) == 6
+    step = 2.0 * (1.0 - 3.0 * mu[0] ** 2) / 10.0
+    assert np.allclose(mu ** 2, mu[0] ** 2 + step * np.arange(6), atol=2e-7)
+    for n in range(2, 13, 2):
+        for ax in range(3):
+            assert abs(np.sum(w * d[:, ax] ** n) - 1.0 / (n + 1)) < 1e-7, (n, ax)
+    assert abs(np.sum(w * d[:, 0] ** 14) - 1.0 / 15) > 1e-6
+    assert abs(np.sum(w * d[:, 0] ** 2 * d[:, 1] ** 2) - 1.0 / 15) < 1e-7
+    assert abs(np.sum(w * d[:, 0] ** 2 * d[:, 1] ** 2 * d[:, 2] ** 2) - 1.0 / 105) < 1e-7
 
 
 def test_c_port_matches_oracle():

@@ -15,8 +15,9 @@ from pampa_b200 import problem as pb
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def extruded_from_oracle(mesh: orc.Mesh) -> pb.ExtrudedMesh:
-    """Oracle generic face tables -> extruded SoA (lateral faces of layer 0 + dz)."""
+def extruded_from_oracle(mesh: orc.Mesh, delta: float = 1.0) -> pb.ExtrudedMesh:
+    """Oracle generic face tables -> extruded SoA (lateral faces of layer 0 + dz); delta < 1 adds the
+    deferred-correction face weights of include/pampa_sn.h."""
     dz = mesh.ext.get("dz")
     nz = 1 if dz is None else len(dz)
     nxy = mesh.num_cells // nz
@@ -29,6 +30,7 @@ def extruded_from_oracle(mesh: orc.Mesh) -> pb.ExtrudedMesh:
     F = int(nf.max())
     nb = np.zeros((nxy, F), dtype=np.int32)
     fx = np.zeros((nxy, F)); fy = np.zeros((nxy, F)); cf = np.ones((nxy, F))
+    kout = np.zeros((nxy, F)); kin = np.zeros((nxy, F))
     h0 = 1.0 if dz is None else dz[0]
     for i, lat in enumerate(rows):
         for a, f in enumerate(lat):
@@ -39,7 +41,10 @@ def extruded_from_oracle(mesh: orc.Mesh) -> pb.ExtrudedMesh:
             if i2 >= 0:
                 r1 = np.linalg.norm(mesh.face_centroid[f] - mesh.centroids[i])
                 r2 = np.linalg.norm(mesh.face_centroid[f] - mesh.centroids[i2])
-                cf[i, a] = (r1 + r2) / np.linalg.norm(mesh.centroids[i] - mesh.centroids[i2])
+                r12 = np.linalg.norm(mesh.centroids[i] - mesh.centroids[i2])
+                cf[i, a] = (r1 + r2) / r12
+                kout[i, a] = (1.0 - delta) * r1 / r12
+                kin[i, a] = (1.0 - delta) * r2 / r12
     bz = (mesh.boundaries.index("-z") + 1, mesh.boundaries.index("+z") + 1) if dz is not None else (0, 0)
     ij = None
     if mesh.ext.get("kind") == "cartesian":
@@ -49,7 +54,8 @@ def extruded_from_oracle(mesh: orc.Mesh) -> pb.ExtrudedMesh:
                            xy_area=mesh.volumes[:nxy] / h0, xy_cx=mesh.centroids[:nxy, 0].copy(),
                            xy_cy=mesh.centroids[:nxy, 1].copy(), materials=mesh.materials.astype(np.int32),
                            bc_types=[0], dz=None if dz is None else np.asarray(dz, dtype=float),
-                           bc_minus_z=bz[0], bc_plus_z=bz[1], xy_ij=ij)
+                           bc_minus_z=bz[0], bc_plus_z=bz[1], xy_ij=ij, delta=delta,
+                           xy_face_kout=kout if delta < 1.0 else None, xy_face_kin=kin if delta < 1.0 else None)
 
 
 def with_bcs(em: pb.ExtrudedMesh, mesh: orc.Mesh, bcs) -> pb.ExtrudedMesh:
@@ -117,7 +123,7 @@ def quad_to_oracle(q: pb.Quadrature):
 
 def deck_problem(deck: orc.Deck, ls_mode: str):
     """(ExtrudedMesh, CrossSections, Quadrature, LSCorrection) of a parsed reference deck."""
-    em = with_bcs(extruded_from_oracle(deck.mesh), deck.mesh, deck.bcs)
+    em = with_bcs(extruded_from_oracle(deck.mesh, deck.delta), deck.mesh, deck.bcs)
     return em, xs_from_oracle(deck.xs), quad_from_oracle(deck.order), ls_from_oracle(deck.mesh, ls_mode, deck.bcs)
 
 
