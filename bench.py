@@ -324,7 +324,7 @@ def run_b200(a, rank, world, local_rank):
             traffic_src = "ncu capture %s (dram__bytes_read.sum + dram__bytes_write.sum per launch)" % tj.get("source", "profiles/")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "sn_sweep_flow_kernel" if info0["tile_classes"] > 0 else "sn_sweep_kernel (generic)",
+                "kernel": "sn_sweep_flow_kernel" if info0["flow_classes"] > 0 else "sn_sweep_kernel (generic)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_update": b_alg, "launches_per_step": info0["sweep_launches"],
                 "algorithmic_bytes_per_launch": b_alg * U_own / max(1, info0["sweep_launches"]),

@@ -194,6 +194,10 @@ typedef struct {
    int64_t kernel_launches;          /* total launches issued by this handle */
    double  timed_kernel_ms;          /* last pampa_sn_iterate_timed: device time of the sweep-kernel launches
                                         alone (between the shear and un-shear passes), summed over iterations */
+   int64_t num_tilings;              /* shared patch partitions (1: structured tiles / k-d leaves; a lattice of
+                                        congruent cells has one per pair of lattice directions) */
+   int64_t flow_classes;             /* ordering classes the one-launch dataflow kernel can sweep */
+   int64_t lattice;                  /* 1: unstructured mesh recognised as a lattice of congruent cells */
 } pampa_sn_info;
 int pampa_sn_get_info(pampa_sn_handle* h, pampa_sn_info* info);
 

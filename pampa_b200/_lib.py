@@ -51,7 +51,8 @@ class Info(C.Structure):
     _fields_ = [("num_cells", i64), ("num_groups", i64), ("num_directions", i64), ("updates_per_sweep", i64),
                 ("sweep_launches", i64), ("sweep_tasks", i64), ("num_classes", i64), ("num_chunks", i64),
                 ("tile_classes", i64), ("device_bytes", i64), ("last_sweep_ms", f64), ("last_source_ms", f64),
-                ("last_reduce_ms", f64), ("kernel_launches", i64), ("timed_kernel_ms", f64)]
+                ("last_reduce_ms", f64), ("kernel_launches", i64), ("timed_kernel_ms", f64), ("num_tilings", i64),
+                ("flow_classes", i64), ("lattice", i64)]
 
 
 # every symbol include/pampa_sn.h declares: name -> (restype, argtypes)

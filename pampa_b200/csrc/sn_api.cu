@@ -1,6 +1,7 @@
 // sn_api.cu -- the C ABI declared in include/pampa_sn.h: handle, device memory, iteration.
 #include <dlfcn.h>
 
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -45,7 +46,9 @@ constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MIN = 3;
 
 struct LaunchGroup { int wave, cls, kind, dt, fin, ring; bool extras; int64_t offset; int count; };
 // one dataflow launch: every tile-class task of one chunk size, in ticket (topological) order
-struct FlowLaunch { int dt; int64_t offset; int count; std::vector<double> mw; int nch; };
+struct FlowLaunch { int dt, fin; int64_t offset; int count; std::vector<double> mw; int nch; };
+// fast classes / chunks of one shared tiling (the shear passes run once per tiling)
+struct TilingDev { int npatch = 0; int32_t* d_cell_of = nullptr; int32_t *d_classes = nullptr, *d_chunks = nullptr; int nclasses = 0, nchunks = 0; };
 
 }  // namespace
 
@@ -117,7 +120,7 @@ struct pampa_sn_handle {
    bool multi_stream = false;
    // staged tile kernel
    std::vector<char> class_fast;
-   int32_t *d_fast_classes = nullptr, *d_fast_chunks = nullptr;
+   std::vector<TilingDev> tilings;       // shear / un-shear work lists per shared tiling
    int nfast_classes = 0, nfast_chunks = 0;
    bool use_graph = false, graph_failed = false;
    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // one per parity of the alternating boundary buffers
@@ -257,10 +260,11 @@ int sweep_launches(pampa_sn_handle* h) {
          h->launches++;
       }
    }
-   if (h->nfast_classes > 0) {
-      launch_shear_q(gp, h->d_classes, h->d_fast_classes, h->nfast_classes, h->plan.npatch_b, h->stream);
-      h->launches++;
-   }
+   for (const TilingDev& tg : h->tilings)
+      if (tg.nclasses > 0) {
+         launch_shear_q(gp, h->d_classes, tg.d_classes, tg.nclasses, tg.npatch, tg.d_cell_of, h->stream);
+         h->launches++;
+      }
    const int ns = h->multi_stream ? pampa_sn_handle::NSTREAMS : 0;
    if (!h->flows.empty()) {
       // tickets and progress counters of the dataflow launches start from zero every sweep
@@ -276,7 +280,7 @@ int sweep_launches(pampa_sn_handle* h) {
    for (size_t f = 0; f < h->flows.size(); f++) {
       const FlowLaunch& fl = h->flows[f];
       cudaStream_t st = ns ? h->cls_stream[f % ns] : h->stream;
-      if (launch_sweep_flow(gp, h->d_tasks + fl.offset, fl.count, fl.dt, h->extras, h->d_flow_ctl + f, h->d_flow_ctl + 16,
+      if (launch_sweep_flow(gp, h->d_tasks + fl.offset, fl.count, fl.dt, fl.fin, h->extras, h->d_flow_ctl + f, h->d_flow_ctl + 16,
                             fl.mw.data(), fl.nch, st))
          SN_FAIL(h, "internal: more chunks in a dataflow launch than its direction table holds");
       h->launches++;
@@ -294,12 +298,15 @@ int sweep_launches(pampa_sn_handle* h) {
    if (h->kernel_events) {
       cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); h->kernel_events->push_back(e);
    }
-   if (h->nfast_chunks > 0) {
-      // every owned chunk on the tile kernels: nothing else adds to phi_new, the first pass may overwrite it
-      launch_unshear_phi(gp, h->d_chunks, h->d_classes, h->d_fast_chunks, h->nfast_chunks, h->plan.npatch_b,
-                         h->groups_generic == 0 ? 1 : 0, h->stream);
-      h->launches++;
-   }
+   // every owned chunk on the tile kernels: nothing else adds to phi_new, the first pass may overwrite it
+   bool overwrite = h->groups_generic == 0;
+   for (const TilingDev& tg : h->tilings)
+      if (tg.nchunks > 0) {
+         launch_unshear_phi(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.npatch, overwrite ? 1 : 0,
+                            tg.d_cell_of, h->stream);
+         overwrite = false;
+         h->launches++;
+      }
    return 0;
 }
 
@@ -466,10 +473,15 @@ int pampa_sn_plan_check(const pampa_sn_mesh* mesh, const pampa_sn_quadrature* qu
                   int64_t u = p * pl.P + pay;
                   int diff = (int)cp.lvl[s] - (int)cp.lvl[u];
                   if (cp.lvl[u] == LVL_EMPTY || diff < 1 || diff >= cp.ring) throw std::runtime_error("local source level");
+                  // the dataflow kernel reads an in-patch source `diff` pipeline steps back (1 or 2)
+                  if (cp.in_hidx[(size_t)f * cp.S + s] != diff) throw std::runtime_error("local source delay");
+                  if (cp.fast_flow && diff > 2) throw std::runtime_error("dataflow class with a source more than two steps back");
                } else if (kind == SRC_GLOBAL) {
                   int64_t up = pay / pl.P;
                   if (cp.lvl[pay] == LVL_EMPTY) throw std::runtime_error("global source hole");
                   if (up != p && cp.patch_level[up] >= cp.patch_level[p]) throw std::runtime_error("patch order");
+                  if (cp.fast_flow && (cp.in_hidx[(size_t)f * cp.S + s] >= FLOW_HALO || cp.eidx[pay] >= FLOW_EXPORT || f >= FLOW_FIN))
+                     throw std::runtime_error("dataflow class outside the kernel's halo / export / face limits");
                }
             }
       }
@@ -481,6 +493,8 @@ int pampa_sn_plan_check(const pampa_sn_mesh* mesh, const pampa_sn_quadrature* qu
          for (auto& w : pl.waves) info->sweep_tasks += (int64_t)w.size();
          info->num_classes = (int64_t)pl.classes.size(); info->num_chunks = (int64_t)pl.chunks.size();
          info->tile_classes = pl.tile_classes;
+         info->num_tilings = (int64_t)pl.tilings.size(); info->lattice = pl.lattice;
+         for (auto& cp : pl.classes) info->flow_classes += cp.fast_flow ? 1 : 0;
       }
    } catch (const std::exception& e) {
       g_create_error = e.what();
@@ -667,17 +681,51 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          h->extras = true;
       }
 
-      // classes
+      // Which kernel sweeps a class.  The dataflow kernel (one launch per sweep) takes the classes the plan marked
+      // fast_flow; with wave_launch = 1 or z chunks the wavefront-launched tile kernel takes the narrower set
+      // `fast`; everything else goes to the generic kernel.  The lagged LS / delta terms live on the generic path.
+      const bool base_ok = h->nls == 0 && h->delta == 1.0 && h->nmat <= 4096 && !h->opts.generic_only;
+      bool want_flow = !h->opts.wave_launch && pl.nzc == 1;
+      auto needs_fin3 = [&](const ClassPlan& cp) { return cp.fin > 2 || cp.ring > 2 || cp.max_halo > 32; };
+      if (want_flow) {   // every chunk of a flow launch needs a slot in its kernel-parameter direction table
+         int per[DT_MAX + 1][2] = {};
+         for (size_t c = 0; c < pl.chunks.size(); c++) {
+            const ClassPlan& cp = pl.classes[pl.chunks[c].cls];
+            if (chunk_owned[c] && base_ok && cp.fast_flow) per[pl.chunks[c].nd][needs_fin3(cp) ? 1 : 0]++;
+         }
+         for (int dt = 1; dt <= DT_MAX; dt++)
+            for (int f3 = 0; f3 < 2; f3++)
+               if (per[dt][f3] > flow_max_chunks(dt) || (f3 && per[dt][f3] > 0 && dt > flow3_max_dt())) want_flow = false;
+      }
+      const bool use_flow = want_flow;
       std::vector<ClassDev> cdev(pl.classes.size());
       h->class_fast.assign(pl.classes.size(), 0);
-      int fast_chunk_count[2] = {0, 0}, fast_class_count[2] = {0, 0};
+      // the streaming shear kernels take a bounded number of classes / chunks per tiling and z direction
+      std::vector<std::array<int, 2>> fast_chunk_count(pl.tilings.size(), std::array<int, 2>{0, 0});
+      std::vector<std::array<int, 2>> fast_class_count(pl.tilings.size(), std::array<int, 2>{0, 0});
       h->d_pos_of.assign(pl.classes.size(), nullptr);
       for (size_t ci = 0; ci < pl.classes.size(); ci++) {
          const ClassPlan& cp = pl.classes[ci];
          ClassDev& cd = cdev[ci];
          cd.S = cp.S; cd.zdir = cp.zdir; cd.ring = cp.ring; cd.tiles = cp.tiles ? 1 : 0; cd.npatch = cp.npatch;
          cd.nsteps = cp.nsteps; cd.gm = gm; cd.nsm = nsm_of(cp); cd.mat_bytes = 4; cd.mats_c = nullptr;
-         {  // material map in the class's (patch, pipeline step, lane) order
+         h->class_fast[ci] = base_ok && (use_flow ? cp.fast_flow : cp.fast);
+         if (h->class_fast[ci]) {
+            bool any_owned = false;
+            for (size_t c = 0; c < pl.chunks.size(); c++) any_owned |= (pl.chunks[c].cls == (int)ci && chunk_owned[c]);
+            if (!any_owned) h->class_fast[ci] = 0;
+         }
+         if (h->class_fast[ci]) {
+            int& cnt = fast_chunk_count[cp.tiling][cp.zdir >= 0 ? 0 : 1];
+            int mine = 0;
+            for (size_t c = 0; c < pl.chunks.size(); c++) mine += (pl.chunks[c].cls == (int)ci && chunk_owned[c]);
+            int& ccnt = fast_class_count[cp.tiling][cp.zdir >= 0 ? 0 : 1];
+            if (cnt + mine > SHEAR_MAX_PER_PASS || ccnt + 1 > shear_max_classes()) h->class_fast[ci] = 0;
+            else { cnt += mine; ccnt++; }
+         }
+         cd.mats_s = nullptr;
+         if (!(use_flow && h->class_fast[ci])) {
+            // material map in the class's (patch, pipeline step, lane) order (generic and tile kernels)
             std::vector<int32_t> ms((size_t)cp.npatch * cp.nsteps * PS, -1);
             for (int64_t sl = 0; sl < cp.S; sl++) {
                if (cp.cell_of[sl] < 0) continue;
@@ -705,20 +753,6 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          if (dev_upload(h, &d_eidx, cp.eidx)) return 1;
          cd.eidx = d_eidx;
          cd.q_sheared = nullptr;
-         h->class_fast[ci] = cp.fast && h->nls == 0 && h->delta == 1.0 && h->nmat <= 4096 && !h->opts.generic_only;
-         if (h->class_fast[ci]) {
-            bool any_owned = false;
-            for (size_t c = 0; c < pl.chunks.size(); c++) any_owned |= (pl.chunks[c].cls == (int)ci && chunk_owned[c]);
-            if (!any_owned) h->class_fast[ci] = 0;
-         }
-         if (h->class_fast[ci]) {   // the streaming shear kernels take a bounded number per z direction
-            int& cnt = fast_chunk_count[cp.zdir >= 0 ? 0 : 1];
-            int mine = 0;
-            for (size_t c = 0; c < pl.chunks.size(); c++) mine += (pl.chunks[c].cls == (int)ci && chunk_owned[c]);
-            int& ccnt = fast_class_count[cp.zdir >= 0 ? 0 : 1];
-            if (cnt + mine > SHEAR_MAX_PER_PASS || ccnt + 1 > shear_max_classes()) h->class_fast[ci] = 0;
-            else { cnt += mine; ccnt++; }
-         }
          if (h->class_fast[ci]) {
             double* d_qs;
             const int64_t nq = (int64_t)nblk * cp.npatch * nsm_of(cp) * PS;
@@ -778,14 +812,24 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
             fast_chunks.push_back((int32_t)c);
          }
       }
-      {
-         std::vector<int32_t> fast_classes;
-         for (size_t ci = 0; ci < pl.classes.size(); ci++) if (h->class_fast[ci]) fast_classes.push_back((int32_t)ci);
+      h->tilings.assign(pl.tilings.size(), TilingDev{});
+      h->nfast_classes = 0; h->nfast_chunks = (int)fast_chunks.size();
+      for (size_t tg = 0; tg < pl.tilings.size(); tg++) {
+         TilingDev& td = h->tilings[tg];
+         td.npatch = pl.tilings[tg].npatch;
+         std::vector<int32_t> cls_list, chunk_list;
+         for (size_t ci = 0; ci < pl.classes.size(); ci++)
+            if (h->class_fast[ci] && pl.classes[ci].tiling == (int)tg) cls_list.push_back((int32_t)ci);
+         for (int32_t c : fast_chunks) if (pl.classes[pl.chunks[c].cls].tiling == (int)tg) chunk_list.push_back(c);
          // +z chunks first: the un-shear kernel processes one z direction per pass, 8 chunks at a time
-         std::stable_sort(fast_chunks.begin(), fast_chunks.end(), [&](int32_t a, int32_t b) {
+         std::stable_sort(chunk_list.begin(), chunk_list.end(), [&](int32_t a, int32_t b) {
             return (pl.classes[pl.chunks[a].cls].zdir < 0) < (pl.classes[pl.chunks[b].cls].zdir < 0); });
-         h->nfast_classes = (int)fast_classes.size(); h->nfast_chunks = (int)fast_chunks.size();
-         if (dev_upload(h, &h->d_fast_classes, fast_classes) || dev_upload(h, &h->d_fast_chunks, fast_chunks)) return 1;
+         td.nclasses = (int)cls_list.size(); td.nchunks = (int)chunk_list.size();
+         h->nfast_classes += td.nclasses;
+         if (dev_upload(h, &td.d_classes, cls_list) || dev_upload(h, &td.d_chunks, chunk_list)) return 1;
+         if (tg > 0 && td.nclasses > 0) {     // slot of this tiling -> base slot (the classes on it share the map)
+            if (dev_upload(h, &td.d_cell_of, pl.classes[cls_list[0]].cell_of)) return 1;
+         }
       }
       {
          std::vector<int32_t> a(h->dir_chunk.begin(), h->dir_chunk.end()), b(h->dir_d.begin(), h->dir_d.end());
@@ -798,25 +842,23 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       // by kernel variant, one launch each.
       std::vector<Task> all;
       h->groups.clear(); h->flows.clear();
-      bool use_flow = !h->opts.wave_launch && pl.nzc == 1;
-      {  // every chunk of a flow launch needs a slot in the kernel-parameter direction table
-         int per_dt[DT_MAX + 1] = {};
-         for (size_t c = 0; c < pl.chunks.size(); c++)
-            if (chunk_owned[c] && h->class_fast[pl.chunks[c].cls]) per_dt[pl.chunks[c].nd]++;
-         for (int dt = 1; dt <= DT_MAX; dt++) if (per_dt[dt] > flow_max_chunks(dt)) use_flow = false;
-      }
       if (use_flow) {
-         for (int dt = 1; dt <= DT_MAX; dt++) {
+         for (int dtf = 2; dtf <= 2 * DT_MAX + 1; dtf++) {
+            const int dt = dtf / 2, fin = (dtf & 1) ? 3 : 2;
+            auto in_launch = [&](int chunk) {
+               const ClassPlan& cpc = pl.classes[pl.chunks[chunk].cls];
+               return h->class_fast[pl.chunks[chunk].cls] && pl.chunks[chunk].nd == dt && (needs_fin3(cpc) ? 3 : 2) == fin;
+            };
             const size_t first = all.size();
             for (size_t w = 0; w < pl.waves.size(); w++)
                for (const Task& t : pl.waves[w])
-                  if (h->class_fast[pl.chunks[t.chunk].cls] && pl.chunks[t.chunk].nd == dt && h->gloc[t.group] % gm == 0)
+                  if (in_launch(t.chunk) && h->gloc[t.group] % gm == 0)
                      all.push_back(Task{t.chunk, h->gloc[t.group] / gm, t.patch, 0});   // group field = block
             if (all.size() > first) {
                if (h->flows.size() >= 16) SN_FAIL(h, "internal: too many dataflow launches");
-               FlowLaunch fl{dt, (int64_t)first, (int)(all.size() - first), {}, 0};
+               FlowLaunch fl{dt, fin, (int64_t)first, (int)(all.size() - first), {}, 0};
                for (size_t c = 0; c < pl.chunks.size(); c++) {
-                  if (!(chunk_owned[c] && h->class_fast[pl.chunks[c].cls] && pl.chunks[c].nd == dt)) continue;
+                  if (!(chunk_owned[c] && in_launch((int)c))) continue;
                   chdev[c].flow_slot = fl.nch++;
                   for (int d = 0; d < DT_MAX; d++) {
                      fl.mw.push_back(pl.has_z ? chdev[c].muz_abs[d] * (h->uniform_dz ? 1.0 / mesh->dz[0] : 1.0) : 0.0);
@@ -827,7 +869,9 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
             }
          }
          if (!h->flows.empty()) {
-            h->flow_ctl_count = 16 + (int64_t)pl.chunks.size() * nblk * pl.npatch_b;
+            int np_max = pl.npatch_b;
+            for (const Tiling& tg : pl.tilings) np_max = std::max(np_max, tg.npatch);
+            h->flow_ctl_count = 16 + (int64_t)pl.chunks.size() * nblk * np_max;
             if (dev_alloc(h, &h->d_flow_ctl, h->flow_ctl_count)) return 1;
          }
       }
@@ -855,8 +899,8 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       for (const LaunchGroup& lg : h->groups) if (lg.kind != 1) h->groups_generic++;
       h->use_graph = h->groups.size() >= 32 && !h->opts.no_graph;
       if (!h->opts.store_psi && !h->groups.empty())
-         SN_FAIL(h, "store_psi = 0 needs every ordering class on the dataflow tile kernel (Cartesian mesh, no "
-                    "least-squares term, wave_launch = 0)");
+         SN_FAIL(h, "store_psi = 0 needs every ordering class on the dataflow tile kernel (Cartesian or lattice mesh, "
+                    "no least-squares / delta < 1 term, wave_launch = 0)");
       // dataflow classes on structured tiles: neighbouring patches read the perimeter lanes of the psi rows
       // themselves (no edge copies); the wavefront-launched kernels keep the copies
       for (size_t ci = 0; ci < pl.classes.size(); ci++) {
@@ -1336,6 +1380,8 @@ int pampa_sn_get_info(pampa_sn_handle* h, pampa_sn_info* info) {
    for (auto& f : h->flows) info->sweep_tasks += f.count;
    info->num_classes = (int64_t)pl.classes.size(); info->num_chunks = (int64_t)pl.chunks.size();
    info->tile_classes = pl.tile_classes;
+   info->num_tilings = (int64_t)pl.tilings.size(); info->lattice = pl.lattice;
+   for (size_t ci = 0; ci < pl.classes.size(); ci++) info->flow_classes += (!h->flows.empty() && h->class_fast[ci]) ? 1 : 0;
    info->device_bytes = h->device_bytes;
    info->timed_kernel_ms = h->timed_kernel_ms;
    info->last_sweep_ms = h->last_sweep_ms; info->last_source_ms = h->last_source_ms;

@@ -684,7 +684,9 @@ cudaError_t configure_tile_kernels() {
 // latency (they wait for the stores in flight) stays off the lanes' critical path.
 // The LSU pipe was the limiter of the per-lane version (81 % busy: 2 LDS + STS + STG per update, all
 // 64-bit); the row stores and halo loads are ~30 % of its wavefronts.
-constexpr int PSXS = PS + 2 * PEDGE;       // smem row: 256 ring lanes | 32 edge copies (out) | 32 halo (in)
+// smem row of one direction: 256 ring lanes | 32 edge copies (out) | halo (in): 32 staged sources on structured
+// tiles (FIN = 2), 64 on lattice tiles with three incoming faces (FIN = 3)
+template <int FIN> struct FlowShape { static constexpr int HALO = FIN > 2 ? FLOW_HALO : PEDGE; static constexpr int PSXS = PS + PEDGE + HALO; };
 constexpr int FLOW_THREADS = PS + 64;       // 8 lane warps + producer warp + store warp
 constexpr int FLOW_DQ = 8, FLOW_PFQ = 6;    // q / material row ring: depth and prefetch distance (steps)
 
@@ -748,17 +750,20 @@ __device__ __forceinline__ void pipe_barrier() { asm volatile("bar.sync 1, 288;"
 
 struct HaloEntry { int32_t code; int32_t lv; };      // upwind source code and level of the reading lane
 
-template <int DT, bool EXTRAS, bool UNIFORM_DZ>
+// FIN = 2: structured tiles (two incoming lateral faces, in-patch sources exactly one step back).  FIN = 3: a third
+// incoming face and in-patch sources one or two steps back (rhombic tiles of a hexagonal lattice, where the
+// neighbour across the tile diagonal is two levels upwind), 64 staged sources, two per producer lane.
+template <int DT, int FIN, bool EXTRAS, bool UNIFORM_DZ>
 __global__ void __launch_bounds__(FLOW_THREADS, (DT <= 8 ? 2 : 1))
 sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int* __restrict__ ticket,
                      int* __restrict__ progress, const __grid_constant__ FlowDirs<DT> dirs) {
    extern __shared__ __align__(128) double smem[];
-   constexpr int ROWG = DT * PSX;                     // global psi row of one pipeline step
-   constexpr int ROWS = DT * PSXS;                    // its shared-memory buffer (+ halo columns)
+   constexpr int PSXS = FlowShape<FIN>::PSXS, HALO = FlowShape<FIN>::HALO;
+   constexpr int ROWS = DT * PSXS;                    // shared-memory buffer of one pipeline step (+ halo columns)
    constexpr int D = TILE_D, PFD = TILE_PFD;
    constexpr int DQ = FLOW_DQ, PFQ = FLOW_PFQ;        // q / material rows: deeper ring (they come from DRAM)
    __shared__ int s_task;
-   __shared__ HaloEntry s_halo[PEDGE];
+   __shared__ HaloEntry s_halo[HALO];
    __shared__ __align__(8) uint64_t s_bar[FLOW_DQ];   // q / material rows of a step have landed
    __shared__ int s_rows_done, s_rows_read;           // rows complete in smem / rows the copy engine has read
    const int t = threadIdx.x;
@@ -768,8 +773,8 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       for (int b = 0; b < FLOW_DQ; b++) mbar_init(&s_bar[b], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
-   if (t < PEDGE) s_halo[t] = HaloEntry{-1, 0};
-   if (t == PEDGE) { s_rows_done = 0; s_rows_read = 0; }
+   if (t < HALO) s_halo[t] = HaloEntry{-1, 0};
+   if (t == HALO) { s_rows_done = 0; s_rows_read = 0; }
    __syncthreads();
    const Task tk = tasks[s_task];
    const ChunkDev* __restrict__ ch = gp.chunks + tk.chunk;
@@ -839,8 +844,9 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       const int lv = cl->lvl[slot];
       const bool valid = (lv != LVL_EMPTY);
       const int lv0 = valid ? lv : (1 << 20);         // holes are never active
-      double a0[DT], a1[DT], so[DT];
-      int off0 = t, off1 = t;                         // default: own ring entry with a zero coefficient
+      double a0[DT], a1[DT], a2[FIN > 2 ? DT : 1], so[DT];
+      int off0 = t, off1 = t, off2 = t;               // default: own ring entry with a zero coefficient
+      int two = 0;                                    // FIN = 3: bit s set = in-patch source s is two steps back
       if (valid) {
          const double2 ov = cl->out_vec[slot];
          const double2 v0 = cl->in_vec[slot];
@@ -851,27 +857,29 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
             a0[d] = -(s_mux[d] * v0.x + s_muy[d] * v0.y);
             a1[d] = -(s_mux[d] * v1.x + s_muy[d] * v1.y);
          }
-         const int c0 = cl->in_src[slot];
-         const int c1 = cl->in_src[S + slot];
-         if (c0 >= 0) {
-            if ((c0 >> SRC_KIND_SHIFT) == SRC_LOCAL) off0 = c0 & SRC_PAYLOAD;
-            else {
-               const int hx = cl->in_hidx[slot];
-               off0 = PS + PEDGE + hx;
-               s_halo[hx] = HaloEntry{c0, lv};
-            }
+         if (FIN > 2) {
+            const double2 v2 = cl->in_vec[2 * S + slot];
+#pragma unroll
+            for (int d = 0; d < DT; d++) a2[FIN > 2 ? d : 0] = -(s_mux[d] * v2.x + s_muy[d] * v2.y);
          }
-         if (c1 >= 0) {
-            if ((c1 >> SRC_KIND_SHIFT) == SRC_LOCAL) off1 = c1 & SRC_PAYLOAD;
-            else {
-               const int hx = cl->in_hidx[S + slot];
-               off1 = PS + PEDGE + hx;
-               s_halo[hx] = HaloEntry{c1, lv};
-            }
-         }
+         // source s: an in-patch lane (ring column; in_hidx = steps back) or a staged halo entry (in_hidx = entry)
+         auto wire = [&](int sidx, int& off) {
+            const int c = cl->in_src[(int64_t)sidx * S + slot];
+            if (c < 0) return;
+            const int hx = cl->in_hidx[(int64_t)sidx * S + slot];
+            if ((c >> SRC_KIND_SHIFT) == SRC_LOCAL) { off = c & SRC_PAYLOAD; if (hx == 2) two |= 1 << sidx; }
+            else { off = PS + PEDGE + hx; s_halo[hx] = HaloEntry{c, lv}; }
+         };
+         wire(0, off0);
+         wire(1, off1);
+         if (FIN > 2) wire(2, off2);
       } else {
 #pragma unroll
          for (int d = 0; d < DT; d++) { so[d] = 0.0; a0[d] = 0.0; a1[d] = 0.0; }
+         if (FIN > 2) {
+#pragma unroll
+            for (int d = 0; d < DT; d++) a2[FIN > 2 ? d : 0] = 0.0;
+         }
       }
       const int ex = (valid && !inl) ? (int)cl->eidx[slot] : 255;   // my compact edge index, if another patch reads me
       int rout[ROUT_MAX];
@@ -880,7 +888,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
          for (int r = 0; r < ROUT_MAX; r++) rout[r] = valid ? cl->rout[(size_t)r * S + slot] : -1;
       }
       double* ph_row = ch->phi_part + prow * PS + t;
-      const int cell = (int)slot;                      // tile classes: class slot == base slot
+      const int cell = (cl->tiles || !valid) ? (int)slot : cl->cell_of[slot];   // base slot (boundary buffers)
 
       // z-upwind start values of a column: zero (vacuum) or the mirrored direction of the last sweep
       double psiz[DT];
@@ -919,6 +927,13 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
             double* wbuf = bufs + (step & (D - 1)) * ROWS + t;
             const double* r0 = rbuf + off0;
             const double* r1 = rbuf + off1;
+            const double* r2 = rbuf + off2;
+            if (FIN > 2) {                             // sources two levels upwind: the buffer of step - 2
+               const double* rbuf2 = bufs + ((step - 2) & (D - 1)) * ROWS;
+               if (two & 1) r0 = rbuf2 + off0;
+               if (two & 2) r1 = rbuf2 + off1;
+               if (two & 4) r2 = rbuf2 + off2;
+            }
             double ph = 0.0;
             if (UNIFORM_DZ) {
                if (mat != tagA && mat != tagB) {        // miss: rare once both materials of a column are seen
@@ -941,6 +956,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
                   double acc = fma(mw.x, psiz[d], qv);
                   acc = fma(a0[d], r0[d * PSXS], acc);
                   acc = fma(a1[d], r1[d * PSXS], acc);
+                  if (FIN > 2) acc = fma(a2[FIN > 2 ? d : 0], r2[d * PSXS], acc);
                   const double v = acc * (useA ? invA[d] : invB[d]);
                   psiz[d] = v;
                   wbuf[d * PSXS] = v;
@@ -956,6 +972,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
                   double acc = fma(az, psiz[d], qv);
                   acc = fma(a0[d], r0[d * PSXS], acc);
                   acc = fma(a1[d], r1[d * PSXS], acc);
+                  if (FIN > 2) acc = fma(a2[FIN > 2 ? d : 0], r2[d * PSXS], acc);
                   const double v = acc * fast_rcp(st + so[d] + az);
                   psiz[d] = v;
                   wbuf[d * PSXS] = v;
@@ -997,43 +1014,52 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       }
    } else if (t < PS + 32) {
       // ---------------------------------------------------------------- producer warp
-      const int hl = t - PS;                           // halo entry of this lane
+      const int hl = t - PS;                           // this lane stages halo entries hl (and hl + 32 when FIN = 3)
       pipe_barrier();                                  // (A) halo table written by the lanes
-      const HaloEntry he = s_halo[hl];
-      const int kind = he.code >= 0 ? (he.code >> SRC_KIND_SHIFT) : -1;
-      const int pay = he.code & SRC_PAYLOAD;
-      const int rlv = he.lv;
-      const double* gsrc = nullptr;                    // upwind row of staging step 0, direction 0
-      const int* flag = nullptr;
-      int need0 = 0;                                   // rows the upwind task must have completed for step 0
-      int rf = 0, ax = 0;
-      if (kind == SRC_GLOBAL) {
-         const int up = pay >> 8;
-         const int dlv = (int)cl->lvl[pay] - rlv;
-         gsrc = psi_gl + ((int64_t)up * NS + dlv) * rowg + (inl ? (pay & (PS - 1)) : goff + (int)cl->eidx[pay]);
-         flag = progress + ((int64_t)tk.chunk * nblk + gb) * npatch + up;
-         need0 = dlv + 1;
-      } else if (kind == SRC_REFL) {
-         ax = pay >> SRC_AXIS_SHIFT; rf = pay & ((1 << SRC_AXIS_SHIFT) - 1);
+      constexpr int NH = HALO / 32;
+      int kind[NH], rlv[NH], need0[NH], rf[NH], ax[NH];
+      const double* gsrc[NH];                          // upwind row of staging step 0, direction 0
+      const int* flag[NH];
+#pragma unroll
+      for (int e = 0; e < NH; e++) {
+         const HaloEntry he = s_halo[hl + 32 * e];
+         kind[e] = he.code >= 0 ? (he.code >> SRC_KIND_SHIFT) : -1;
+         const int pay = he.code & SRC_PAYLOAD;
+         rlv[e] = he.lv;
+         gsrc[e] = nullptr; flag[e] = nullptr; need0[e] = 0; rf[e] = 0; ax[e] = 0;
+         if (kind[e] == SRC_GLOBAL) {
+            const int up = pay >> 8;
+            const int dlv = (int)cl->lvl[pay] - rlv[e];
+            gsrc[e] = psi_gl + ((int64_t)up * NS + dlv) * rowg + (inl ? (pay & (PS - 1)) : goff + (int)cl->eidx[pay]);
+            flag[e] = progress + ((int64_t)tk.chunk * nblk + gb) * npatch + up;
+            need0[e] = dlv + 1;                        // rows the upwind task must have completed for step 0
+         } else if (kind[e] == SRC_REFL) {
+            ax[e] = pay >> SRC_AXIS_SHIFT; rf[e] = pay & ((1 << SRC_AXIS_SHIFT) - 1);
+         }
       }
-      int seen = 0;
+      int seen[NH];
+#pragma unroll
+      for (int e = 0; e < NH; e++) seen[e] = 0;
       auto stage_halo = [&](int st) {
-         const int klt = st - rlv;
-         if (kind < 0 || klt < 0 || klt >= kcnt) return;
-         double* dst = bufs + ((st - 1) & (D - 1)) * ROWS + PS + PEDGE + hl;
-         if (kind == SRC_GLOBAL) {
-            const int need = st + need0;
-            while (seen < need) seen = ld_acquire_gpu(flag);
 #pragma unroll
-            for (int d = 0; d < DT; d++) cp_async8(dst + d * PSXS, gsrc + (int64_t)st * rowg + d * gstr);
-         } else if (EXTRAS) {
-            const int gi = klt / nz;
-            const int kk = kstart + (klt - gi * nz) * kdir;
-            const int g = s_g[gi];
+         for (int e = 0; e < NH; e++) {
+            const int klt = st - rlv[e];
+            if (kind[e] < 0 || klt < 0 || klt >= kcnt) continue;
+            double* dst = bufs + ((st - 1) & (D - 1)) * ROWS + PS + PEDGE + hl + 32 * e;
+            if (kind[e] == SRC_GLOBAL) {
+               const int need = st + need0[e];
+               while (seen[e] < need) seen[e] = ld_acquire_gpu(flag[e]);
 #pragma unroll
-            for (int d = 0; d < DT; d++)
-               cp_async8(dst + d * PSXS,
-                         gp.bnd_old + (((int64_t)ch->mrefl[d][ax] * gp.G + g) * nz + kk) * gp.nrf + rf);
+               for (int d = 0; d < DT; d++) cp_async8(dst + d * PSXS, gsrc[e] + (int64_t)st * rowg + d * gstr);
+            } else if (EXTRAS) {
+               const int gi = klt / nz;
+               const int kk = kstart + (klt - gi * nz) * kdir;
+               const int g = s_g[gi];
+#pragma unroll
+               for (int d = 0; d < DT; d++)
+                  cp_async8(dst + d * PSXS,
+                            gp.bnd_old + (((int64_t)ch->mrefl[d][ax[e]] * gp.G + g) * nz + kk) * gp.nrf + rf[e]);
+            }
          }
       };
       // q and material rows of a step: two bulk copies (2 KB + 1 KB) counted on the step's mbarrier
@@ -1110,10 +1136,12 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
    }
 }
 
-template <int DT>
-static int launch_flow_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, bool extras, int* ticket,
+constexpr int FLOW3_DT_MAX = FLOW3_DT_CAP;  // chunk sizes the FIN = 3 variant is instantiated for (sn_plan.hpp)
+
+template <int DT, int FIN>
+static int launch_flow_fin(const SweepGlobals& gp, const Task* d_tasks, int ntasks, bool extras, int* ticket,
                            int* progress, const double* mw_host, int nch, cudaStream_t st) {
-   const size_t smem = ((size_t)TILE_D * DT * PSXS + FLOW_DQ * PS + (FLOW_DQ * PS) / 2 + 4 * DT + gp.nz +
+   const size_t smem = ((size_t)TILE_D * DT * FlowShape<FIN>::PSXS + FLOW_DQ * PS + (FLOW_DQ * PS) / 2 + 4 * DT + gp.nz +
                         (size_t)gp.gm * gp.nmat + (gp.gm + 1) / 2) * sizeof(double);
    FlowDirs<DT> dirs;
    std::memset(&dirs, 0, sizeof(dirs));
@@ -1121,41 +1149,59 @@ static int launch_flow_dt(const SweepGlobals& gp, const Task* d_tasks, int ntask
    for (int c = 0; c < nch; c++)
       for (int d = 0; d < DT; d++) dirs.mw[c][d] = make_double2(mw_host[(c * DT_MAX + d) * 2], mw_host[(c * DT_MAX + d) * 2 + 1]);
    if (gp.uniform_dz) {
-      if (extras) sn_sweep_flow_kernel<DT, true, true><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
-      else        sn_sweep_flow_kernel<DT, false, true><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
+      if (extras) sn_sweep_flow_kernel<DT, FIN, true, true><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
+      else        sn_sweep_flow_kernel<DT, FIN, false, true><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
    } else {
-      if (extras) sn_sweep_flow_kernel<DT, true, false><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
-      else        sn_sweep_flow_kernel<DT, false, false><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
+      if (extras) sn_sweep_flow_kernel<DT, FIN, true, false><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
+      else        sn_sweep_flow_kernel<DT, FIN, false, false><<<ntasks, FLOW_THREADS, smem, st>>>(gp, d_tasks, ticket, progress, dirs);
    }
    return 0;
 }
 
-// mw_host: [nch][DT_MAX][2] = {|mu_z| (/dz when uniform), weight} of the launch's chunks, by ChunkDev::flow_slot
-int launch_sweep_flow(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras, int* ticket,
+template <int DT>
+static int launch_flow_dt(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int fin, bool extras, int* ticket,
+                          int* progress, const double* mw_host, int nch, cudaStream_t st) {
+   if (fin <= 2) return launch_flow_fin<DT, 2>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
+   if constexpr (DT <= FLOW3_DT_MAX)
+      return launch_flow_fin<DT, 3>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
+   return 2;                                  // chunk too wide for the three-face variant (plan caps it)
+}
+
+// mw_host: [nch][DT_MAX][2] = {|mu_z| (/dz when uniform), weight} of the launch's chunks, by ChunkDev::flow_slot;
+// fin: 2 = structured tiles, 3 = three incoming faces / in-patch sources two steps back (FlowShape)
+int launch_sweep_flow(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, int fin, bool extras, int* ticket,
                       int* progress, const double* mw_host, int nch, cudaStream_t st) {
    if (ntasks <= 0) return 0;
    switch (dt) {
-      case 1: return launch_flow_dt<1>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
-      case 2: return launch_flow_dt<2>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
-      case 3: return launch_flow_dt<3>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
-      case 4: return launch_flow_dt<4>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
-      case 5: return launch_flow_dt<5>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
-      case 6: return launch_flow_dt<6>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
-      case 7: return launch_flow_dt<7>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
-      case 8: return launch_flow_dt<8>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
-      case 9: return launch_flow_dt<9>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
-      default: return launch_flow_dt<10>(gp, d_tasks, ntasks, extras, ticket, progress, mw_host, nch, st);
+      case 1: return launch_flow_dt<1>(gp, d_tasks, ntasks, fin, extras, ticket, progress, mw_host, nch, st);
+      case 2: return launch_flow_dt<2>(gp, d_tasks, ntasks, fin, extras, ticket, progress, mw_host, nch, st);
+      case 3: return launch_flow_dt<3>(gp, d_tasks, ntasks, fin, extras, ticket, progress, mw_host, nch, st);
+      case 4: return launch_flow_dt<4>(gp, d_tasks, ntasks, fin, extras, ticket, progress, mw_host, nch, st);
+      case 5: return launch_flow_dt<5>(gp, d_tasks, ntasks, fin, extras, ticket, progress, mw_host, nch, st);
+      case 6: return launch_flow_dt<6>(gp, d_tasks, ntasks, fin, extras, ticket, progress, mw_host, nch, st);
+      case 7: return launch_flow_dt<7>(gp, d_tasks, ntasks, fin, extras, ticket, progress, mw_host, nch, st);
+      case 8: return launch_flow_dt<8>(gp, d_tasks, ntasks, fin, extras, ticket, progress, mw_host, nch, st);
+      case 9: return launch_flow_dt<9>(gp, d_tasks, ntasks, fin, extras, ticket, progress, mw_host, nch, st);
+      default: return launch_flow_dt<10>(gp, d_tasks, ntasks, fin, extras, ticket, progress, mw_host, nch, st);
    }
 }
+int flow3_max_dt() { return FLOW3_DT_MAX; }
 
-template <int DT>
-static cudaError_t cfg_flow() {
+template <int DT, int FIN>
+static cudaError_t cfg_flow_fin() {
    cudaError_t e;
    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-   if ((e = cudaFuncSetAttribute(sn_sweep_flow_kernel<DT, false, false>, attr, 200 * 1024)) != cudaSuccess) return e;
-   if ((e = cudaFuncSetAttribute(sn_sweep_flow_kernel<DT, true, false>, attr, 200 * 1024)) != cudaSuccess) return e;
-   if ((e = cudaFuncSetAttribute(sn_sweep_flow_kernel<DT, false, true>, attr, 200 * 1024)) != cudaSuccess) return e;
-   return cudaFuncSetAttribute(sn_sweep_flow_kernel<DT, true, true>, attr, 200 * 1024);
+   if ((e = cudaFuncSetAttribute(sn_sweep_flow_kernel<DT, FIN, false, false>, attr, 200 * 1024)) != cudaSuccess) return e;
+   if ((e = cudaFuncSetAttribute(sn_sweep_flow_kernel<DT, FIN, true, false>, attr, 200 * 1024)) != cudaSuccess) return e;
+   if ((e = cudaFuncSetAttribute(sn_sweep_flow_kernel<DT, FIN, false, true>, attr, 200 * 1024)) != cudaSuccess) return e;
+   return cudaFuncSetAttribute(sn_sweep_flow_kernel<DT, FIN, true, true>, attr, 200 * 1024);
+}
+template <int DT>
+static cudaError_t cfg_flow() {
+   cudaError_t e = cfg_flow_fin<DT, 2>();
+   if (e != cudaSuccess) return e;
+   if constexpr (DT <= FLOW3_DT_MAX) return cfg_flow_fin<DT, 3>();
+   return cudaSuccess;
 }
 
 cudaError_t configure_flow_kernels() {
@@ -1190,7 +1236,8 @@ int shear_max_classes() { return SHEAR_MAXC; }
 
 __global__ void __launch_bounds__(PS)
 sn_shear_q_kernel(const SweepGlobals gp, const ClassDev* __restrict__ classes,
-                  const int32_t* __restrict__ fast_classes, int nfast, int npatch_b) {
+                  const int32_t* __restrict__ fast_classes, int nfast, int npatch_b,
+                  const int32_t* __restrict__ cell_of) {
    extern __shared__ __align__(16) unsigned char shear_raw[];
    ShearSmem& sm = *reinterpret_cast<ShearSmem*>(shear_raw);
    const int t = threadIdx.x;
@@ -1198,6 +1245,8 @@ sn_shear_q_kernel(const SweepGlobals gp, const ClassDev* __restrict__ classes,
    const int g = (blockIdx.x / npatch_b) % gp.G;
    const int zpass = blockIdx.x / (npatch_b * gp.G);            // 0: ascending k, 1: descending k
    const int64_t slot = (int64_t)patch * PS + t;
+   // classes swept on another shared tiling than the base one: slot of that tiling -> base slot (-1 in holes)
+   const int64_t bslot = cell_of ? cell_of[slot] : slot;
    const int nz = gp.nz;
    if (gp.gloc[g] < 0) return;                                   // not swept by this rank
    if (t == 0) {
@@ -1225,19 +1274,20 @@ sn_shear_q_kernel(const SweepGlobals gp, const ClassDev* __restrict__ classes,
    if (nc == 0) return;
    // the column of this thread, in sweep order; the loads run SHEAR_U..2*SHEAR_U layers ahead of the
    // stores (a thread only ever touches its own ring column: no barriers in the loop)
-   const double* qg = gp.q + (int64_t)g * nz * gp.Sb + slot + (zpass == 0 ? 0 : (int64_t)(nz - 1) * gp.Sb);
+   const double* qg = gp.q + (int64_t)g * nz * gp.Sb + (bslot < 0 ? 0 : bslot) + (zpass == 0 ? 0 : (int64_t)(nz - 1) * gp.Sb);
    const int64_t kstr = zpass == 0 ? gp.Sb : -gp.Sb;
    const int nrow = nz + sm.maxlev - 1;
+   const int nzl = bslot < 0 ? 0 : nz;                  // holes load nothing
    double nxt[SHEAR_U];
 #pragma unroll
-   for (int u = 0; u < SHEAR_U; u++) nxt[u] = u < nz ? __ldcs(qg + (int64_t)u * kstr) : 0.0;
+   for (int u = 0; u < SHEAR_U; u++) nxt[u] = u < nzl ? __ldcs(qg + (int64_t)u * kstr) : 0.0;
    for (int s0 = 0; s0 < nrow; s0 += SHEAR_U) {
       double cur[SHEAR_U];
 #pragma unroll
       for (int u = 0; u < SHEAR_U; u++) {
          cur[u] = nxt[u];
          const int sn = s0 + SHEAR_U + u;
-         nxt[u] = sn < nz ? __ldcs(qg + (int64_t)sn * kstr) : 0.0;
+         nxt[u] = sn < nzl ? __ldcs(qg + (int64_t)sn * kstr) : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < SHEAR_U; u++) {
@@ -1253,10 +1303,10 @@ sn_shear_q_kernel(const SweepGlobals gp, const ClassDev* __restrict__ classes,
 }
 
 void launch_shear_q(const SweepGlobals& gp, const ClassDev* d_classes, const int32_t* d_fast_classes,
-                    int nfast, int npatch_b, cudaStream_t st) {
+                    int nfast, int npatch_b, const int32_t* cell_of, cudaStream_t st) {
    if (nfast <= 0) return;
    sn_shear_q_kernel<<<npatch_b * gp.G * 2, PS, sizeof(ShearSmem), st>>>(gp, d_classes, d_fast_classes, nfast,
-                                                                         npatch_b);
+                                                                         npatch_b, cell_of);
 }
 
 // phi_new[g][k][slot] += sum over the fast chunks of their step-major partial moments (streamed the
@@ -1268,7 +1318,7 @@ constexpr int UNSHEAR_NC = 8;
 __global__ void __launch_bounds__(PS)
 sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks,
                       const ClassDev* __restrict__ classes, const int32_t* __restrict__ fast_chunks,
-                      int nfast, int npatch_b, int overwrite_first) {
+                      int nfast, int npatch_b, int overwrite_first, const int32_t* __restrict__ cell_of) {
    extern __shared__ __align__(16) unsigned char shear_raw[];
    double (*ring)[PS] = reinterpret_cast<double (*)[PS]>(shear_raw);      // [SHEAR_RING][PS]
    bool overwrite = overwrite_first != 0;   // phi_new holds nothing yet: the first pass stores instead of adding
@@ -1278,8 +1328,10 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
    const int gl = gp.gloc[g];
    if (gl < 0) return;
    const int64_t slot = (int64_t)patch * PS + t;
+   const int64_t bslot = cell_of ? cell_of[slot] : slot;     // base slot of this lane (-1: hole of another tiling)
+   const bool live = bslot >= 0;
    const int nz = gp.nz;
-   double* pg = gp.phi_new + (int64_t)g * nz * gp.Sb + slot;
+   double* pg = gp.phi_new + (int64_t)g * nz * gp.Sb + (live ? bslot : 0);
    for (int zpass = 0; zpass < 2; zpass++) {
       for (int c0 = 0; c0 < nfast; c0 += UNSHEAR_NC) {
          // up to UNSHEAR_NC chunks of this z direction, starting the search at chunk c0
@@ -1319,7 +1371,7 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                const int ad = s + u - (maxlev - 1);
-               old[u] = (!overwrite && ad >= 0 && ad < nz) ? pg[(int64_t)(zpass == 0 ? ad : nz - 1 - ad) * gp.Sb] : 0.0;
+               old[u] = (!overwrite && live && ad >= 0 && ad < nz) ? pg[(int64_t)(zpass == 0 ? ad : nz - 1 - ad) * gp.Sb] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 2; u++) {
@@ -1331,7 +1383,7 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
                const int ad = s + u - (maxlev - 1);      // complete for every chunk and lane
                if (ad >= 0 && ad < nz) {
                   const int k = zpass == 0 ? ad : nz - 1 - ad;
-                  pg[(int64_t)k * gp.Sb] = old[u] + ring[ad & (SHEAR_RING - 1)][t];
+                  if (live) pg[(int64_t)k * gp.Sb] = old[u] + ring[ad & (SHEAR_RING - 1)][t];
                   ring[ad & (SHEAR_RING - 1)][t] = 0.0;
                }
             }
@@ -1342,10 +1394,11 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
 }
 
 void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
-                        const int32_t* d_fast_chunks, int nfast, int npatch_b, int overwrite_first, cudaStream_t st) {
+                        const int32_t* d_fast_chunks, int nfast, int npatch_b, int overwrite_first,
+                        const int32_t* cell_of, cudaStream_t st) {
    if (nfast <= 0) return;
    sn_unshear_phi_kernel<<<npatch_b * gp.G, PS, SHEAR_RING * PS * sizeof(double), st>>>(
-      gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first);
+      gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, cell_of);
 }
 
 cudaError_t configure_shear_kernels() {

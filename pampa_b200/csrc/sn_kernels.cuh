@@ -124,15 +124,18 @@ void launch_sweep_tile(const SweepGlobals& gp, const Task* d_tasks, int ntasks, 
                        cudaStream_t st);
 // dataflow version of the tile kernel: one launch, tasks taken by ticket in topological order,
 // patch-to-patch dependencies through progress counters (see sn_kernels.cu)
-int launch_sweep_flow(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, bool extras, int* ticket,
+int launch_sweep_flow(const SweepGlobals& gp, const Task* d_tasks, int ntasks, int dt, int fin, bool extras, int* ticket,
                       int* progress, const double* mw_host, int nch, cudaStream_t st);   // 1: direction table overflow
+int flow3_max_dt();           // widest chunk of the three-incoming-face variant
 int flow_max_chunks(int dt);
 cudaError_t configure_flow_kernels();
 // base [g][k][slot] <-> step-major [g][patch][step][lane] transforms for the tile kernel
+// (per shared tiling: npatch and cell_of are the tiling's; cell_of = nullptr for the base tiling)
 void launch_shear_q(const SweepGlobals& gp, const ClassDev* d_classes, const int32_t* d_fast_classes,
-                    int nfast, int npatch_b, cudaStream_t st);
+                    int nfast, int npatch, const int32_t* cell_of, cudaStream_t st);
 void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
-                        const int32_t* d_fast_chunks, int nfast, int npatch_b, int overwrite_first, cudaStream_t st);
+                        const int32_t* d_fast_chunks, int nfast, int npatch, int overwrite_first,
+                        const int32_t* cell_of, cudaStream_t st);
 
 void launch_source(const double* phi, double* q, const int32_t* mats, const double* sig_s,
                    const double* chi, const double* nusf, const ReduceScalars* sc, const int32_t* gloc,

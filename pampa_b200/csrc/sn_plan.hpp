@@ -37,6 +37,11 @@ constexpr int ROUT_MAX = 2;        // outgoing reflective lateral faces per cell
 constexpr int DT_MAX = 10;         // directions per sweep chunk (register-resident chains)
 constexpr int DT_DEFAULT = 5;      // measured best on B200 (registers -> 2 CTAs/SM without spills)
 constexpr int RING_MAX = 4;        // smem ring depth for in-patch upwind values
+constexpr int FLOW_FIN = 3;        // incoming lateral faces the dataflow kernel handles (hexagonal lattices: 3)
+constexpr int FLOW_HALO = 64;      // patch-boundary / reflective sources per patch the dataflow kernel stages
+constexpr int FLOW3_DT_CAP = 6;    // widest chunk the three-face variant is instantiated for
+constexpr int FLOW3_DT_DEFAULT = 4;
+constexpr int FLOW_EXPORT = 32;    // lanes of a patch other patches read (compact edge copies per psi row)
 constexpr uint16_t LVL_EMPTY = 0xFFFF;
 constexpr int PERIM_MAX = 64;           // perimeter lanes of a structured tile (16x16: 60)
 
@@ -49,10 +54,18 @@ constexpr int32_t SRC_AXIS_SHIFT = 26;
 
 struct Vec2 { double x, y; };
 
+// A partition of the xy cells into patches of <= P cells shared by several ordering classes: the structured tiles
+// of a Cartesian mesh, the rhombic tiles of a lattice of congruent cells in one of its bases, or k-d leaves.
+struct Tiling {
+   int npatch = 0;
+   std::vector<int32_t> slot_of_xy;     // [nxy] xy cell -> slot of this tiling (patch * P + lane)
+};
+
 struct ClassPlan {
    int zdir = 0;                        // +1: sweep k upward, -1: downward, 0: no z faces
    std::vector<int> dirs;               // quadrature directions of this class
-   bool tiles = false;                  // true: shares the base tile partition
+   bool tiles = false;                  // true: swept on the base tiling (class slot == base slot)
+   int tiling = -1;                     // shared tiling this class is swept on (-1: its own level-chunk patches)
    int npatch = 0;
    int64_t S = 0;                       // slots = npatch * P
    int fin = 0;                         // max incoming lateral faces
@@ -71,7 +84,9 @@ struct ClassPlan {
    int max_halo = 0;                    // largest number of such sources in one patch
    std::vector<uint8_t> eidx;           // [S] compact index of a lane other patches read from (255: none)
    int max_export = 0;
-   bool fast = false;                   // eligible for the staged tile kernel
+   bool fast = false;                   // eligible for the staged tile kernel (and the dataflow kernel)
+   bool fast_flow = false;              // eligible for the dataflow kernel: shared tiling, <= 3 incoming faces,
+                                        // in-patch level differences <= 2, <= 64 staged sources per patch
    bool inline_ok = false;              // every lane another patch reads is one of the first PERIM_MAX lanes
 };
 
@@ -103,6 +118,8 @@ struct Plan {
    int64_t owned_updates = 0;
    int tile_classes = 0;
    int nperim = 0;                      // structured tiles: lanes 0 .. nperim-1 are the tile perimeter (0: row-major)
+   std::vector<Tiling> tilings;         // [0] = the base partition (slot numbering of q, phi, materials)
+   int lattice = 0;                     // 1: unstructured mesh recognised as a lattice of congruent cells
 };
 
 namespace detail {
@@ -148,6 +165,58 @@ inline bool dag_levels(int n, const std::vector<std::vector<int>>& up, std::vect
    return done == n;
 }
 
+// Unstructured meshes whose cells are translates of one another (hexagonal assemblies, quadrilateral grids written
+// as polygon lists) are lattices: every centroid is c0 + q a + r b with integer (q, r).  Returns the integer
+// coordinates and the distinct neighbour offsets (up to sign) in those coordinates, or false.
+inline bool detect_lattice(const pampa_sn_mesh& ms, std::vector<int>& qr, std::vector<std::pair<int, int>>& offs) {
+   const int nxy = ms.num_xy_cells, F = ms.max_xy_faces;
+   if (nxy < 4) return false;
+   int c0 = -1, best = 0;
+   for (int c = 0; c < nxy && best < F; c++) {          // a cell with as many interior neighbours as possible
+      int n = 0;
+      for (int f = 0; f < ms.xy_num_faces[c]; f++) n += ms.xy_neighbor[(size_t)c * F + f] >= 0;
+      if (n > best) { best = n; c0 = c; }
+   }
+   if (c0 < 0 || best < 2) return false;
+   std::vector<Vec2> o;
+   for (int f = 0; f < ms.xy_num_faces[c0]; f++) {
+      const int nb = ms.xy_neighbor[(size_t)c0 * F + f];
+      if (nb >= 0) o.push_back(Vec2{ms.xy_cx[nb] - ms.xy_cx[c0], ms.xy_cy[nb] - ms.xy_cy[c0]});
+   }
+   const Vec2 a = o[0];
+   const double la = std::sqrt(a.x * a.x + a.y * a.y);
+   Vec2 b{0, 0};
+   double bdet = 0.0;
+   for (const Vec2& v : o) {                            // the neighbour offset that spans the smallest cell with a
+      const double det = a.x * v.y - a.y * v.x;
+      if (std::fabs(det) > 1.0e-6 * la * la && (bdet == 0.0 || std::fabs(det) < std::fabs(bdet) - 1.0e-9 * la * la)) { b = v; bdet = det; }
+   }
+   if (bdet == 0.0) return false;
+   qr.assign((size_t)2 * nxy, 0);
+   std::map<std::pair<int, int>, int> seen;
+   for (int c = 0; c < nxy; c++) {
+      const double dx = ms.xy_cx[c] - ms.xy_cx[c0], dy = ms.xy_cy[c] - ms.xy_cy[c0];
+      const double q = (dx * b.y - dy * b.x) / bdet, r = (a.x * dy - a.y * dx) / bdet;
+      const double qi = std::nearbyint(q), ri = std::nearbyint(r);
+      if (std::fabs(q - qi) > 1.0e-5 || std::fabs(r - ri) > 1.0e-5 || std::fabs(qi) > 1.0e8 || std::fabs(ri) > 1.0e8) return false;
+      qr[2 * c] = (int)qi; qr[2 * c + 1] = (int)ri;
+      if (!seen.emplace(std::make_pair((int)qi, (int)ri), c).second) return false;
+   }
+   std::map<std::pair<int, int>, int> dirs;
+   for (int c = 0; c < nxy; c++)
+      for (int f = 0; f < ms.xy_num_faces[c]; f++) {
+         const int nb = ms.xy_neighbor[(size_t)c * F + f];
+         if (nb < 0) continue;
+         int dq = qr[2 * nb] - qr[2 * c], dr = qr[2 * nb + 1] - qr[2 * c + 1];
+         if (std::abs(dq) > 1 || std::abs(dr) > 1) return false;       // neighbours are lattice neighbours
+         if (dq < 0 || (dq == 0 && dr < 0)) { dq = -dq; dr = -dr; }
+         dirs[{dq, dr}]++;
+      }
+   offs.clear();
+   for (auto& d : dirs) offs.push_back(d.first);
+   return offs.size() >= 2 && offs.size() <= 4;
+}
+
 }  // namespace detail
 
 struct PlanInput {
@@ -185,56 +254,96 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
       return ms.bc_types[b];
    };
 
-   // ---- base partition (class independent) -------------------------------------------------
-   pl.slot_of_xy.assign(nxy, -1);
-   if (ms.xy_ij) {
+   // ---- shared partitions (class independent) ------------------------------------------------
+   // tilings[0] is the base partition (numbering of q, phi and the material map).  Structured meshes have one
+   // tiling; a lattice of congruent cells (hexagonal assemblies) gets one rhombic tiling per pair of lattice
+   // directions, because the straight tile edges of a basis are zig-zag lines for the directions that run along
+   // them (the two neighbouring tiles would depend on each other): every ordering class picks a tiling whose
+   // patch graph is acyclic for it.  Anything else: k-d leaves.
+   pl.tilings.clear();
+   pl.nperim = 0;
+   auto tile_from_coords = [&](const int* ij, int ti_, int tj_, bool perimeter_first) {
+      Tiling tg;
+      tg.slot_of_xy.assign(nxy, -1);
       int imax = 0, jmax = 0;
-      for (int c = 0; c < nxy; c++) { imax = std::max(imax, ms.xy_ij[2*c]); jmax = std::max(jmax, ms.xy_ij[2*c+1]); }
-      int ntx = imax / ti + 1, nty = jmax / tj + 1;
-      std::vector<int> tile_id(ntx * nty, -1);
+      for (int c = 0; c < nxy; c++) { imax = std::max(imax, ij[2*c]); jmax = std::max(jmax, ij[2*c+1]); }
+      int ntx = imax / ti_ + 1, nty = jmax / tj_ + 1;
+      std::vector<int> tile_id((size_t)ntx * nty, -1);
       int np = 0;
       for (int c = 0; c < nxy; c++) {           // number the non-empty tiles in first-touch order
-         int t = (ms.xy_ij[2*c+1] / tj) * ntx + ms.xy_ij[2*c] / ti;
+         int t = (ij[2*c+1] / tj_) * ntx + ij[2*c] / ti_;
          if (tile_id[t] < 0) tile_id[t] = 0;
       }
       for (int t = 0; t < ntx * nty; t++) if (tile_id[t] == 0) tile_id[t] = np++;
-      // Lane order inside a tile: the perimeter first, walked as a ring (bottom row, right column, top row
-      // backwards, left column downwards), then the interior row by row.  Only perimeter lanes are read by
-      // other patches, and the two sides a sweep direction exports are adjacent on the ring, so a neighbouring
-      // patch can read them straight from the psi rows as one or two contiguous segments of the first
-      // PERIM_MAX lanes (no edge copies).  Thin tiles (a side < 3) keep the row-major order.
-      std::vector<int> lane_of_pos(ti * tj);
+      // Lane order inside a tile: row-major, or (inline_edges) the perimeter first, walked as a ring (bottom row,
+      // right column, top row backwards, left column downwards), then the interior row by row.  Only perimeter
+      // lanes are read by other patches, and the two sides a sweep direction exports are adjacent on the ring, so
+      // a neighbouring patch can read them straight from the psi rows as one or two contiguous segments of the
+      // first PERIM_MAX lanes (no edge copies).  Thin tiles (a side < 3) keep the row-major order.
+      std::vector<int> lane_of_pos(ti_ * tj_);
       std::iota(lane_of_pos.begin(), lane_of_pos.end(), 0);
-      pl.nperim = 0;
-      if (in.opts.inline_edges && ti >= 3 && tj >= 3 && 2 * (ti + tj) - 4 <= PERIM_MAX) {
+      if (perimeter_first && ti_ >= 3 && tj_ >= 3 && 2 * (ti_ + tj_) - 4 <= PERIM_MAX) {
          int n = 0;
-         for (int i = 0; i < ti; i++) lane_of_pos[i] = n++;                                  // j = 0
-         for (int j = 1; j < tj; j++) lane_of_pos[j * ti + ti - 1] = n++;                    // i = ti - 1
-         for (int i = ti - 2; i >= 0; i--) lane_of_pos[(tj - 1) * ti + i] = n++;             // j = tj - 1
-         for (int j = tj - 2; j >= 1; j--) lane_of_pos[j * ti] = n++;                        // i = 0
+         for (int i = 0; i < ti_; i++) lane_of_pos[i] = n++;                                   // j = 0
+         for (int j = 1; j < tj_; j++) lane_of_pos[j * ti_ + ti_ - 1] = n++;                   // i = ti - 1
+         for (int i = ti_ - 2; i >= 0; i--) lane_of_pos[(tj_ - 1) * ti_ + i] = n++;            // j = tj - 1
+         for (int j = tj_ - 2; j >= 1; j--) lane_of_pos[j * ti_] = n++;                        // i = 0
          pl.nperim = n;
-         for (int j = 1; j < tj - 1; j++)
-            for (int i = 1; i < ti - 1; i++) lane_of_pos[j * ti + i] = n++;
+         for (int j = 1; j < tj_ - 1; j++)
+            for (int i = 1; i < ti_ - 1; i++) lane_of_pos[j * ti_ + i] = n++;
       }
       for (int c = 0; c < nxy; c++) {
-         int i = ms.xy_ij[2*c], j = ms.xy_ij[2*c+1];
-         int t = (j / tj) * ntx + i / ti;
-         pl.slot_of_xy[c] = tile_id[t] * P + lane_of_pos[(j % tj) * ti + (i % ti)];   // ti*tj <= P lanes used
+         int i = ij[2*c], j = ij[2*c+1];
+         int t = (j / tj_) * ntx + i / ti_;
+         tg.slot_of_xy[c] = tile_id[t] * P + lane_of_pos[(j % tj_) * ti_ + (i % ti_)];   // ti*tj <= P lanes used
       }
-      pl.npatch_b = np;
+      tg.npatch = np;
+      return tg;
+   };
+   pl.lattice = 0;
+   if (ms.xy_ij) {
+      pl.tilings.push_back(tile_from_coords(ms.xy_ij, ti, tj, in.opts.inline_edges != 0));
    } else {
-      std::vector<int> ids(nxy);
-      std::iota(ids.begin(), ids.end(), 0);
-      std::vector<std::pair<int, int>> leaves;
-      detail::kd_split(ids, 0, nxy, ms.xy_cx, ms.xy_cy, cap, leaves);
-      int np = 0;
-      for (auto& lf : leaves) {
-         std::sort(ids.begin() + lf.first, ids.begin() + lf.second);
-         for (int a = lf.first; a < lf.second; a++) pl.slot_of_xy[ids[a]] = np * P + (a - lf.first);
-         np++;
+      std::vector<int> qr;
+      std::vector<std::pair<int, int>> offs;
+      if (cap == P && detail::detect_lattice(ms, qr, offs)) {
+         pl.lattice = 1;
+         for (size_t a = 0; a < offs.size(); a++)
+            for (size_t b = a + 1; b < offs.size(); b++) {
+               const int det = offs[a].first * offs[b].second - offs[a].second * offs[b].first;
+               if (det != 1 && det != -1) continue;
+               std::vector<int> ab((size_t)2 * nxy);
+               int amin = INT32_MAX, bmin = INT32_MAX;
+               for (int c = 0; c < nxy; c++) {
+                  const int q = qr[2*c], r = qr[2*c+1];
+                  ab[2*c] = (q * offs[b].second - r * offs[b].first) / det;
+                  ab[2*c+1] = (offs[a].first * r - offs[a].second * q) / det;
+                  amin = std::min(amin, ab[2*c]); bmin = std::min(bmin, ab[2*c+1]);
+               }
+               for (int c = 0; c < nxy; c++) { ab[2*c] -= amin; ab[2*c+1] -= bmin; }
+               pl.tilings.push_back(tile_from_coords(ab.data(), ti, tj, false));
+            }
       }
-      pl.npatch_b = np;
+      if (pl.tilings.empty()) {
+         pl.lattice = 0;
+         std::vector<int> ids(nxy);
+         std::iota(ids.begin(), ids.end(), 0);
+         std::vector<std::pair<int, int>> leaves;
+         detail::kd_split(ids, 0, nxy, ms.xy_cx, ms.xy_cy, cap, leaves);
+         Tiling tg;
+         tg.slot_of_xy.assign(nxy, -1);
+         int np = 0;
+         for (auto& lf : leaves) {
+            std::sort(ids.begin() + lf.first, ids.begin() + lf.second);
+            for (int a = lf.first; a < lf.second; a++) tg.slot_of_xy[ids[a]] = np * P + (a - lf.first);
+            np++;
+         }
+         tg.npatch = np;
+         pl.tilings.push_back(tg);
+      }
    }
+   pl.slot_of_xy = pl.tilings[0].slot_of_xy;
+   pl.npatch_b = pl.tilings[0].npatch;
    pl.Sb = (int64_t)pl.npatch_b * P;
    pl.xy_of_slot.assign(pl.Sb, -1);
    for (int c = 0; c < nxy; c++) {
@@ -325,9 +434,8 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
       std::vector<int> glevel;
       if (!detail::dag_levels(nxy, up, glevel)) throw std::runtime_error("cyclic upwind dependency in the xy mesh");
 
-      // candidate 1: base tiles
       std::vector<int32_t> patch_of(nxy), lane_of(nxy);
-      auto try_partition = [&](int np) -> bool {
+      auto try_partition = [&](ClassPlan& cq, int np) -> bool {
          // patch graph
          std::vector<std::vector<int>> pup(np);
          for (int c = 0; c < nxy; c++)
@@ -335,15 +443,129 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
          for (auto& v : pup) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
          std::vector<int> plevel;
          if (!detail::dag_levels(np, pup, plevel)) return false;
-         cp.npatch = np; cp.S = (int64_t)np * P;
-         cp.patch_level.assign(plevel.begin(), plevel.end());
+         cq.npatch = np; cq.S = (int64_t)np * P;
+         cq.patch_level.assign(plevel.begin(), plevel.end());
          return true;
       };
-      for (int c = 0; c < nxy; c++) { patch_of[c] = pl.slot_of_xy[c] / P; lane_of[c] = pl.slot_of_xy[c] % P; }
-      cp.tiles = try_partition(pl.npatch_b);
-      if (cp.tiles) pl.tile_classes++;
+      // slot tables, local levels, upwind sources of the partition in patch_of / lane_of
+      auto build_tables = [&](ClassPlan& cq) {
+         const int64_t S = cq.S;
+         cq.cell_of.assign(S, -1); cq.pos_of.assign(pl.Sb, -1);
+         for (int c = 0; c < nxy; c++) {
+            int64_t sl = (int64_t)patch_of[c] * P + lane_of[c];
+            cq.cell_of[sl] = pl.slot_of_xy[c];
+            cq.pos_of[pl.slot_of_xy[c]] = (int32_t)sl;
+         }
+         // local levels: longest path over in-patch edges
+         std::vector<std::vector<int>> lup(nxy);
+         for (int c = 0; c < nxy; c++)
+            for (int u : up[c]) if (patch_of[u] == patch_of[c]) lup[c].push_back(u);
+         std::vector<int> ll;
+         detail::dag_levels(nxy, lup, ll);
+         cq.lvl.assign(S, LVL_EMPTY);
+         cq.patch_nlev.assign(cq.npatch, 1);
+         int maxdiff = 1;
+         for (int c = 0; c < nxy; c++) {
+            if (ll[c] >= LVL_EMPTY) throw std::runtime_error("patch pipeline too deep");
+            cq.lvl[(int64_t)patch_of[c] * P + lane_of[c]] = (uint16_t)ll[c];
+            cq.patch_nlev[patch_of[c]] = std::max(cq.patch_nlev[patch_of[c]], ll[c] + 1);
+            for (int u : lup[c]) maxdiff = std::max(maxdiff, ll[c] - ll[u]);
+         }
+         cq.ring = std::min(RING_MAX, maxdiff + 1);
+         cq.nsteps = *std::max_element(cq.patch_nlev.begin(), cq.patch_nlev.end()) + pl.nz - 1;
+         // sources and vectors
+         cq.out_vec.assign(S, Vec2{0, 0});
+         cq.in_src.assign((size_t)FIN_MAX * S, SRC_NONE);
+         cq.in_vec.assign((size_t)FIN_MAX * S, Vec2{0, 0});
+         cq.rout.assign((size_t)ROUT_MAX * S, -1);
+         cq.in_hidx.assign((size_t)FIN_MAX * S, 0);
+         std::vector<int> halo_count(cq.npatch, 0);
+         for (int c = 0; c < nxy; c++) {
+            const int64_t sl = (int64_t)patch_of[c] * P + lane_of[c];
+            int nin = 0, nro = 0;
+            const double ia = 1.0 / ms.xy_area[c];
+            for (int f = 0; f < ms.xy_num_faces[c]; f++) {
+               size_t a = (size_t)c * F + f;
+               const double vx = ms.xy_face_cf[a] * ms.xy_face_fx[a] * ia;
+               const double vy = ms.xy_face_cf[a] * ms.xy_face_fy[a] * ia;
+               const int nb = ms.xy_neighbor[a];
+               if (flg[a] == 1) {
+                  cq.out_vec[sl].x += vx; cq.out_vec[sl].y += vy;
+                  if (nb < 0 && rface_id[a] >= 0) {
+                     if (nro >= ROUT_MAX) throw std::runtime_error("cell with more than 2 outgoing reflective faces");
+                     cq.rout[(size_t)nro * S + sl] = rface_id[a]; nro++;
+                  }
+               } else if (flg[a] == 2) {
+                  int32_t code = SRC_NONE;
+                  int dly = 0;
+                  if (nb >= 0) {
+                     if (patch_of[nb] == patch_of[c] && ll[c] - ll[nb] < cq.ring) {
+                        code = (SRC_LOCAL << SRC_KIND_SHIFT) | lane_of[nb];
+                        dly = ll[c] - ll[nb];
+                     } else
+                        code = (SRC_GLOBAL << SRC_KIND_SHIFT) | (int32_t)((int64_t)patch_of[nb] * P + lane_of[nb]);
+                  } else if (rface_id[a] >= 0) {
+                     code = (SRC_REFL << SRC_KIND_SHIFT) | (pl.rface_axis[rface_id[a]] << SRC_AXIS_SHIFT) | rface_id[a];
+                  }
+                  if (code != SRC_NONE) {
+                     cq.in_src[(size_t)nin * S + sl] = code;
+                     cq.in_vec[(size_t)nin * S + sl] = Vec2{vx, vy};
+                     // in-patch sources: pipeline steps between the writer and the reader (1 when the ring has two
+                     // entries); other sources: index of the staged ("halo") entry of the patch
+                     if ((code >> SRC_KIND_SHIFT) != SRC_LOCAL)
+                        cq.in_hidx[(size_t)nin * S + sl] = (uint16_t)std::min(65535, halo_count[patch_of[c]]++);
+                     else
+                        cq.in_hidx[(size_t)nin * S + sl] = (uint16_t)dly;
+                     nin++;
+                  }
+               }
+            }
+         }
+         cq.max_halo = *std::max_element(halo_count.begin(), halo_count.end());
+         // lanes whose flux another patch reads get a compact "edge" index: the tile kernel stores a
+         // contiguous copy of them behind each psi row so that the importing patch reads whole sectors
+         cq.eidx.assign(S, 255);
+         std::vector<char> exported(S, 0);
+         for (int f = 0; f < FIN_MAX; f++)
+            for (int64_t sl = 0; sl < S; sl++) {
+               const int32_t code = cq.in_src[(size_t)f * S + sl];
+               if (code >= 0 && (code >> SRC_KIND_SHIFT) == SRC_GLOBAL) exported[code & SRC_PAYLOAD] = 1;
+            }
+         cq.max_export = 0;
+         for (int p = 0; p < cq.npatch; p++) {
+            int n = 0;
+            for (int l = 0; l < P; l++)
+               if (exported[(int64_t)p * P + l]) { cq.eidx[(int64_t)p * P + l] = (uint8_t)std::min(254, n); n++; }
+            cq.max_export = std::max(cq.max_export, n);
+         }
+         cq.inline_ok = pl.nperim > 0 && cq.tiling == 0;
+         for (int64_t sl = 0; sl < S; sl++) if (exported[sl] && (sl % P) >= PERIM_MAX) cq.inline_ok = false;
+         const int maxlev = *std::max_element(cq.patch_nlev.begin(), cq.patch_nlev.end());
+         // the staged tile kernel: base tiling, <= 2 incoming faces, double-buffered ring, a halo that fits the
+         // 256-wide staging rows; the dataflow kernel also takes other shared tilings, a third incoming face,
+         // in-patch sources two steps back and 64 staged sources
+         cq.fast = cq.tiling == 0 && cq.fin <= 2 && cq.ring == 2 && cq.max_halo <= 32 && cq.max_export <= 32 && maxlev <= 31;
+         cq.fast_flow = cq.tiling >= 0 && cq.fin <= FLOW_FIN && cq.ring <= 3 && cq.max_halo <= FLOW_HALO &&
+                        cq.max_export <= FLOW_EXPORT && maxlev <= 31;
+      };
+      // candidates: the shared tilings in order (the first one the dataflow kernel can sweep, else the first acyclic
+      // one), then chunks of the class's own (level, lateral) order, which are acyclic by construction
+      bool placed = false;
+      ClassPlan fallback;
+      bool have_fallback = false;
+      for (size_t tgi = 0; tgi < pl.tilings.size() && !placed; tgi++) {
+         const Tiling& tg = pl.tilings[tgi];
+         for (int c = 0; c < nxy; c++) { patch_of[c] = tg.slot_of_xy[c] / P; lane_of[c] = tg.slot_of_xy[c] % P; }
+         ClassPlan cq = cp;
+         cq.tiling = (int)tgi; cq.tiles = (tgi == 0);
+         if (!try_partition(cq, tg.npatch)) continue;
+         build_tables(cq);
+         if (cq.fast_flow) { cp = std::move(cq); placed = true; }
+         else if (!have_fallback) { fallback = std::move(cq); have_fallback = true; }
+      }
+      if (!placed && have_fallback) { cp = std::move(fallback); placed = true; }
+      if (placed) pl.tile_classes++;
       else {
-         // candidate 2: chunks of the (level, lateral) order -- acyclic by construction
          double ox = 0, oy = 0;
          for (int m : cp.dirs) { ox += qd.directions[3*m]; oy += qd.directions[3*m+1]; }
          std::vector<int> ord(nxy);
@@ -355,99 +577,9 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
             if (lat[a] != lat[b]) return lat[a] < lat[b];
             return a < b; });
          for (int a = 0; a < nxy; a++) { patch_of[ord[a]] = a / cap; lane_of[ord[a]] = a % cap; }
-         if (!try_partition((nxy + cap - 1) / cap)) throw std::runtime_error("internal: level-chunk partition is cyclic");
-      }
-      // slot tables
-      const int64_t S = cp.S;
-      cp.cell_of.assign(S, -1); cp.pos_of.assign(pl.Sb, -1);
-      for (int c = 0; c < nxy; c++) {
-         int64_t s = (int64_t)patch_of[c] * P + lane_of[c];
-         cp.cell_of[s] = pl.slot_of_xy[c];
-         cp.pos_of[pl.slot_of_xy[c]] = (int32_t)s;
-      }
-      // local levels: longest path over in-patch edges
-      {
-         std::vector<std::vector<int>> lup(nxy);
-         for (int c = 0; c < nxy; c++)
-            for (int u : up[c]) if (patch_of[u] == patch_of[c]) lup[c].push_back(u);
-         std::vector<int> ll;
-         detail::dag_levels(nxy, lup, ll);
-         cp.lvl.assign(S, LVL_EMPTY);
-         cp.patch_nlev.assign(cp.npatch, 1);
-         int maxdiff = 1;
-         for (int c = 0; c < nxy; c++) {
-            if (ll[c] >= LVL_EMPTY) throw std::runtime_error("patch pipeline too deep");
-            cp.lvl[(int64_t)patch_of[c] * P + lane_of[c]] = (uint16_t)ll[c];
-            cp.patch_nlev[patch_of[c]] = std::max(cp.patch_nlev[patch_of[c]], ll[c] + 1);
-            for (int u : lup[c]) maxdiff = std::max(maxdiff, ll[c] - ll[u]);
-         }
-         cp.ring = std::min(RING_MAX, maxdiff + 1);
-         cp.nsteps = *std::max_element(cp.patch_nlev.begin(), cp.patch_nlev.end()) + pl.nz - 1;
-         // sources and vectors
-         cp.out_vec.assign(S, Vec2{0, 0});
-         cp.in_src.assign((size_t)FIN_MAX * S, SRC_NONE);
-         cp.in_vec.assign((size_t)FIN_MAX * S, Vec2{0, 0});
-         cp.rout.assign((size_t)ROUT_MAX * S, -1);
-         cp.in_hidx.assign((size_t)FIN_MAX * S, 0);
-         std::vector<int> halo_count(cp.npatch, 0);
-         for (int c = 0; c < nxy; c++) {
-            const int64_t s = (int64_t)patch_of[c] * P + lane_of[c];
-            int nin = 0, nro = 0;
-            const double ia = 1.0 / ms.xy_area[c];
-            for (int f = 0; f < ms.xy_num_faces[c]; f++) {
-               size_t a = (size_t)c * F + f;
-               const double vx = ms.xy_face_cf[a] * ms.xy_face_fx[a] * ia;
-               const double vy = ms.xy_face_cf[a] * ms.xy_face_fy[a] * ia;
-               const int nb = ms.xy_neighbor[a];
-               if (flg[a] == 1) {
-                  cp.out_vec[s].x += vx; cp.out_vec[s].y += vy;
-                  if (nb < 0 && rface_id[a] >= 0) {
-                     if (nro >= ROUT_MAX) throw std::runtime_error("cell with more than 2 outgoing reflective faces");
-                     cp.rout[(size_t)nro * S + s] = rface_id[a]; nro++;
-                  }
-               } else if (flg[a] == 2) {
-                  int32_t code = SRC_NONE;
-                  if (nb >= 0) {
-                     if (patch_of[nb] == patch_of[c] && ll[c] - ll[nb] < cp.ring)
-                        code = (SRC_LOCAL << SRC_KIND_SHIFT) | lane_of[nb];
-                     else
-                        code = (SRC_GLOBAL << SRC_KIND_SHIFT) | (int32_t)((int64_t)patch_of[nb] * P + lane_of[nb]);
-                  } else if (rface_id[a] >= 0) {
-                     code = (SRC_REFL << SRC_KIND_SHIFT) | (pl.rface_axis[rface_id[a]] << SRC_AXIS_SHIFT) | rface_id[a];
-                  }
-                  if (code != SRC_NONE) {
-                     cp.in_src[(size_t)nin * S + s] = code;
-                     cp.in_vec[(size_t)nin * S + s] = Vec2{vx, vy};
-                     if ((code >> SRC_KIND_SHIFT) != SRC_LOCAL)
-                        cp.in_hidx[(size_t)nin * S + s] = (uint16_t)std::min(65535, halo_count[patch_of[c]]++);
-                     nin++;
-                  }
-               }
-            }
-         }
-         cp.max_halo = *std::max_element(halo_count.begin(), halo_count.end());
-         // lanes whose flux another patch reads get a compact "edge" index: the tile kernel stores a
-         // contiguous copy of them behind each psi row so that the importing patch reads whole sectors
-         cp.eidx.assign(S, 255);
-         std::vector<char> exported(S, 0);
-         for (int f = 0; f < FIN_MAX; f++)
-            for (int64_t sl = 0; sl < S; sl++) {
-               const int32_t code = cp.in_src[(size_t)f * S + sl];
-               if (code >= 0 && (code >> SRC_KIND_SHIFT) == SRC_GLOBAL) exported[code & SRC_PAYLOAD] = 1;
-            }
-         cp.max_export = 0;
-         for (int p = 0; p < cp.npatch; p++) {
-            int n = 0;
-            for (int l = 0; l < P; l++)
-               if (exported[(int64_t)p * P + l]) { cp.eidx[(int64_t)p * P + l] = (uint8_t)std::min(254, n); n++; }
-            cp.max_export = std::max(cp.max_export, n);
-         }
-         cp.inline_ok = pl.nperim > 0;
-         for (int64_t sl = 0; sl < S; sl++) if (exported[sl] && (sl % P) >= PERIM_MAX) cp.inline_ok = false;
-         // the staged tile kernel: shared tiles, <= 2 incoming faces, double-buffered ring, and a
-         // halo that fits the 256-wide staging rows
-         cp.fast = cp.tiles && cp.fin <= 2 && cp.ring == 2 && cp.max_halo <= 32 && cp.max_export <= 32 &&
-                   *std::max_element(cp.patch_nlev.begin(), cp.patch_nlev.end()) <= 31;
+         cp.tiling = -1; cp.tiles = false;
+         if (!try_partition(cp, (nxy + cap - 1) / cap)) throw std::runtime_error("internal: level-chunk partition is cyclic");
+         build_tables(cp);
       }
    }
    class_flags.clear();
@@ -458,7 +590,11 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
    for (size_t ci = 0; ci < pl.classes.size(); ci++) {
       const ClassPlan& cp = pl.classes[ci];
       int n = (int)cp.dirs.size();
-      const int dtm = (in.opts.dt_max >= 1 && in.opts.dt_max <= DT_MAX) ? in.opts.dt_max : DT_DEFAULT;
+      int dtm = (in.opts.dt_max >= 1 && in.opts.dt_max <= DT_MAX) ? in.opts.dt_max : DT_DEFAULT;
+      // classes only the three-face variant of the dataflow kernel can sweep (a third coefficient set per lane):
+      // narrower chunks keep it at two CTAs per SM without spills
+      if (cp.fast_flow && !cp.fast)
+         dtm = (in.opts.dt_max >= 1 && in.opts.dt_max <= DT_MAX) ? std::min(in.opts.dt_max, FLOW3_DT_CAP) : FLOW3_DT_DEFAULT;
       int nch = (n + dtm - 1) / dtm;
       int per = (n + nch - 1) / nch;
       for (int a = 0; a < n; a += per) {

@@ -57,6 +57,38 @@ def test_plan_on_synthetic_meshes(opts):
     assert info["num_classes"] >= 8          # the hexagon normals split the octants further
 
 
+def test_plan_lattice_tilings():
+    """Unstructured meshes of congruent cells are recognised as lattices: a hexagonal core gets one rhombic tiling
+    per pair of lattice directions and every ordering class finds one whose patch graph is acyclic for it, so the
+    one-launch dataflow kernel sweeps them all; quadrilaterals written as polygons behave like a Cartesian mesh;
+    hexagons cut into triangles sit on a finer lattice with a third of its points empty: still tiled, and swept by
+    the general kernel where the dataflow kernel's limits (levels per patch, steps back) do not hold."""
+    for rings, order in ((6, 8), (20, 12)):
+        mesh, xs, _ = syn.hex_core(rings, 6, num_groups=2)
+        info = pb.plan_check(mesh, syn.level_symmetric(order), 2)
+        assert info["lattice"] == 1 and info["num_tilings"] == 3
+        assert info["num_classes"] == 12 and info["flow_classes"] == 12 and info["tile_classes"] == 12
+    em, xs, quad, ls, z = util.load_golden("pwr_unstructured_s2")
+    info = pb.plan_check(em, quad, 2)
+    assert info["lattice"] == 1 and info["num_tilings"] == 1 and info["flow_classes"] >= 3
+    # small patches are an explicit request for the general path
+    mesh, xs, _ = syn.hex_core(6, 4, num_groups=2)
+    info = pb.plan_check(mesh, syn.level_symmetric(4), 2, patch_cells=32)
+    assert info["lattice"] == 0
+    # triangles: a honeycomb of centroids = a triangular lattice with holes
+    pts, cells, _ = syn.hex_lattice(4, 1.0)
+    pts = list(map(tuple, pts))
+    tri = []
+    for c in cells:
+        cx = sum(pts[p][0] for p in c) / 6.0; cy = sum(pts[p][1] for p in c) / 6.0
+        pts.append((cx, cy))
+        for a in range(6):
+            tri.append([c[a], c[(a + 1) % 6], len(pts) - 1])
+    tmesh = syn.polygon_mesh(np.array(pts), tri, np.ones(3), np.zeros(3 * len(tri), dtype=np.int32))
+    info = pb.plan_check(tmesh, syn.level_symmetric(4), 2)
+    assert info["lattice"] == 1 and info["tile_classes"] == info["num_classes"] == 12
+
+
 def test_plan_sharding_partitions_the_work():
     q8 = syn.level_symmetric(8)
     mesh, xs = syn.checkerboard_core(20, 20, 8, num_groups=4)

@@ -121,3 +121,26 @@ def test_vtk_output(decks, tmp_path):
         assert util.rel_l2(s, vals["flux_%d" % (g + 1)]) < 1e-5
     # without the switch nothing is written
     assert not os.path.exists(os.path.join(decks, "pwr_cartesian_s2", "output_0.vtk"))
+
+
+def test_default_face_interpolation(decks, tmp_path):
+    """A deck that omits `mixed-face-interpolation` runs with the reference's default, 0.1 (src/SNSolver.hxx:16).  On
+    the PWR deck that eigenvector has negative angular fluxes, and the reference fails such a solve in
+    normalizeAngularFlux (src/SNSolver.cxx:329): same message, non-zero exit.  With 0.9 the solve goes through."""
+    import shutil
+    exe = os.path.join(ROOT, "pampa_b200", "bin", "pampa")
+    for delta, ok in ((None, False), ("0.9", True)):
+        case = tmp_path / ("case_%s" % delta)
+        shutil.copytree(os.path.join(decks, "pwr_cartesian_s2"), case)
+        text = open(case / "input.pmp").read()
+        assert "mixed-face-interpolation 1.0" in text
+        text = text.replace("   mixed-face-interpolation 1.0\n", "" if delta is None else "   mixed-face-interpolation %s\n" % delta)
+        text = text.replace("least-squares-boundary-interpolation 1", "least-squares-boundary-interpolation 0")
+        open(case / "input.pmp", "w").write(text)
+        r = subprocess.run([exe, "input.pmp"], cwd=case, capture_output=True, text=True)
+        if ok:
+            assert r.returncode == 0, r.stdout + r.stderr
+            assert "Effective multiplication factor: 0.96" in r.stdout
+        else:
+            assert r.returncode != 0
+            assert "negative values in the angular-flux solution" in r.stdout + r.stderr

@@ -144,7 +144,9 @@ def load_golden(name):
         xy_face_fy=z["xy_face_fy"], xy_face_cf=z["xy_face_cf"], xy_area=z["xy_area"], xy_cx=z["xy_cx"],
         xy_cy=z["xy_cy"], materials=z["materials"], bc_types=[int(v) for v in z["bc_types"]],
         dz=z["dz"] if len(z["dz"]) else None, bc_minus_z=int(z["bc_z"][0]), bc_plus_z=int(z["bc_z"][1]),
-        xy_ij=z["xy_ij"] if len(z["xy_ij"]) else None)
+        xy_ij=z["xy_ij"] if len(z["xy_ij"]) else None, delta=float(z["delta"]) if "delta" in z else 1.0,
+        xy_face_kout=z["xy_face_kout"] if "xy_face_kout" in z else None,
+        xy_face_kin=z["xy_face_kin"] if "xy_face_kin" in z else None)
     xs = pb.CrossSections(z["sigma_total"], z["sigma_scattering"], z["nu_sigma_fission"],
                           z["kappa_sigma_fission"], z["chi_effective"], np.zeros(len(z["sigma_total"])))
     quad = syn.level_symmetric(int(z["order"]))
