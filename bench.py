@@ -219,20 +219,37 @@ def sharded_parity(a, dist, rank, world, local_rank, shard_opts):
         one.close()
     dev = pb.SNDevice(mesh, xs, quad, device=local_rank, rank=rank, num_ranks=world, **shard_opts)
     comm_setup(dev, dist, rank)
+    # the iterate goes in through the (partitioned) field interface too: every rank sets its own range of cells
+    dev.set("flux-moments", np.ones(dev.field_size("flux-moments")))
     k, it = dev.solve_keff(tol_k=1e-10, tol_phi=1e-9)
-    phi = dev.get("scalar-flux")
+    phi = dev.get("scalar-flux")                        # this rank's range of cells when the fields are partitioned
     dev.close()
-    ks = torch.tensor([k, -k], dtype=torch.float64, device="cuda")
-    dist.all_reduce(ks, op=dist.ReduceOp.MAX)
-    spread = float(ks[0] + ks[1])                       # max k - min k over the ranks
+    # every rank checks its own part against the one-GPU flux of rank 0
+    nphi = mesh.num_cells * a.groups
+    full = torch.zeros(nphi, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        full.copy_(torch.from_numpy(ref[1]))
+    dist.broadcast(full, 0)
+    full = full.cpu().numpy()
+    per = -(-mesh.num_cells // world) * a.groups if shard_opts.get("partition_fields") else nphi
+    i0 = min(nphi, per * rank) if shard_opts.get("partition_fields") else 0
+    mine = full[i0:i0 + phi.size]
+    err = torch.tensor([float(np.sum((phi - mine) ** 2)), float(np.sum(mine ** 2))], dtype=torch.float64, device="cuda")
+    mx = torch.tensor([float(np.max(np.abs(phi - mine) / np.abs(mine))), k, -k], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(phi.size)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(err)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(cnt)
+    spread = float(mx[1] + mx[2])                       # max k - min k over the ranks
     out = None
     if rank == 0:
-        l2 = float(np.linalg.norm(phi - ref[1]) / np.linalg.norm(ref[1]))
-        mx = float(np.max(np.abs(phi - ref[1]) / np.abs(ref[1])))
+        l2 = float(torch.sqrt(err[0] / err[1]))
+        covered = float(cnt[0]) / nphi                  # 1 with partitioned fields (each cell checked once), else N
         out = {"problem": "%d^3 cells, S%d, %d groups, reflective -x/-y" % (n, a.order, a.groups),
                "keff_1gpu": ref[0], "keff_sharded": k, "keff_diff": k - ref[0], "keff_spread_over_ranks": spread,
-               "phi_rel_l2": l2, "phi_max_rel": mx, "iterations": [ref[2], it],
-               "ok": bool(abs(k - ref[0]) < 1e-7 and l2 < 1e-6 and mx < 1e-5 and spread < 1e-12)}
+               "phi_rel_l2": l2, "phi_max_rel": float(mx[0]), "iterations": [ref[2], it],
+               "field_coverage": covered,
+               "ok": bool(abs(k - ref[0]) < 1e-7 and l2 < 1e-6 and float(mx[0]) < 1e-5 and spread < 1e-12)}
     return out
 
 
@@ -257,8 +274,11 @@ def run_b200(a, rank, world, local_rank):
     M = len(quad.weights)
     # sharding: by energy group when the groups divide evenly over the ranks (allgather of the group
     # slabs, sharded source / reduction), else by angle set (allreduce of the flux moments)
+    # partition_fields: every rank moves its own contiguous range of cells between host and device (the
+    # local-length vectors the reference hands its MPI ranks), 1/N of the host bytes each
     opts = dict(device=local_rank, rank=rank, num_ranks=world,
-                shard_mode=1 if (world > 1 and a.groups % world == 0) else 0)
+                shard_mode=1 if (world > 1 and a.groups % world == 0) else 0,
+                partition_fields=1 if world > 1 else 0)
     opts.update(json.loads(a.opts))
     parity = None
     if world > 1 and not a.no_parity:
@@ -337,10 +357,10 @@ def run_b200(a, rank, world, local_rank):
     # sections and of the flux iterate, K source iterations, download of scalar flux and power
     e2e = None
     if not a.no_e2e:
-        n_phi = mesh.num_cells * a.groups
+        n_phi = dev.field_size("flux-moments")          # this rank's part of the field when sharded
         host_in = torch.empty(n_phi, dtype=torch.float64, pin_memory=True).numpy()
         host_phi = torch.empty(n_phi, dtype=torch.float64, pin_memory=True).numpy()
-        host_pow = torch.empty(mesh.num_cells, dtype=torch.float64, pin_memory=True).numpy()
+        host_pow = torch.empty(dev.field_size("power"), dtype=torch.float64, pin_memory=True).numpy()
         host_in[:] = 1.0
         # untimed warm-up of the same call sequence (first use allocates the device staging buffer)
         dev.set("flux-moments", host_in)
@@ -367,9 +387,14 @@ def run_b200(a, rank, world, local_rank):
             dt = float(t[0])
         xs_bytes = sum(v.nbytes for v in (xs.sigma_total, xs.sigma_scattering, xs.nu_sigma_fission,
                                           xs.kappa_sigma_fission, xs.chi_effective))
+        h2d, d2h = host_in.nbytes + xs_bytes, phi_out.nbytes + pow_out.nbytes
+        if dist is not None:                              # whole-job bytes: summed over the ranks
+            t = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            h2d, d2h = float(t[0]), float(t[1])
         e2e = {"value": U_total * a.steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": (host_in.nbytes + xs_bytes) / a.steps,
-               "d2h_bytes_per_step": (phi_out.nbytes + pow_out.nbytes) / a.steps,
+               "h2d_bytes_per_step": h2d / a.steps,
+               "d2h_bytes_per_step": d2h / a.steps,
                "call": "update_xs + set(flux-moments) + %d source iterations + get(scalar-flux, power)" % a.steps,
                "phases_ms": phases}
 
@@ -379,7 +404,7 @@ def run_b200(a, rank, world, local_rank):
     if not a.no_solve:
         # cold start: flat flux, k = 1 (the timed steps above leave a settled k estimate behind, which saves
         # ~40 of ~200 accelerated iterations)
-        dev.set("flux-moments", np.ones(mesh.num_cells * a.groups))
+        dev.set("flux-moments", np.ones(dev.field_size("flux-moments")))
         dev.set("keff", np.ones(1))
         barrier()
         t0 = time.perf_counter()

@@ -9,6 +9,7 @@
  *                          + buildGaussGradientScheme           src/SNSolver.cxx:159-208 (via cf)
  *                          + AngularQuadratureSet tables         src/AngularQuadratureSet.cxx:4-209
  *   pampa_sn_update_xs     the XS reads of buildMatrices        src/SNSolver.cxx:383-439
+ *   pampa_sn_update_materials   ... when T_data changes them   src/SNSolver.cxx:383-439, src/FeedbackNuclearData.hxx:62-140
  *   pampa_sn_source        scattering + fission rows of R / F   src/SNSolver.cxx:417-439
  *   pampa_sn_sweep         R^-1 applied by EPSSolve (LU solve)  src/petsc.cxx:428-433
  *   pampa_sn_reduce        calculateScalarFlux + production     src/SNSolver.cxx:272-299,
@@ -130,6 +131,11 @@ typedef struct {
                                     no faster: measured 22.35 vs 21.90 ms per iteration); 0: default */
    int32_t no_graph;             /* 1: never replay the sweep's launch sequence from a CUDA graph (plans with >= 32
                                     launches per sweep are captured once and replayed; A/B testing) */
+   int32_t partition_fields;     /* sharded runs, 1: pampa_sn_get / _set / _field_size of the cell fields work on this
+                                    rank's contiguous range of cells only -- the local-length vectors the reference
+                                    hands its MPI ranks (src/Solver.cxx:18-43) -- so that every rank moves 1/N of the
+                                    host bytes: cells [rank*c, min(N, (rank+1)*c)), c = ceil(N / num_ranks);
+                                    set("flux-moments") completes the iterate with an allgather on the device */
 } pampa_sn_options;
 
 void pampa_sn_default_options(pampa_sn_options* opts);
@@ -141,6 +147,11 @@ int pampa_sn_destroy(pampa_sn_handle* h);
 const char* pampa_sn_last_error(const pampa_sn_handle* h);   /* h may be NULL: create errors */
 
 int pampa_sn_update_xs(pampa_sn_handle* h, const pampa_sn_xs* xs);
+/* Temperature feedback (src/FeedbackNuclearData.hxx:62-140 through SNSolver::buildMatrices): a new table of
+ * (material, temperature) rows AND a new cell -> row map [num_layers*num_xy_cells]; the number of rows may differ
+ * from the one the handle was created with.  Returns 1 (handle unchanged but for the error text) when the new
+ * table does not fit the handle's sweep plan; the caller then destroys and re-creates it. */
+int pampa_sn_update_materials(pampa_sn_handle* h, const pampa_sn_xs* xs, const int32_t* materials);
 
 /* One source iteration, split the way the three kernels are: q <- (S + F/keff) phi;
  * psi <- T^-1 q (all owned angle sets and groups); phi <- sum_m w_m psi and the production /

@@ -146,8 +146,36 @@ def _finish_nuclear_data(xs: XS, beta_total: float) -> None:
 
 def read_material(path) -> XS:
     """Material file -> the cross-section table a standalone SN run sees (T = 0)."""
+    return read_material_tables(path)[1][0]
+
+
+def xs_at_temperature(temperatures, tables, T) -> XS:
+    """Linear interpolation between the tabulated temperatures, clamped outside the table
+    (src/FeedbackNuclearData.hxx:62-140).  T equal to the first tabulated temperature is read as that table (the
+    reference's lowerBound would index entry -1 there)."""
+    n = len(tables)
+    if n < 2 or T <= temperatures[0]:
+        return tables[0]
+    if T > temperatures[-1]:
+        return tables[-1]
+    i2 = int(np.searchsorted(temperatures, T, side="left"))
+    i1 = i2 - 1
+    f = (T - temperatures[i1]) / (temperatures[i2] - temperatures[i1])
+    a, b = tables[i1], tables[i2]
+    mix = lambda u, v: (1.0 - f) * u + f * v
+    return XS(G=a.G, sigma_total=mix(a.sigma_total, b.sigma_total),
+              nu_sigma_fission=mix(a.nu_sigma_fission, b.nu_sigma_fission),
+              kappa_sigma_fission=mix(a.kappa_sigma_fission, b.kappa_sigma_fission),
+              sigma_scattering=mix(a.sigma_scattering, b.sigma_scattering),
+              chi_prompt=mix(a.chi_prompt, b.chi_prompt), chi_delayed=mix(a.chi_delayed, b.chi_delayed),
+              chi_effective=mix(a.chi_effective, b.chi_effective))
+
+
+def read_material_tables(path):
+    """Material file -> (temperatures, [XS per tabulated temperature]); constant data: ([0.0], [XS])."""
     L = Lines(path)
     tables, beta_total = [], 0.0
+    temperatures = [0.0]
     while True:
         line = L.next()
         if not line or line[0] == "}":
@@ -162,7 +190,7 @@ def read_material(path) -> XS:
                 if not sub or sub[0] == "}":
                     break
                 if sub[0] == "temperature":
-                    L.numbers(int(sub[1]))
+                    temperatures = L.numbers(int(sub[1]))
                 elif sub[0] == "nuclear-data":
                     tables.append(_read_nuclear_data(L))
                 else:
@@ -183,9 +211,9 @@ def read_material(path) -> XS:
             pass
         else:
             raise ValueError("unrecognized keyword '%s'" % k)
-    xs = tables[0]                     # T = 0 clamps to the first table
-    _finish_nuclear_data(xs, beta_total)
-    return xs
+    for xs in tables:                  # (T = 0 clamps to the first table)
+        _finish_nuclear_data(xs, beta_total)
+    return np.array(temperatures, dtype=float), tables
 
 
 # --------------------------------------------------------------------------- mesh

@@ -44,7 +44,8 @@ class Options(C.Structure):
     _fields_ = [("device", i32), ("store_psi", i32), ("patch_cells", i32), ("tile_i", i32), ("tile_j", i32),
                 ("z_chunk", i32), ("rank", i32), ("num_ranks", i32), ("shard_mode", i32), ("verbose", i32),
                 ("dt_max", i32), ("generic_only", i32), ("single_stream", i32),
-                ("anderson_depth", i32), ("wave_launch", i32), ("group_merge", i32), ("inline_edges", i32), ("no_graph", i32)]
+                ("anderson_depth", i32), ("wave_launch", i32), ("group_merge", i32), ("inline_edges", i32), ("no_graph", i32),
+                ("partition_fields", i32)]
 
 
 class Info(C.Structure):
@@ -63,6 +64,7 @@ SYMBOLS = {
     "pampa_sn_destroy": (C.c_int, [C.c_void_p]),
     "pampa_sn_last_error": (C.c_char_p, [C.c_void_p]),
     "pampa_sn_update_xs": (C.c_int, [C.c_void_p, C.POINTER(XS)]),
+    "pampa_sn_update_materials": (C.c_int, [C.c_void_p, C.POINTER(XS), p_i32]),
     "pampa_sn_source": (C.c_int, [C.c_void_p, f64]),
     "pampa_sn_sweep": (C.c_int, [C.c_void_p]),
     "pampa_sn_reduce": (C.c_int, [C.c_void_p, p_f64, p_f64, p_f64]),

@@ -80,13 +80,15 @@ struct pampa_sn_handle {
    double *d_bnd[2] = {nullptr, nullptr}, *d_bndz[2] = {nullptr, nullptr};
    int bnd_cur = 0;
    int64_t bnd_count = 0, bndz_count = 0;
-   double *d_partials = nullptr, *d_sums = nullptr;
+   double *d_partials = nullptr, *d_sums = nullptr, *d_sums_all = nullptr;   // d_sums_all: [rank][5] (sharded runs)
    // Anderson acceleration state (allocated by the first accelerated solve)
    double* aa_f[AA_SLOTS] = {};
    double* aa_g[AA_SLOTS] = {};
    double* aa_b[AA_SLOTS] = {};         // boundary-flux part of the state (reflective problems)
    double* aa_bz[AA_SLOTS] = {};
    double *d_aa_partials = nullptr, *d_aa_dots = nullptr;
+   AAState* d_aa_state = nullptr;       // device-resident bookkeeping of the accelerated iteration
+   AAState* h_aa_ring = nullptr;        // pinned: snapshots of it, read one iteration late
    int aa_slots = 0;
    double psi_scale_factor = 1.0;       // psi normalisation relative to phi (1 unless accelerated)
    double* d_stage = nullptr;           // device staging buffer of the field import / export calls
@@ -121,6 +123,10 @@ struct pampa_sn_handle {
    // staged tile kernel
    std::vector<char> class_fast;
    std::vector<TilingDev> tilings;       // shear / un-shear work lists per shared tiling
+   std::vector<int32_t*> class_mats_s;   // per class: device material maps (nullptr: not used by its kernel)
+   std::vector<uint8_t*> class_mats_c;
+   int mat_bytes = 4;                    // element size of the dataflow kernel's material rows
+   int nmat_cap = 0;                     // materials the cross-section tables were allocated for
    int nfast_classes = 0, nfast_chunks = 0;
    bool use_graph = false, graph_failed = false;
    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // one per parity of the alternating boundary buffers
@@ -204,14 +210,16 @@ int dev_upload(pampa_sn_handle* h, T** p, const std::vector<T>& v) {
 
 int dt_template(int nd) { return nd; }      // one instantiation per chunk size 1..DT_MAX
 
-int upload_xs(pampa_sn_handle* h, const pampa_sn_xs* xs, bool first) {
+int upload_xs(pampa_sn_handle* h, const pampa_sn_xs* xs, bool first, bool allow_resize = false) {
    const int G = xs->num_groups, nm = xs->num_materials;
-   if (!first && (G != h->G || nm != h->nmat)) SN_FAIL(h, "cross-section table shape changed");
+   if (!first && (G != h->G || (nm != h->nmat && !allow_resize))) SN_FAIL(h, "cross-section table shape changed");
    const int64_t n = (int64_t)nm * G;
-   if (first) {
+   if (first || nm > h->nmat_cap) {      // (the old tables of a grown set stay allocated until the handle goes)
       if (dev_alloc(h, &h->d_sig_t, n) || dev_alloc(h, &h->d_sig_s, n * G) || dev_alloc(h, &h->d_chi, n) ||
           dev_alloc(h, &h->d_nusf, n) || dev_alloc(h, &h->d_kapsf, n)) return 1;
+      h->nmat_cap = nm;
    }
+   h->nmat = nm;
    SN_CUDA(h, cudaMemcpy(h->d_sig_t, xs->sigma_total, n * sizeof(double), cudaMemcpyHostToDevice));
    SN_CUDA(h, cudaMemcpy(h->d_sig_s, xs->sigma_scattering, n * G * sizeof(double), cudaMemcpyHostToDevice));
    SN_CUDA(h, cudaMemcpy(h->d_chi, xs->chi_effective, n * sizeof(double), cudaMemcpyHostToDevice));
@@ -220,6 +228,45 @@ int upload_xs(pampa_sn_handle* h, const pampa_sn_xs* xs, bool first) {
    h->h_beta.assign(nm, 0.0);
    if (xs->beta_total) h->h_beta.assign(xs->beta_total, xs->beta_total + nm);
    return 0;
+}
+
+// material map in the padded base numbering [nz][Sb] (-1 in holes)
+std::vector<int32_t> base_material_map(const Plan& pl, const int32_t* materials) {
+   std::vector<int32_t> mats((size_t)pl.nz * pl.Sb, -1);
+   for (int k = 0; k < pl.nz; k++)
+      for (int c = 0; c < pl.nxy; c++) mats[(size_t)k * pl.Sb + pl.slot_of_xy[c]] = materials[(size_t)k * pl.nxy + c];
+   return mats;
+}
+// ... in a class's (patch, pipeline step, lane) order (generic and tile kernels)
+std::vector<int32_t> class_step_map(const Plan& pl, const ClassPlan& cp, const std::vector<int32_t>& mats) {
+   const int nz = pl.nz;
+   std::vector<int32_t> ms((size_t)cp.npatch * cp.nsteps * PS, -1);
+   for (int64_t sl = 0; sl < cp.S; sl++) {
+      if (cp.cell_of[sl] < 0) continue;
+      const int64_t p = sl / PS, lane = sl % PS;
+      for (int kp = 0; kp < nz; kp++) {
+         const int k = cp.zdir >= 0 ? kp : nz - 1 - kp;
+         ms[((size_t)p * cp.nsteps + kp + cp.lvl[sl]) * PS + lane] = mats[(size_t)k * pl.Sb + cp.cell_of[sl]];
+      }
+   }
+   return ms;
+}
+// ... of the dataflow kernel, cyclic in the pipeline step: the lane at level l is at layer (step - l) mod nz of
+// some group of its block
+std::vector<uint8_t> class_cyclic_map(const Plan& pl, const ClassPlan& cp, const std::vector<int32_t>& mats, int mb) {
+   const int nz = pl.nz;
+   std::vector<uint8_t> mc((size_t)cp.npatch * nz * PS * mb, 0);
+   for (int64_t sl = 0; sl < cp.S; sl++) {
+      if (cp.cell_of[sl] < 0) continue;
+      const int64_t p = sl / PS, lane = sl % PS;
+      for (int kp = 0; kp < nz; kp++) {
+         const int k = cp.zdir >= 0 ? kp : nz - 1 - kp;
+         const int32_t m = mats[(size_t)k * pl.Sb + cp.cell_of[sl]];
+         const size_t e = ((size_t)p * nz + (kp + cp.lvl[sl]) % nz) * PS + lane;
+         if (mb == 1) mc[e] = (uint8_t)m; else std::memcpy(&mc[e * 4], &m, 4);
+      }
+   }
+   return mc;
 }
 
 int sync_scalars(pampa_sn_handle* h) {
@@ -392,9 +439,11 @@ int reduce_sums(pampa_sn_handle* h, int rotate) {
                  pl.nz, pl.Sb, h->d_gloc, owned_only, rotate, h->d_partials, h->nblocks_reduce, h->d_sums, h->stream);
    h->launches += 2;
    if (owned_only) {
-      int r = g_nccl.AllReduce(h->d_sums, h->d_sums, 4, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
-      if (r == 0) r = g_nccl.AllReduce(h->d_sums + 4, h->d_sums + 4, 1, NCCL_FLOAT64, NCCL_MIN, h->comm, h->stream);
-      if (r != 0) return nccl_fail(h, r, "the scalar allreduce");
+      // one collective for the five scalars (four sums and a minimum): allgather, combined in rank order
+      int r = g_nccl.AllGather(h->d_sums, h->d_sums_all, 5, NCCL_FLOAT64, h->comm, h->stream);
+      if (r != 0) return nccl_fail(h, r, "the scalar allgather");
+      launch_combine_sums(h->d_sums_all, h->opts.num_ranks, h->d_sums, h->stream);
+      h->launches++;
    }
    return 0;
 }
@@ -582,13 +631,11 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
 
       // mesh arrays in the padded slot numbering
       const int64_t Sb = pl.Sb; const int nz = pl.nz;
-      std::vector<int32_t> mats((size_t)nz * Sb, -1);
+      std::vector<int32_t> mats = base_material_map(pl, mesh->materials);
       std::vector<double> area(Sb, 0.0), dz(nz, 1.0), idz(nz, 0.0);
       for (int c = 0; c < pl.nxy; c++) area[pl.slot_of_xy[c]] = mesh->xy_area[c];
-      for (int k = 0; k < nz; k++) {
+      for (int k = 0; k < nz; k++)
          if (pl.has_z) { dz[k] = mesh->dz[k]; idz[k] = 1.0 / mesh->dz[k]; }
-         for (int c = 0; c < pl.nxy; c++) mats[(size_t)k * Sb + pl.slot_of_xy[c]] = mesh->materials[(size_t)k * pl.nxy + c];
-      }
       h->uniform_dz = 1;
       for (int k = 1; k < nz; k++) if (pl.has_z && mesh->dz[k] != mesh->dz[0]) h->uniform_dz = 0;
       if (dev_upload(h, &h->d_slot_of_xy, pl.slot_of_xy) || dev_upload(h, &h->d_mats, mats) ||
@@ -704,6 +751,9 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       std::vector<std::array<int, 2>> fast_chunk_count(pl.tilings.size(), std::array<int, 2>{0, 0});
       std::vector<std::array<int, 2>> fast_class_count(pl.tilings.size(), std::array<int, 2>{0, 0});
       h->d_pos_of.assign(pl.classes.size(), nullptr);
+      h->class_mats_s.assign(pl.classes.size(), nullptr);
+      h->class_mats_c.assign(pl.classes.size(), nullptr);
+      h->mat_bytes = h->nmat <= 256 ? 1 : 4;
       for (size_t ci = 0; ci < pl.classes.size(); ci++) {
          const ClassPlan& cp = pl.classes[ci];
          ClassDev& cd = cdev[ci];
@@ -725,19 +775,10 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          }
          cd.mats_s = nullptr;
          if (!(use_flow && h->class_fast[ci])) {
-            // material map in the class's (patch, pipeline step, lane) order (generic and tile kernels)
-            std::vector<int32_t> ms((size_t)cp.npatch * cp.nsteps * PS, -1);
-            for (int64_t sl = 0; sl < cp.S; sl++) {
-               if (cp.cell_of[sl] < 0) continue;
-               const int64_t p = sl / PS, lane = sl % PS;
-               for (int kp = 0; kp < nz; kp++) {
-                  const int k = cp.zdir >= 0 ? kp : nz - 1 - kp;
-                  ms[((size_t)p * cp.nsteps + kp + cp.lvl[sl]) * PS + lane] = mats[(size_t)k * Sb + cp.cell_of[sl]];
-               }
-            }
             int32_t* d_ms;
-            if (dev_upload(h, &d_ms, ms)) return 1;
+            if (dev_upload(h, &d_ms, class_step_map(pl, cp, mats))) return 1;
             cd.mats_s = d_ms;
+            h->class_mats_s[ci] = d_ms;
          }
          int32_t *d_cell_of, *d_patch_nlev, *d_in_src, *d_rout, *d_ls_of = nullptr;
          uint16_t* d_lvl; Vec2 *d_out_vec, *d_in_vec;
@@ -759,24 +800,12 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
             if (dev_alloc(h, &d_qs, nq)) return 1;
             SN_CUDA(h, cudaMemsetAsync(d_qs, 0, (size_t)nq * sizeof(double), h->stream));
             cd.q_sheared = d_qs;
-            // material map of the dataflow kernel, cyclic in the pipeline step: the lane at level l
-            // is at layer (step - l) mod nz of some group of its block
-            const int mb = h->nmat <= 256 ? 1 : 4;
-            std::vector<uint8_t> mc((size_t)cp.npatch * nz * PS * mb, 0);
-            for (int64_t sl = 0; sl < cp.S; sl++) {
-               if (cp.cell_of[sl] < 0) continue;
-               const int64_t p = sl / PS, lane = sl % PS;
-               for (int kp = 0; kp < nz; kp++) {
-                  const int k = cp.zdir >= 0 ? kp : nz - 1 - kp;
-                  const int32_t m = mats[(size_t)k * Sb + cp.cell_of[sl]];
-                  const size_t e = ((size_t)p * nz + (kp + cp.lvl[sl]) % nz) * PS + lane;
-                  if (mb == 1) mc[e] = (uint8_t)m; else std::memcpy(&mc[e * 4], &m, 4);
-               }
-            }
+            const int mb = h->mat_bytes;
             uint8_t* d_mc;
-            if (dev_upload(h, &d_mc, mc)) return 1;
+            if (dev_upload(h, &d_mc, class_cyclic_map(pl, cp, mats, mb))) return 1;
             cd.mat_bytes = mb;
             cd.mats_c = d_mc;
+            h->class_mats_c[ci] = d_mc;
          }
          cd.cell_of = d_cell_of; cd.lvl = d_lvl; cd.patch_nlev = d_patch_nlev;
          cd.out_vec = (const double2*)d_out_vec; cd.in_src = d_in_src; cd.in_vec = (const double2*)d_in_vec;
@@ -917,7 +946,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       // reduction scratch and iteration state
       h->nblocks_reduce = (int)std::min<int64_t>(((int64_t)nz * Sb + 255) / 256, 148 * 8);
       if (dev_alloc(h, &h->d_partials, 5LL * h->nblocks_reduce) || dev_alloc(h, &h->d_sc, 1) ||
-          dev_alloc(h, &h->d_sums, 8)) return 1;
+          dev_alloc(h, &h->d_sums, 8) || dev_alloc(h, &h->d_sums_all, 5LL * std::max(1, h->opts.num_ranks))) return 1;
       ReduceScalars sc0{}; sc0.keff = 1.0;
       SN_CUDA(h, cudaMemcpyAsync(h->d_sc, &sc0, sizeof(sc0), cudaMemcpyHostToDevice, h->stream));
       SN_CUDA(h, cudaMemsetAsync(h->d_phi, 0, (size_t)nphi * sizeof(double), h->stream));
@@ -942,6 +971,7 @@ int pampa_sn_destroy(pampa_sn_handle* h) {
    if (h->stream) cudaStreamSynchronize(h->stream);
    for (void* p : h->allocs) cudaFree(p);
    if (h->d_stage) cudaFree(h->d_stage);
+   if (h->h_aa_ring) cudaFreeHost(h->h_aa_ring);
    for (int i = 0; i < pampa_sn_handle::NSTREAMS; i++) {
       if (h->cls_stream[i]) { cudaStreamSynchronize(h->cls_stream[i]); cudaStreamDestroy(h->cls_stream[i]); }
       if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
@@ -959,6 +989,37 @@ int pampa_sn_update_xs(pampa_sn_handle* h, const pampa_sn_xs* xs) {
    SN_CUDA(h, cudaSetDevice(h->device));
    SN_CUDA(h, cudaStreamSynchronize(h->stream));
    return upload_xs(h, xs, false);
+}
+
+// New cross-section tables together with a new cell -> table-row map (temperature feedback changes which
+// (material, temperature) pair a cell uses): the material maps of every kernel are rebuilt in place.  Fails
+// when the new number of rows does not fit what the handle was planned for -- the caller then re-creates it.
+int pampa_sn_update_materials(pampa_sn_handle* h, const pampa_sn_xs* xs, const int32_t* materials) {
+   SN_CUDA(h, cudaSetDevice(h->device));
+   const Plan& pl = h->plan;
+   const int nm = xs->num_materials;
+   if (xs->num_groups != h->G) SN_FAIL(h, "cross-section table shape changed");
+   for (int64_t i = 0; i < (int64_t)pl.nz * pl.nxy; i++)
+      if (materials[i] < 0 || materials[i] >= nm) SN_FAIL(h, "wrong material index");
+   bool any_fast = false;
+   for (char f : h->class_fast) any_fast |= f != 0;
+   if ((h->mat_bytes == 1 && nm > 256) || (any_fast && ((int64_t)h->gm * nm > 2048 || nm > 4096)))
+      SN_FAIL(h, "the new material table does not fit the sweep plan of this handle: re-create it");
+   SN_CUDA(h, cudaStreamSynchronize(h->stream));
+   if (upload_xs(h, xs, false, true)) return 1;
+   const std::vector<int32_t> mats = base_material_map(pl, materials);
+   SN_CUDA(h, cudaMemcpy(h->d_mats, mats.data(), mats.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+   for (size_t ci = 0; ci < pl.classes.size(); ci++) {
+      if (h->class_mats_s[ci]) {
+         const std::vector<int32_t> ms = class_step_map(pl, pl.classes[ci], mats);
+         SN_CUDA(h, cudaMemcpy(h->class_mats_s[ci], ms.data(), ms.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      }
+      if (h->class_mats_c[ci]) {
+         const std::vector<uint8_t> mc = class_cyclic_map(pl, pl.classes[ci], mats, h->mat_bytes);
+         SN_CUDA(h, cudaMemcpy(h->class_mats_c[ci], mc.data(), mc.size(), cudaMemcpyHostToDevice));
+      }
+   }
+   return 0;
 }
 
 int pampa_sn_source(pampa_sn_handle* h, double keff) {
@@ -1045,36 +1106,6 @@ int pampa_sn_iterate_timed(pampa_sn_handle* h, int32_t iterations, double* keff,
    return check_async(h, "the source iteration");
 }
 
-// Solve min ||sum_j alpha_j f_j|| subject to sum alpha = 1 over the `n` history slots in `idx`
-// (Gram matrix M of the residuals); false when the system is too ill-conditioned.
-static bool aa_weights(const double M[AA_SLOTS][AA_SLOTS], const int* idx, int n, double* alpha) {
-   double A[AA_SLOTS][AA_SLOTS + 1];
-   double dmax = 0.0;
-   for (int i = 0; i < n; i++) dmax = std::max(dmax, M[idx[i]][idx[i]]);
-   if (!(dmax > 0.0)) return false;
-   for (int i = 0; i < n; i++) {
-      for (int j = 0; j < n; j++) A[i][j] = M[idx[i]][idx[j]] / dmax + (i == j ? 1.0e-13 : 0.0);
-      A[i][n] = 1.0;
-   }
-   for (int c = 0; c < n; c++) {                        // Gaussian elimination with partial pivoting
-      int p = c;
-      for (int r = c + 1; r < n; r++) if (std::fabs(A[r][c]) > std::fabs(A[p][c])) p = r;
-      if (std::fabs(A[p][c]) < 1.0e-300) return false;
-      for (int j = 0; j <= n; j++) std::swap(A[c][j], A[p][j]);
-      for (int r = 0; r < n; r++) {
-         if (r == c) continue;
-         const double m = A[r][c] / A[c][c];
-         for (int j = c; j <= n; j++) A[r][j] -= m * A[c][j];
-      }
-   }
-   double sum = 0.0;
-   for (int i = 0; i < n; i++) { alpha[i] = A[i][n] / A[i][i]; sum += alpha[i]; }
-   if (!(std::fabs(sum) > 1.0e-300)) return false;
-   double amax = 0.0;
-   for (int i = 0; i < n; i++) { alpha[i] /= sum; amax = std::max(amax, std::fabs(alpha[i])); }
-   return amax == amax && amax < 1.0e4;
-}
-
 int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_t max_it, double power,
                         double* keff, int32_t* iterations) {
    SN_CUDA(h, cudaSetDevice(h->device));
@@ -1103,96 +1134,85 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
       }
       power_integral = h->sc.power; min_phi = h->sc.min_phi;
    } else {
-      // Anderson-accelerated fixed-point iteration on x = phi (unit production) and k
+      // Anderson-accelerated fixed-point iteration on x = phi (constant production) and k.  All the bookkeeping
+      // (Gram matrix, window, weights, k) is in the device-resident AAState: the host enqueues iteration after
+      // iteration and reads the convergence flag of iteration i while iteration i + 1 is already in the queue, so
+      // the device never waits for the host (one iteration may run past convergence; it is a valid iterate).
       const int slots = depth + 1;
       if (h->aa_slots < slots) {
          for (int j = h->aa_slots; j < slots; j++)
             if (dev_alloc(h, &h->aa_f[j], nphi) || dev_alloc(h, &h->aa_g[j], nphi) ||
                 dev_alloc(h, &h->aa_b[j], h->bnd_count) || dev_alloc(h, &h->aa_bz[j], h->bndz_count)) return 1;
          if (!h->d_aa_partials && (dev_alloc(h, &h->d_aa_partials, (int64_t)AA_SLOTS * h->nblocks_reduce) ||
-                                   dev_alloc(h, &h->d_aa_dots, AA_SLOTS))) return 1;
+                                   dev_alloc(h, &h->d_aa_dots, AA_SLOTS) || dev_alloc(h, &h->d_aa_state, 1))) return 1;
          h->aa_slots = slots;
       }
+      if (!h->h_aa_ring) SN_CUDA(h, cudaHostAlloc((void**)&h->h_aa_ring, 2 * sizeof(AAState), cudaHostAllocDefault));
       const int owned_only = (h->comm && h->group_gather) ? 1 : 0;
-      double M[AA_SLOTS][AA_SLOTS] = {};
-      double kg[AA_SLOTS] = {};
-      int age[AA_SLOTS];                                // iteration that filled each slot (-1: empty)
-      for (int j = 0; j < AA_SLOTS; j++) age[j] = -1;
       if (sync_scalars(h)) return 1;
-      double kn = h->sc.keff;
-      const double prod_x = h->sc.production;           // production of the iterate, kept constant
-      if (!(prod_x > 0.0)) SN_FAIL(h, "zero fission production: no fissile material in the mesh");
-      double best = 1.0e300;
-      int cur = 0;
-      // the first iterations only settle k and the gross flux shape: mixing them in slows the
-      // acceleration down, so the history starts after `aa_start` plain steps
-      const char* env_start = std::getenv("PAMPA_SN_AA_START");
-      const int aa_start = env_start ? std::atoi(env_start) : 0;   // measured: no benefit at depth 7
-      while (it < max_it) {
-         if (do_source(h) || do_sweep(h) || reduce_sums(h, 0)) return 1;
+      if (!(h->sc.production > 0.0)) SN_FAIL(h, "zero fission production: no fissile material in the mesh");
+      AAState st0;
+      std::memset(&st0, 0, sizeof(st0));
+      for (int j = 0; j < AA_SLOTS; j++) st0.age[j] = -1;
+      st0.kn = h->sc.keff; st0.prod_x = h->sc.production; st0.best = 1.0e300; st0.inv = 1.0;
+      st0.tol_k = tol_k; st0.tol_phi = tol_phi; st0.slots = slots;
+      // the first iterations only settle k and the gross flux shape: mixing them in could slow the acceleration
+      // down, so the history may start after `aa_start` plain steps (measured: no benefit at depth 7, default 0)
+      { const char* e = std::getenv("PAMPA_SN_AA_START"); st0.aa_start = e ? std::atoi(e) : 0; }
+      SN_CUDA(h, cudaMemcpyAsync(h->d_aa_state, &st0, sizeof(st0), cudaMemcpyHostToDevice, h->stream));
+      SN_CUDA(h, cudaStreamSynchronize(h->stream));     // st0 is on the stack
+      double* fptr[AA_SLOTS]; double* gptr[AA_SLOTS]; double* bptr[AA_SLOTS]; double* bzptr[AA_SLOTS];
+      for (int j = 0; j < AA_SLOTS; j++) {
+         fptr[j] = h->aa_f[j < slots ? j : 0]; gptr[j] = h->aa_g[j < slots ? j : 0];
+         bptr[j] = h->aa_b[j < slots ? j : 0]; bzptr[j] = h->aa_bz[j < slots ? j : 0];
+      }
+      cudaEvent_t ev[2] = {nullptr, nullptr};
+      for (auto& e : ev) SN_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      int rc = 0;
+      bool failed = false;
+      while (it < max_it && !rc) {
+         if ((rc = do_source(h) || do_sweep(h) || reduce_sums(h, 0))) break;
          it++;
-         if (it == aa_start) { for (int j = 0; j < slots; j++) if (j != cur) age[j] = -1; best = 1.0e300; }
-         double sums[5];
-         SN_CUDA(h, cudaMemcpyAsync(sums, h->d_sums, sizeof(sums), cudaMemcpyDeviceToHost, h->stream));
-         SN_CUDA(h, cudaStreamSynchronize(h->stream));
-         if (!(sums[0] == sums[0]) || !(sums[0] > 0.0)) SN_FAIL(h, "the power iteration diverged");
-         const double inv = prod_x / sums[0];
-         kg[cur] = kn * sums[0] / prod_x;
-         age[cur] = it;
-         int nh = 0;
-         for (int j = 0; j < slots; j++) nh += age[j] >= 0;
-         // history slots are packed in [0, slots): the kernel visits every slot < slots that is filled
-         double* fptr[AA_SLOTS]; double* gptr[AA_SLOTS];
-         for (int j = 0; j < AA_SLOTS; j++) { fptr[j] = h->aa_f[j < slots ? j : 0]; gptr[j] = h->aa_g[j < slots ? j : 0]; }
-         int nvisit = 0;
-         for (int j = 0; j < slots; j++) if (age[j] >= 0) nvisit = j + 1;
-         launch_aa_store(h->d_phi, h->d_phi_new, h->d_mats, h->d_gloc, owned_only, h->G, nslab, inv, fptr, gptr, cur,
-                         nvisit, h->d_aa_partials, h->nblocks_reduce, h->d_aa_dots, h->stream);
-         h->launches += 2;
+         launch_aa_begin(h->d_aa_state, h->d_sums, h->stream);
+         launch_aa_store(h->d_phi, h->d_phi_new, h->d_gloc, owned_only, h->G, nslab, fptr, gptr, h->d_aa_state,
+                         h->d_aa_partials, h->nblocks_reduce, h->d_aa_dots, h->stream);
+         h->launches += 3;
          // the lagged boundary fluxes are part of the fixed-point state: same normalisation, same mixing
-         launch_scale_copy(h->aa_b[cur], h->d_bnd[h->bnd_cur], inv, h->bnd_count, h->stream);
-         launch_scale_copy(h->aa_bz[cur], h->d_bndz[h->bnd_cur], inv, h->bndz_count, h->stream);
+         launch_scale_copy_slot(bptr, h->d_bnd[h->bnd_cur], h->d_aa_state, h->bnd_count, h->stream);
+         launch_scale_copy_slot(bzptr, h->d_bndz[h->bnd_cur], h->d_aa_state, h->bndz_count, h->stream);
          if (owned_only) {
             int r = g_nccl.AllReduce(h->d_aa_dots, h->d_aa_dots, AA_SLOTS, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
-            if (r != 0) return nccl_fail(h, r, "the Anderson allreduce");
+            if (r != 0) { rc = nccl_fail(h, r, "the Anderson allreduce"); break; }
          }
-         double dots[AA_SLOTS];
-         SN_CUDA(h, cudaMemcpyAsync(dots, h->d_aa_dots, sizeof(dots), cudaMemcpyDeviceToHost, h->stream));
-         SN_CUDA(h, cudaStreamSynchronize(h->stream));
-         for (int j = 0; j < nvisit; j++) M[cur][j] = M[j][cur] = dots[j];
-         const double res = std::sqrt(dots[cur] / (sums[3] * inv * inv));
-         const double dk = kg[cur] - kn;
-         power_integral = sums[1] * inv; min_phi = sums[4] * inv;
-         h->psi_scale_factor = inv;
-         double alpha[AA_SLOTS] = {};
-         double mix[AA_SLOTS] = {};
-         if (it > 1 && std::fabs(dk) < tol_k && res < tol_phi) {
-            converged = true;
-            mix[cur] = 1.0; kn = kg[cur];
-         } else {
-            if (res > 10.0 * best) { for (int j = 0; j < slots; j++) if (j != cur) age[j] = -1; }   // restart
-            best = std::min(best, res);
-            // window = filled slots, newest first; shrink it until the weights are well conditioned
-            int idx[AA_SLOTS], n = 0;
-            for (int a = 0; a < slots; a++) { int j = (cur - a + slots) % slots; if (age[j] >= 0) idx[n++] = j; }
-            if (it < aa_start) n = 1;                     // plain step
-            while (n > 1 && !aa_weights(M, idx, n, alpha)) n--;
-            if (n <= 1) { n = 1; alpha[0] = 1.0; }
-            kn = 0.0;
-            for (int a = 0; a < n; a++) { mix[idx[a]] = alpha[a]; kn += alpha[a] * kg[idx[a]]; }
+         launch_aa_solve(h->d_aa_state, h->d_aa_dots, h->d_sc, h->stream);
+         launch_aa_mix(h->d_phi, h->d_mats, h->d_gloc, owned_only, h->G, nslab, gptr, h->d_aa_state, h->nblocks_reduce,
+                       h->stream);
+         h->launches += 2;
+         if (h->bnd_count > 0) launch_vec_mix(h->d_bnd[h->bnd_cur], bptr, h->d_aa_state, h->bnd_count, h->stream);
+         if (h->bndz_count > 0) launch_vec_mix(h->d_bndz[h->bnd_cur], bzptr, h->d_aa_state, h->bndz_count, h->stream);
+         if ((rc = gather_phi(h))) break;
+         // snapshot of the state after this iteration; looked at one iteration later
+         cudaMemcpyAsync(&h->h_aa_ring[it & 1], h->d_aa_state, sizeof(AAState), cudaMemcpyDeviceToHost, h->stream);
+         cudaEventRecord(ev[it & 1], h->stream);
+         if (it >= 2) {
+            cudaEventSynchronize(ev[(it - 1) & 1]);
+            const AAState& prev = h->h_aa_ring[(it - 1) & 1];
+            if (prev.failed) { failed = true; break; }
+            if (prev.converged) { converged = true; break; }
          }
-         launch_aa_mix(h->d_phi, h->d_mats, h->d_gloc, owned_only, h->G, nslab, fptr, gptr, mix, slots,
-                       h->nblocks_reduce, h->stream);
-         h->launches++;
-         if (h->bnd_count > 0) launch_vec_mix(h->d_bnd[h->bnd_cur], h->aa_b, mix, slots, h->bnd_count, h->stream);
-         if (h->bndz_count > 0) launch_vec_mix(h->d_bndz[h->bnd_cur], h->aa_bz, mix, slots, h->bndz_count, h->stream);
-         SN_CUDA(h, cudaMemcpyAsync(&h->d_sc->keff, &kn, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-         if (gather_phi(h)) return 1;
-         if (converged) break;
-         cur = (cur + 1) % slots;
       }
-      SN_CUDA(h, cudaStreamSynchronize(h->stream));
-      h->sc.keff = kn;
+      cudaError_t es = cudaStreamSynchronize(h->stream);
+      for (auto& e : ev) if (e) cudaEventDestroy(e);
+      if (rc) return 1;
+      if (es != cudaSuccess) SN_FAIL(h, std::string("CUDA error in the k-eff iteration: ") + cudaGetErrorString(es));
+      if (it > 0) {
+         const AAState& last = h->h_aa_ring[it & 1];     // the state the device fields are in
+         if (last.failed || failed) SN_FAIL(h, "the power iteration diverged");
+         converged = converged || last.converged != 0;
+         h->sc.keff = last.kn;
+         h->psi_scale_factor = last.inv;
+         power_integral = last.power_integral; min_phi = last.min_phi;
+      }
    }
    if (check_async(h, "the k-eff iteration")) return 1;
    h->keff = h->sc.keff;
@@ -1206,12 +1226,26 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
    return 0;
 }
 
+// Partitioned fields (opts.partition_fields in a sharded run): this rank's window of cells
+static void cell_window(const pampa_sn_handle* h, int64_t* i0, int64_t* ni, int64_t* per_rank) {
+   const int64_t N = (int64_t)h->plan.nxy * h->plan.nz;
+   if (h->opts.partition_fields && h->opts.num_ranks > 1) {
+      const int64_t c = (N + h->opts.num_ranks - 1) / h->opts.num_ranks;
+      *i0 = std::min(N, c * h->opts.rank);
+      *ni = std::min(N, c * (h->opts.rank + 1)) - *i0;
+      if (per_rank) *per_rank = c;
+   } else { *i0 = 0; *ni = N; if (per_rank) *per_rank = N; }
+}
+
 int64_t pampa_sn_field_size(const pampa_sn_handle* h, const char* name) {
    const int64_t N = (int64_t)h->plan.nxy * h->plan.nz;
    const std::string s(name);
-   if (s == "scalar-flux" || s == "flux-moments") return N * h->G;
+   int64_t i0, ni;
+   cell_window(h, &i0, &ni, nullptr);
+   if (s == "scalar-flux" || s == "flux-moments") return ni * h->G;
    if (s == "angular-flux") return N * h->G * h->M;
-   if (s == "power" || s == "production-rate" || s == "temperature" || s == "delayed-source") return N;
+   if (s == "power" || s == "production-rate") return ni;
+   if (s == "temperature" || s == "delayed-source") return N;
    if (s == "keff" || s == "angular-flux-min") return 1;
    return -1;
 }
@@ -1246,7 +1280,11 @@ int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
       if (s == "delayed-source" && h->solved) {
          // S_i = beta * P_i (reference src/NeutronicSolver.cxx:103)
          std::vector<double> P(N);
-         if (pampa_sn_get(h, "production-rate", P.data())) return 1;
+         const int32_t part = h->opts.partition_fields;
+         h->opts.partition_fields = 0;                   // whole field
+         const int rcp = pampa_sn_get(h, "production-rate", P.data());
+         h->opts.partition_fields = part;
+         if (rcp) return 1;
          std::vector<int32_t> mats((size_t)pl.nz * pl.Sb);
          SN_CUDA(h, cudaMemcpy(mats.data(), h->d_mats, mats.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
          for (int64_t i = 0; i < N; i++) {
@@ -1272,16 +1310,18 @@ int pampa_sn_get(pampa_sn_handle* h, const char* name, double* out) {
       temp = true;
    }
    int rc = 0;
+   int64_t i0, ni;
+   cell_window(h, &i0, &ni, nullptr);
    if (s == "scalar-flux") {
-      launch_export_phi(h->d_phi, h->d_slot_of_xy, h->scale, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
+      launch_export_phi(h->d_phi, h->d_slot_of_xy, h->scale, h->G, pl.nz, pl.nxy, pl.Sb, i0, ni, d_out, h->stream);
    } else if (s == "flux-moments") {      // raw device moments sum_m w_m psi, no normalisation
-      launch_export_phi(h->d_phi, h->d_slot_of_xy, 1.0, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
+      launch_export_phi(h->d_phi, h->d_slot_of_xy, 1.0, h->G, pl.nz, pl.nxy, pl.Sb, i0, ni, d_out, h->stream);
    } else if (s == "power") {
       launch_export_cell(h->d_phi, h->d_slot_of_xy, h->d_mats, h->d_kapsf, h->d_area, h->d_dz, pl.has_z,
-                         h->scale, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
+                         h->scale, h->G, pl.nz, pl.nxy, pl.Sb, i0, ni, d_out, h->stream);
    } else if (s == "production-rate") {
       launch_export_cell(h->d_phi, h->d_slot_of_xy, h->d_mats, h->d_nusf, h->d_area, h->d_dz, pl.has_z,
-                         h->scale / h->keff, h->G, pl.nz, pl.nxy, pl.Sb, d_out, h->stream);
+                         h->scale / h->keff, h->G, pl.nz, pl.nxy, pl.Sb, i0, ni, d_out, h->stream);
    } else {   // angular-flux
       cudaMemsetAsync(d_out, 0, (size_t)count * sizeof(double), h->stream);
       double* d_min = nullptr;
@@ -1324,7 +1364,10 @@ int pampa_sn_set(pampa_sn_handle* h, const char* name, const double* in) {
    }
    if (s == "flux-moments") {      // iteration state / initial guess, layout [i][g]
       SN_CUDA(h, cudaSetDevice(h->device));
-      const int64_t count = N * h->G;
+      int64_t i0, ni, per_rank;
+      cell_window(h, &i0, &ni, &per_rank);
+      const bool part = h->opts.partition_fields && h->opts.num_ranks > 1;
+      const int64_t count = part ? per_rank * h->opts.num_ranks * h->G : N * h->G;
       if (count > h->stage_count) {
          if (h->d_stage) cudaFree(h->d_stage);
          h->d_stage = nullptr; h->stage_count = 0;
@@ -1332,7 +1375,15 @@ int pampa_sn_set(pampa_sn_handle* h, const char* name, const double* in) {
          h->stage_count = count;
       }
       double* d_in = h->d_stage;
-      cudaMemcpyAsync(d_in, in, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+      if (part) {
+         // this rank uploads its window of cells; the windows are exchanged on the device (in-place allgather)
+         if (!h->comm) SN_FAIL(h, "partitioned fields need the communicator (pampa_sn_comm_init)");
+         cudaMemcpyAsync(d_in + i0 * h->G, in, (size_t)(ni * h->G) * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+         int r = g_nccl.AllGather(d_in + (int64_t)h->opts.rank * per_rank * h->G, d_in, (size_t)(per_rank * h->G), NCCL_FLOAT64,
+                                  h->comm, h->stream);
+         if (r != 0) return nccl_fail(h, r, "the field allgather");
+      } else
+         cudaMemcpyAsync(d_in, in, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->stream);
       cudaMemsetAsync(h->d_phi, 0, (size_t)h->G * h->plan.nz * h->plan.Sb * sizeof(double), h->stream);
       launch_import_phi(h->d_phi_new, h->d_slot_of_xy, h->G, h->plan.nz, h->plan.nxy, h->plan.Sb, d_in, h->stream);
       if (do_reduce(h, 0)) return 1;

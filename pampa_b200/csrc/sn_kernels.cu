@@ -1546,6 +1546,22 @@ __global__ void sn_reduce_final_kernel(const double* __restrict__ partials, int 
    if (threadIdx.x < 5) sums[threadIdx.x] = sh[threadIdx.x][0];
 }
 
+// Group-sharded runs: the five sums of every rank arrive with ONE allgather ([rank][5]); combined here
+// (four sums and a minimum) in rank order, so every rank gets the same bits.
+__global__ void sn_combine_sums_kernel(const double* __restrict__ all, int nranks, double* __restrict__ sums) {
+   if (threadIdx.x < 5) {
+      double v = all[threadIdx.x];
+      for (int r = 1; r < nranks; r++) {
+         const double x = all[r * 5 + threadIdx.x];
+         v = threadIdx.x < 4 ? v + x : fmin(v, x);
+      }
+      sums[threadIdx.x] = v;
+   }
+}
+void launch_combine_sums(const double* all, int nranks, double* sums, cudaStream_t st) {
+   sn_combine_sums_kernel<<<1, 32, 0, st>>>(all, nranks, sums);
+}
+
 // Power-iteration update k <- k * P_new / P_old.
 __global__ void sn_update_k_kernel(const double* __restrict__ sums, ReduceScalars* sc, int update_k) {
    const double pnew = sums[0];
@@ -1576,18 +1592,41 @@ void launch_update_k(const double* sums, ReduceScalars* sc, int update_k, cudaSt
 
 // ------------------------------------------------------------------------------------ Anderson
 // Anderson acceleration of the fixed-point map x -> G(x) = A(k) x / P(A(k) x) (one source iteration,
-// normalised to unit production).  History slot `cur` receives g = G(x) and the residual f = g - x;
-// the dot products of the new residual with every stored residual go to partials.
+// normalised to constant production).  History slot `cur` receives g = G(x) and the residual f = g - x;
+// the dot products of the new residual with every stored residual go to partials.  Slot, window and weights
+// live in the device-resident AAState: the host only enqueues.
 constexpr int AA_MAX = 8;
 struct AAHist { double* f[AA_MAX]; double* g[AA_MAX]; };
+
+// Start of an accelerated iteration, after the sweep and its block reduction (sums = {production, power,
+// ||dphi||^2, ||phi_new||^2, min phi} of the sweep result): normalisation and eigenvalue estimate of slot `cur`.
+__global__ void sn_aa_begin_kernel(AAState* __restrict__ s, const double* __restrict__ sums) {
+   if (threadIdx.x != 0) return;
+   s->it++;
+   if (s->it == s->aa_start) { for (int j = 0; j < s->slots; j++) if (j != s->cur) s->age[j] = -1; s->best = 1.0e300; }
+   const double prod = sums[0];
+   if (!(prod == prod) || !(prod > 0.0)) { s->failed = 1; s->inv = 0.0; return; }
+   s->inv = s->prod_x / prod;
+   s->kg[s->cur] = s->kn * prod / s->prod_x;
+   s->age[s->cur] = s->it;
+   int nv = 0;
+   for (int j = 0; j < s->slots; j++) if (s->age[j] >= 0) nv = j + 1;
+   s->nvisit = nv;
+   s->power_integral = sums[1] * s->inv;
+   s->min_phi = sums[4] * s->inv;
+   s->phi2 = sums[3];
+}
+void launch_aa_begin(AAState* st_dev, const double* sums, cudaStream_t st) { sn_aa_begin_kernel<<<1, 32, 0, st>>>(st_dev, sums); }
 
 // Streams the flat [G][n] arrays two doubles per thread with every load of a step issued before its stores
 // (9 x 16 B in flight per thread at full depth): bandwidth-bound, ~12 x 0.645 GB per call at C4.  Holes need no
 // test: phi and phi_new are zero there, so g, f and the dot products get zeros.
 __global__ void __launch_bounds__(256)
 sn_aa_store_kernel(const double* __restrict__ phi, double* __restrict__ phi_new,
-                   const int32_t* __restrict__ gloc, int owned_only, int G, int64_t n, double inv_prod,
-                   AAHist hist, int cur, int nhist, double* __restrict__ partials) {
+                   const int32_t* __restrict__ gloc, int owned_only, int G, int64_t n,
+                   AAHist hist, const AAState* __restrict__ state, double* __restrict__ partials) {
+   const int cur = state->cur, nhist = state->nvisit;
+   const double inv_prod = state->inv;
    double dots[AA_MAX];
 #pragma unroll
    for (int j = 0; j < AA_MAX; j++) dots[j] = 0.0;
@@ -1625,16 +1664,17 @@ sn_aa_store_kernel(const double* __restrict__ phi, double* __restrict__ phi_new,
       if (lane == 0) sh[j][warp] = v;
    }
    __syncthreads();
-   if ((int)threadIdx.x < nhist) {
+   if ((int)threadIdx.x < AA_MAX) {
       double v = 0.0;
       for (int w = 0; w < 8; w++) v += sh[threadIdx.x][w];
       partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
    }
 }
 
-__global__ void sn_aa_dots_final_kernel(const double* __restrict__ partials, int nblocks, int nhist, double* out) {
+// dots[0 .. AA_MAX): deterministic sum of the block partials (entries of empty slots are zero)
+__global__ void sn_aa_dots_final_kernel(const double* __restrict__ partials, int nblocks, double* out) {
    __shared__ double sh[256];
-   for (int j = 0; j < nhist; j++) {
+   for (int j = 0; j < AA_MAX; j++) {
       double v = 0.0;
       for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += partials[(size_t)j * nblocks + b];
       sh[threadIdx.x] = v;
@@ -1648,12 +1688,81 @@ __global__ void sn_aa_dots_final_kernel(const double* __restrict__ partials, int
    }
 }
 
-struct AACoef { double alpha[AA_MAX]; };
+// min ||sum_j alpha_j f_j|| subject to sum alpha = 1 over the n history slots in idx (Gram matrix M of the
+// residuals); false when the system is too ill-conditioned
+__device__ bool aa_weights(const double (*M)[AA_SLOTS], const int* idx, int n, double* alpha) {
+   double A[AA_SLOTS][AA_SLOTS + 1];
+   double dmax = 0.0;
+   for (int i = 0; i < n; i++) dmax = fmax(dmax, M[idx[i]][idx[i]]);
+   if (!(dmax > 0.0)) return false;
+   for (int i = 0; i < n; i++) {
+      for (int j = 0; j < n; j++) A[i][j] = M[idx[i]][idx[j]] / dmax + (i == j ? 1.0e-13 : 0.0);
+      A[i][n] = 1.0;
+   }
+   for (int c = 0; c < n; c++) {                        // Gaussian elimination with partial pivoting
+      int p = c;
+      for (int r = c + 1; r < n; r++) if (fabs(A[r][c]) > fabs(A[p][c])) p = r;
+      if (fabs(A[p][c]) < 1.0e-300) return false;
+      for (int j = 0; j <= n; j++) { const double t = A[c][j]; A[c][j] = A[p][j]; A[p][j] = t; }
+      for (int r = 0; r < n; r++) {
+         if (r == c) continue;
+         const double m = A[r][c] / A[c][c];
+         for (int j = c; j <= n; j++) A[r][j] -= m * A[c][j];
+      }
+   }
+   double sum = 0.0;
+   for (int i = 0; i < n; i++) { alpha[i] = A[i][n] / A[i][i]; sum += alpha[i]; }
+   if (!(fabs(sum) > 1.0e-300)) return false;
+   double amax = 0.0;
+   for (int i = 0; i < n; i++) { alpha[i] /= sum; amax = fmax(amax, fabs(alpha[i])); }
+   return amax == amax && amax < 1.0e4;
+}
 
-// x_next = sum_j alpha_j g_j  (sum alpha = 1, so the production of x_next is 1)
+// End of an accelerated iteration: Gram row of the new residual, convergence test, restart, window and weights
+// of the next iterate, its k -- one thread, a few hundred flops.
+__global__ void sn_aa_solve_kernel(AAState* __restrict__ s, const double* __restrict__ dots, ReduceScalars* __restrict__ sc) {
+   if (threadIdx.x != 0) return;
+   const int cur = s->cur, slots = s->slots;
+   for (int j = 0; j < AA_SLOTS; j++) s->mix[j] = 0.0;
+   if (s->failed) { s->mix[cur] = 1.0; return; }
+   for (int j = 0; j < s->nvisit; j++) { s->M[cur][j] = dots[j]; s->M[j][cur] = dots[j]; }
+   const double res = sqrt(dots[cur] / (s->phi2 * s->inv * s->inv));
+   const double dk = s->kg[cur] - s->kn;
+   s->res = res; s->dk = dk;
+   if (!(res == res)) { s->failed = 1; s->mix[cur] = 1.0; return; }
+   double kn;
+   if (s->it > 1 && fabs(dk) < s->tol_k && res < s->tol_phi) {
+      s->converged = 1;
+      s->mix[cur] = 1.0; kn = s->kg[cur];
+   } else {
+      s->converged = 0;
+      if (res > 10.0 * s->best) { for (int j = 0; j < slots; j++) if (j != cur) s->age[j] = -1; }   // restart
+      s->best = fmin(s->best, res);
+      // window = filled slots, newest first; shrink it until the weights are well conditioned
+      int idx[AA_SLOTS], n = 0;
+      double alpha[AA_SLOTS];
+      for (int a = 0; a < slots; a++) { const int j = (cur - a + slots) % slots; if (s->age[j] >= 0) idx[n++] = j; }
+      if (s->it < s->aa_start) n = 1;                   // plain step
+      while (n > 1 && !aa_weights(s->M, idx, n, alpha)) n--;
+      if (n <= 1) { n = 1; alpha[0] = 1.0; }
+      kn = 0.0;
+      for (int a = 0; a < n; a++) { s->mix[idx[a]] = alpha[a]; kn += alpha[a] * s->kg[idx[a]]; }
+      s->cur = (cur + 1) % slots;
+   }
+   s->kn = kn;
+   sc->keff = kn;
+}
+void launch_aa_solve(AAState* st_dev, const double* dots, ReduceScalars* sc, cudaStream_t st) {
+   sn_aa_solve_kernel<<<1, 32, 0, st>>>(st_dev, dots, sc);
+}
+
+// x_next = sum_j alpha_j g_j  (sum alpha = 1, so the production of x_next is that of the iterates)
 __global__ void __launch_bounds__(256)
 sn_aa_mix_kernel(double* __restrict__ phi, const int32_t* __restrict__ mats, const int32_t* __restrict__ gloc,
-                 int owned_only, int G, int64_t n, AAHist hist, AACoef coef, int nhist) {
+                 int owned_only, int G, int64_t n, AAHist hist, const AAState* __restrict__ state) {
+   double alpha[AA_MAX];
+#pragma unroll
+   for (int j = 0; j < AA_MAX; j++) alpha[j] = state->mix[j];
    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
         idx += (int64_t)gridDim.x * blockDim.x) {
       if (mats[idx] < 0) continue;
@@ -1663,56 +1772,61 @@ sn_aa_mix_kernel(double* __restrict__ phi, const int32_t* __restrict__ mats, con
          double v = 0.0;
 #pragma unroll
          for (int j = 0; j < AA_MAX; j++)
-            if (j < nhist && coef.alpha[j] != 0.0) v = fma(coef.alpha[j], hist.g[j][a], v);
+            if (alpha[j] != 0.0) v = fma(alpha[j], hist.g[j][a], v);
          phi[a] = v;
       }
    }
 }
 
 // plain vector helpers for the boundary-flux part of the Anderson state
-__global__ void sn_scale_copy_kernel(double* __restrict__ dst, const double* __restrict__ src, double c, int64_t n) {
+__global__ void sn_scale_copy_slot_kernel(AAHist hist, const double* __restrict__ src, const AAState* __restrict__ state, int64_t n) {
+   double* __restrict__ dst = hist.g[0];
+#pragma unroll
+   for (int j = 1; j < AA_MAX; j++) if (j == state->cur) dst = hist.g[j];
+   const double c = state->inv;
    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
       dst[i] = c * src[i];
 }
-__global__ void sn_vec_mix_kernel(double* __restrict__ out, AAHist hist, AACoef coef, int nhist, int64_t n) {
+__global__ void sn_vec_mix_kernel(double* __restrict__ out, AAHist hist, const AAState* __restrict__ state, int64_t n) {
+   double alpha[AA_MAX];
+#pragma unroll
+   for (int j = 0; j < AA_MAX; j++) alpha[j] = state->mix[j];
    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
       double v = 0.0;
 #pragma unroll
       for (int j = 0; j < AA_MAX; j++)
-         if (j < nhist && coef.alpha[j] != 0.0) v = fma(coef.alpha[j], hist.g[j][i], v);
+         if (alpha[j] != 0.0) v = fma(alpha[j], hist.g[j][i], v);
       out[i] = v;
    }
 }
-void launch_scale_copy(double* dst, const double* src, double c, int64_t n, cudaStream_t st) {
-   if (n <= 0) return;
-   sn_scale_copy_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(dst, src, c, n);
-}
-void launch_vec_mix(double* out, double* const* hist, const double* alpha, int nhist, int64_t n, cudaStream_t st) {
+// hist[cur] = inv * src (cur and inv from the device state)
+void launch_scale_copy_slot(double* const* hist, const double* src, const AAState* st_dev, int64_t n, cudaStream_t st) {
    if (n <= 0) return;
    AAHist h{};
-   AACoef c{};
-   for (int j = 0; j < AA_MAX; j++) { h.g[j] = hist[j]; h.f[j] = nullptr; c.alpha[j] = j < nhist ? alpha[j] : 0.0; }
-   sn_vec_mix_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(out, h, c, nhist, n);
+   for (int j = 0; j < AA_MAX; j++) { h.g[j] = hist[j]; h.f[j] = nullptr; }
+   sn_scale_copy_slot_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(h, src, st_dev, n);
+}
+void launch_vec_mix(double* out, double* const* hist, const AAState* st_dev, int64_t n, cudaStream_t st) {
+   if (n <= 0) return;
+   AAHist h{};
+   for (int j = 0; j < AA_MAX; j++) { h.g[j] = hist[j]; h.f[j] = nullptr; }
+   sn_vec_mix_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(out, h, st_dev, n);
 }
 
-void launch_aa_store(const double* phi, double* phi_new, const int32_t* mats, const int32_t* gloc,
-                     int owned_only, int G, int64_t n, double inv_prod, double* const* hist_f,
-                     double* const* hist_g, int cur, int nhist, double* partials, int nblocks, double* dots,
-                     cudaStream_t st) {
+void launch_aa_store(const double* phi, double* phi_new, const int32_t* gloc, int owned_only, int G, int64_t n,
+                     double* const* hist_f, double* const* hist_g, const AAState* st_dev, double* partials,
+                     int nblocks, double* dots, cudaStream_t st) {
    AAHist h{};
    for (int j = 0; j < AA_MAX; j++) { h.f[j] = hist_f[j]; h.g[j] = hist_g[j]; }
-   (void)mats;
-   sn_aa_store_kernel<<<nblocks, 256, 0, st>>>(phi, phi_new, gloc, owned_only, G, n, inv_prod, h, cur, nhist, partials);
-   sn_aa_dots_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, nhist, dots);
+   sn_aa_store_kernel<<<nblocks, 256, 0, st>>>(phi, phi_new, gloc, owned_only, G, n, h, st_dev, partials);
+   sn_aa_dots_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, dots);
 }
 
 void launch_aa_mix(double* phi, const int32_t* mats, const int32_t* gloc, int owned_only, int G, int64_t n,
-                   double* const* hist_f, double* const* hist_g, const double* alpha, int nhist, int nblocks,
-                   cudaStream_t st) {
+                   double* const* hist_g, const AAState* st_dev, int nblocks, cudaStream_t st) {
    AAHist h{};
-   AACoef c{};
-   for (int j = 0; j < AA_MAX; j++) { h.f[j] = hist_f[j]; h.g[j] = hist_g[j]; c.alpha[j] = j < nhist ? alpha[j] : 0.0; }
-   sn_aa_mix_kernel<<<nblocks, 256, 0, st>>>(phi, mats, gloc, owned_only, G, n, h, c, nhist);
+   for (int j = 0; j < AA_MAX; j++) { h.f[j] = nullptr; h.g[j] = hist_g[j]; }
+   sn_aa_mix_kernel<<<nblocks, 256, 0, st>>>(phi, mats, gloc, owned_only, G, n, h, st_dev);
 }
 
 // ------------------------------------------------------------------------------------ LS term
@@ -1844,22 +1958,24 @@ void launch_min(const double* p, int64_t n, double* out, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------ fields
+// cells i0 .. i0 + ni - 1 of the reference numbering (the whole field, or this rank's part of a partitioned field)
 __global__ void sn_export_phi_kernel(const double* __restrict__ phi,
                                      const int32_t* __restrict__ slot_of_xy, double scale, int G,
-                                     int nz, int nxy, int64_t Sb, double* __restrict__ out) {
+                                     int nz, int nxy, int64_t Sb, int64_t i0, int64_t ni, double* __restrict__ out) {
    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   const int64_t total = (int64_t)nz * nxy * G;
+   const int64_t total = ni * G;
    if (tid >= total) return;
    const int g = (int)(tid % G);
-   const int64_t i = tid / G;
+   const int64_t i = i0 + tid / G;
    const int k = (int)(i / nxy), c = (int)(i % nxy);
    out[tid] = scale * phi[((int64_t)g * nz + k) * Sb + slot_of_xy[c]];
 }
 void launch_export_phi(const double* phi, const int32_t* slot_of_xy, double scale, int G, int nz,
-                       int nxy, int64_t Sb, double* out, cudaStream_t st) {
-   const int64_t total = (int64_t)nz * nxy * G;
+                       int nxy, int64_t Sb, int64_t i0, int64_t ni, double* out, cudaStream_t st) {
+   const int64_t total = ni * G;
+   if (total <= 0) return;
    sn_export_phi_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(phi, slot_of_xy, scale, G, nz,
-                                                                    nxy, Sb, out);
+                                                                    nxy, Sb, i0, ni, out);
 }
 
 // out[i] = scale * V_i * sum_g xs_g[mat][g] * phi[g][i]   (power, production-rate)
@@ -1869,9 +1985,10 @@ __global__ void sn_export_cell_kernel(const double* __restrict__ phi,
                                       const double* __restrict__ xs_g,
                                       const double* __restrict__ area,
                                       const double* __restrict__ dz, int has_z, double scale, int G,
-                                      int nz, int nxy, int64_t Sb, double* __restrict__ out) {
-   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= (int64_t)nz * nxy) return;
+                                      int nz, int nxy, int64_t Sb, int64_t i0, int64_t ni, double* __restrict__ out) {
+   const int64_t il = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (il >= ni) return;
+   const int64_t i = i0 + il;
    const int k = (int)(i / nxy), c = (int)(i % nxy);
    const int s = slot_of_xy[c];
    const int64_t idx = (int64_t)k * Sb + s;
@@ -1879,15 +1996,15 @@ __global__ void sn_export_cell_kernel(const double* __restrict__ phi,
    const double vol = area[s] * (has_z ? dz[k] : 1.0);
    double acc = 0.0;
    for (int g = 0; g < G; g++) acc = fma(xs_g[mat * G + g], phi[(int64_t)g * nz * Sb + idx], acc);
-   out[i] = scale * vol * acc;
+   out[il] = scale * vol * acc;
 }
 void launch_export_cell(const double* phi, const int32_t* slot_of_xy, const int32_t* mats,
                         const double* xs_g, const double* area, const double* dz, int has_z,
-                        double scale, int G, int nz, int nxy, int64_t Sb, double* out,
+                        double scale, int G, int nz, int nxy, int64_t Sb, int64_t i0, int64_t ni, double* out,
                         cudaStream_t st) {
-   const int64_t total = (int64_t)nz * nxy;
-   sn_export_cell_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(
-      phi, slot_of_xy, mats, xs_g, area, dz, has_z, scale, G, nz, nxy, Sb, out);
+   if (ni <= 0) return;
+   sn_export_cell_kernel<<<(int)((ni + 255) / 256), 256, 0, st>>>(
+      phi, slot_of_xy, mats, xs_g, area, dz, has_z, scale, G, nz, nxy, Sb, i0, ni, out);
 }
 
 // angular flux of one direction m into the reference layout out[(i*G + g)*M + m]

@@ -147,16 +147,35 @@ void launch_reduce(double* phi, double* phi_new, const int32_t* mats, const doub
                    int nblocks, double* sums, cudaStream_t st);
 // Anderson acceleration (history of up to 8 iterates, see sn_api.cu: pampa_sn_solve_keff)
 constexpr int AA_SLOTS = 8;
-void launch_aa_store(const double* phi, double* phi_new, const int32_t* mats, const int32_t* gloc,
-                     int owned_only, int G, int64_t n, double inv_prod, double* const* hist_f,
-                     double* const* hist_g, int cur, int nhist, double* partials, int nblocks, double* dots,
-                     cudaStream_t st);
-void launch_scale_copy(double* dst, const double* src, double c, int64_t n, cudaStream_t st);
-void launch_vec_mix(double* out, double* const* hist, const double* alpha, int nhist, int64_t n, cudaStream_t st);
+// The whole bookkeeping of the accelerated iteration lives on the device, so that pampa_sn_solve_keff enqueues
+// iteration after iteration without waiting for any of them (the host reads `converged` one iteration late):
+// Gram matrix of the stored residuals, eigenvalue estimates, window ages, mixing weights.
+struct AAState {
+   double M[AA_SLOTS][AA_SLOTS];   // Gram matrix of the residuals in the history slots
+   double kg[AA_SLOTS];            // k estimate that came with each slot
+   double mix[AA_SLOTS];           // weights of the next iterate
+   double kn;                      // k of the current iterate
+   double prod_x;                  // production the iterates are normalised to
+   double inv;                     // normalisation of the last sweep result (prod_x / its production)
+   double best, res, dk;           // smallest residual so far, last residual, last k change
+   double power_integral, min_phi, phi2;
+   double tol_k, tol_phi;
+   int32_t age[AA_SLOTS];          // iteration that filled each slot (-1: empty)
+   int32_t cur, slots, it, nvisit;
+   int32_t converged, failed, aa_start, pad_;
+};
+// (every launcher below takes the device-resident AAState: slot, window and weights are read on the device)
+void launch_aa_begin(AAState* st_dev, const double* sums, cudaStream_t st);
+void launch_aa_store(const double* phi, double* phi_new, const int32_t* gloc, int owned_only, int G, int64_t n,
+                     double* const* hist_f, double* const* hist_g, const AAState* st_dev, double* partials,
+                     int nblocks, double* dots, cudaStream_t st);
+void launch_aa_solve(AAState* st_dev, const double* dots, ReduceScalars* sc, cudaStream_t st);
+void launch_scale_copy_slot(double* const* hist, const double* src, const AAState* st_dev, int64_t n, cudaStream_t st);
+void launch_vec_mix(double* out, double* const* hist, const AAState* st_dev, int64_t n, cudaStream_t st);
 void launch_aa_mix(double* phi, const int32_t* mats, const int32_t* gloc, int owned_only, int G, int64_t n,
-                   double* const* hist_f, double* const* hist_g, const double* alpha, int nhist, int nblocks,
-                   cudaStream_t st);
+                   double* const* hist_g, const AAState* st_dev, int nblocks, cudaStream_t st);
 void launch_update_k(const double* sums, ReduceScalars* sc, int update_k, cudaStream_t st);
+void launch_combine_sums(const double* all, int nranks, double* sums, cudaStream_t st);   // [rank][5] -> [5]
 
 void launch_ls_rhs(const SweepGlobals& gp, const int32_t* ls_ptr, const int32_t* ls_nbr_slot,
                    const double* ls_coef, int64_t nnz, const int32_t* dir_chunk,
@@ -169,11 +188,12 @@ void launch_delta_corr(const SweepGlobals& gp, int chunk, int npatch, const int3
 void launch_min(const double* p, int64_t n, double* out, cudaStream_t st);   // *out = min(*out, min p), *out <= 0
 
 // field export (reference layouts)
+// i0, ni: window of cells (reference numbering) written to out[0 .. ni*G) / out[0 .. ni)
 void launch_export_phi(const double* phi, const int32_t* slot_of_xy, double scale, int G, int nz,
-                       int nxy, int64_t Sb, double* out, cudaStream_t st);
+                       int nxy, int64_t Sb, int64_t i0, int64_t ni, double* out, cudaStream_t st);
 void launch_export_cell(const double* phi, const int32_t* slot_of_xy, const int32_t* mats,
                         const double* xs_g, const double* area, const double* dz, int has_z,
-                        double scale, int G, int nz, int nxy, int64_t Sb, double* out,
+                        double scale, int G, int nz, int nxy, int64_t Sb, int64_t i0, int64_t ni, double* out,
                         cudaStream_t st);
 void launch_export_psi(const double* psi_block, const ClassDev* cl, const int32_t* pos_of,
                        const int32_t* slot_of_xy, int d, int nd, int m, const int32_t* gloc,

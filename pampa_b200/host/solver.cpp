@@ -238,8 +238,9 @@ int SNSolver::build() {
    num_directions = quadrature.getNumDirections();
 
    // fields, in the reference's order and layouts (src/SNSolver.cxx:721-747)
-   T.assign(num_cells, 0.0);
-   S.assign(num_cells, 0.0);
+   // (build() also runs when a temperature update needs a new device plan: the input fields are kept then)
+   if ((int)T.size() != num_cells) T.assign(num_cells, 0.0);
+   if ((int)S.size() != num_cells) S.assign(num_cells, 0.0);
    phi.assign((size_t)num_cells * num_energy_groups, 0.0);
    q.assign(num_cells, 0.0);
    P.assign(num_cells, 0.0);
@@ -352,10 +353,11 @@ int SNSolver::buildMatrices(int n, double, double) {
    xs.num_materials = (int)beta.size(); xs.num_groups = num_energy_groups;
    xs.sigma_total = st.data(); xs.sigma_scattering = ss.data(); xs.nu_sigma_fission = nsf.data();
    xs.kappa_sigma_fission = ksf.data(); xs.chi_effective = chi.data(); xs.beta_total = beta.data();
-   if (pampa_sn_update_xs(device, &xs)) {
-      // the temperature field changed the (material, temperature) pairs: rebuild the device problem
+   // the temperature field changes which (material, temperature) row each cell uses, and possibly how many rows
+   // there are: new tables and a new cell -> row map; if the new table does not fit the device plan, re-create the
+   // device problem (build() keeps the temperature and delayed-source fields)
+   if (pampa_sn_update_materials(device, &xs, cell_material.data()))
       PAMPA_CHECK(build(), "unable to rebuild the device transport solver");
-   }
    xs_dirty = false;
    return 0;
 }

@@ -224,6 +224,12 @@ class SNDevice:
         cx = pack_xs(xs, pk)
         self._check(self.lib.pampa_sn_update_xs(self.h, C.byref(cx)))
 
+    def update_materials(self, xs: CrossSections, materials):
+        """New cross-section rows and a new cell -> row map (temperature feedback)."""
+        pk = _Packed()
+        cx = pack_xs(xs, pk)
+        self._check(self.lib.pampa_sn_update_materials(self.h, C.byref(cx), pk.i32(materials)))
+
     def source(self, keff: float):
         self._check(self.lib.pampa_sn_source(self.h, keff))
 
@@ -262,6 +268,13 @@ class SNDevice:
             raise ValueError("out must be a contiguous float64 buffer of at least %d elements" % n)
         self._check(self.lib.pampa_sn_get(self.h, name.encode(), out.ctypes.data_as(_lib.p_f64)))
         return out[:n]
+
+    def field_size(self, name: str) -> int:
+        """Length of a field as get / set see it (this rank's part when the fields are partitioned)."""
+        n = self.lib.pampa_sn_field_size(self.h, name.encode())
+        if n < 0:
+            raise SNError("unable to find field '%s'" % name)
+        return int(n)
 
     def set(self, name: str, values):
         v = _f64(values)

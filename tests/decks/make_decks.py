@@ -40,19 +40,36 @@ PWR_MAP = [
 ]
 
 
+# temperature feedback: the slab fuel tabulated at two temperatures (nuclear-data-set, the format of
+# test/hex-core/materials/fuel-2-groups.pmp); absorption grows and fission drops with temperature
+SLAB_FUEL_HOT = dict(st=[0.031, 0.086], nsf=[0.000, 0.128], ss=[[0.0, 0.019], [0.0, 0.0]], chi=[1.0, 0.0], fuel=1)
+SLAB_FEEDBACK_MATERIALS = dict(SLAB_MATERIALS)
+SLAB_FEEDBACK_MATERIALS["fuel"] = dict(SLAB_MATERIALS["fuel"], set=[(300.0, SLAB_MATERIALS["fuel"]), (900.0, SLAB_FUEL_HOT)])
+
+
 def write_material(path, m):
     G = len(m["st"])
     row = lambda v: " ".join("%.6g" % x for x in v)
+
+    def block(f, t, ind):
+        f.write("%snuclear-data {\n%s   energy-groups %d\n%s   sigma-total\n%s   %s\n" % (ind, ind, G, ind, ind, row(t["st"])))
+        if "nsf" in t:
+            f.write("%s   nu-sigma-fission\n%s   %s\n" % (ind, ind, row(t["nsf"])))
+        f.write("%s   sigma-scattering\n" % ind)
+        for r in t["ss"]:
+            f.write("%s   %s\n" % (ind, row(r)))
+        if "chi" in t:
+            f.write("%s   fission-spectrum\n%s   %s\n" % (ind, ind, row(t["chi"])))
+        f.write("%s}\n" % ind)
+
     with open(path, "w") as f:
-        f.write("nuclear-data {\n   energy-groups %d\n   sigma-total\n   %s\n" % (G, row(m["st"])))
-        if "nsf" in m:
-            f.write("   nu-sigma-fission\n   %s\n" % row(m["nsf"]))
-        f.write("   sigma-scattering\n")
-        for r in m["ss"]:
-            f.write("   %s\n" % row(r))
-        if "chi" in m:
-            f.write("   fission-spectrum\n   %s\n" % row(m["chi"]))
-        f.write("}\n")
+        if "set" in m:
+            f.write("nuclear-data-set {\n   temperature %d\n   %s\n" % (len(m["set"]), row([T for T, _ in m["set"]])))
+            for _, t in m["set"]:
+                block(f, t, "   ")
+            f.write("}\n")
+        else:
+            block(f, m, "")
         if "prec" in m:
             f.write("precursor-data {\n   precursor-groups %d\n   lambda\n   %s\n   beta\n   %s\n}\n" % (
                 len(m["prec"]["lam"]), row(m["prec"]["lam"]), row(m["prec"]["beta"])))
@@ -142,6 +159,7 @@ def main(out=None):
     pwr_cartesian_mesh(write_deck("pwr_cartesian_s2", "cartesian", PWR_MATERIALS, 2, 1))
     pwr_unstructured_mesh(write_deck("pwr_unstructured_s2", "unstructured", PWR_MATERIALS, 2, 1))
     pwr_cartesian_mesh(write_deck("pwr_cartesian_s8_lsoff", "cartesian", PWR_MATERIALS, 8, 0))
+    slab_mesh(write_deck("slab_s2_feedback", "cartesian", SLAB_FEEDBACK_MATERIALS, 2, 0))
     return OUT
 
 

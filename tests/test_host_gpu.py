@@ -124,23 +124,101 @@ def test_vtk_output(decks, tmp_path):
 
 
 def test_default_face_interpolation(decks, tmp_path):
-    """A deck that omits `mixed-face-interpolation` runs with the reference's default, 0.1 (src/SNSolver.hxx:16).  On
-    the PWR deck that eigenvector has negative angular fluxes, and the reference fails such a solve in
-    normalizeAngularFlux (src/SNSolver.cxx:329): same message, non-zero exit.  With 0.9 the solve goes through."""
+    """A deck that omits `mixed-face-interpolation` runs with the reference's default, 0.1 (src/SNSolver.hxx:16).
+    (1) The slab problem between two reflective boundaries: the solve goes through and prints the k of the oracle's
+    delta = 0.1 operator.  (2) With a vacuum boundary the linear face interpolation undershoots next to it: the
+    eigenvector has negative angular fluxes, which the reference reports as an error in normalizeAngularFlux
+    (src/SNSolver.cxx:329) -- same message, non-zero exit (PWR deck, committed oracle fixture: psi_min < 0)."""
     import shutil
+    from oracle import pampa_oracle as orc
     exe = os.path.join(ROOT, "pampa_b200", "bin", "pampa")
-    for delta, ok in ((None, False), ("0.9", True)):
-        case = tmp_path / ("case_%s" % delta)
-        shutil.copytree(os.path.join(decks, "pwr_cartesian_s2"), case)
+
+    def variant(src, name, edit_mesh=None):
+        case = tmp_path / name
+        shutil.copytree(os.path.join(decks, src), case)
         text = open(case / "input.pmp").read()
-        assert "mixed-face-interpolation 1.0" in text
-        text = text.replace("   mixed-face-interpolation 1.0\n", "" if delta is None else "   mixed-face-interpolation %s\n" % delta)
+        assert "   mixed-face-interpolation 1.0\n" in text
+        text = text.replace("   mixed-face-interpolation 1.0\n", "")
         text = text.replace("least-squares-boundary-interpolation 1", "least-squares-boundary-interpolation 0")
         open(case / "input.pmp", "w").write(text)
-        r = subprocess.run([exe, "input.pmp"], cwd=case, capture_output=True, text=True)
-        if ok:
-            assert r.returncode == 0, r.stdout + r.stderr
-            assert "Effective multiplication factor: 0.96" in r.stdout
-        else:
-            assert r.returncode != 0
-            assert "negative values in the angular-flux solution" in r.stdout + r.stderr
+        if edit_mesh:
+            open(case / "mesh.pmp", "w").write(edit_mesh(open(case / "mesh.pmp").read()))
+        return case
+
+    case = variant("slab_s2", "slab_reflected", lambda m: m.replace("bc -x vacuum", "bc -x reflective").replace("bc +x vacuum", "bc +x reflective"))
+    deck = orc.read_deck(str(case / "input.pmp"))
+    assert deck.delta == 0.1 and deck.bcs[1:] == [orc.REFLECTIVE, orc.REFLECTIVE]
+    sol = orc.solve_monolithic(orc.build_operator(deck.mesh, deck.xs, deck.G, deck.order, deck.delta, "off", deck.bcs))
+    assert sol.psi.min() > 0.0
+    r = subprocess.run([exe, "input.pmp"], cwd=case, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout == EXPECTED % ("%.6f" % sol.keff), r.stdout
+
+    z = np.load(os.path.join(util.GOLDEN, "pwr_cartesian_s2_delta01_lsoff.npz"))
+    assert float(z["psi_min"]) < 0.0
+    case = variant("pwr_cartesian_s2", "pwr_default_delta")
+    r = subprocess.run([exe, "input.pmp"], cwd=case, capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "negative values in the angular-flux solution" in r.stdout + r.stderr
+
+
+def test_temperature_feedback(decks):
+    """The CouplingSolver-facing half of the path: pampa_set_field("temperature") re-tabulates the cross sections per
+    cell (linear interpolation between the tabulated temperatures, src/FeedbackNuclearData.hxx:62-140) for the next
+    solve.  Slab deck whose fuel is a nuclear-data-set at 300 K / 900 K; three temperature fields in a row through
+    the C API -- uniform cold, a profile with 7 distinct fuel temperatures (the number of (material, temperature)
+    rows on the device grows from 3 to 9), uniform hot (shrinks back) -- each against the oracle's eigenpair of the
+    same per-cell data."""
+    from oracle import pampa_oracle as orc
+    case = os.path.join(decks, "slab_s2_feedback")
+    deck = orc.read_deck(os.path.join(case, "input.pmp"))
+    names = ["reflector-left", "fuel", "reflector-right"]      # material order of the deck (ids 2 | 1 | 3 in the mesh)
+    order_in_deck = [l.split()[1] for l in open(os.path.join(case, "input.pmp")) if l.startswith("material ")]
+    tabs = {n: orc.read_material_tables(os.path.join(case, n + ".pmp")) for n in names}
+    mesh = deck.mesh
+    N = mesh.num_cells
+    x = mesh.centroids[:, 0]
+    fuel = np.array([order_in_deck[m] == "fuel" for m in mesh.materials])
+    assert fuel.sum() == 1000
+
+    def oracle_solve(T):
+        xs, ids, cell = [], {}, np.zeros(N, dtype=np.int64)
+        for i in range(N):
+            key = (int(mesh.materials[i]), float(T[i]))
+            if key not in ids:
+                ids[key] = len(xs)
+                t, tb = tabs[order_in_deck[key[0]]]
+                xs.append(orc.xs_at_temperature(t, tb, key[1]))
+            cell[i] = ids[key]
+        m2 = orc.Mesh(**{**mesh.__dict__, "materials": cell})
+        op = orc.build_operator(m2, xs, deck.G, deck.order, 1.0, "off", deck.bcs)
+        return orc.solve_monolithic(op)
+
+    lib = ctypes.CDLL(os.path.join(ROOT, "pampa_b200", "lib", "libpampa.so"))
+    lib.pampa_get_keff.restype = ctypes.c_double
+    err = ctypes.c_int(0)
+    argv = (ctypes.c_char_p * 3)(b"pampa", b"input.pmp", b"-silent")
+    pd = ctypes.POINTER(ctypes.c_double)
+    cwd = os.getcwd()
+    os.chdir(case)
+    try:
+        lib.pampa_initialize_steady_state(3, argv, ctypes.byref(err)); assert err.value == 0
+        profile = np.where(fuel, 300.0 + 100.0 * np.floor((x - 20.0) / 100.0 * 7.0).clip(0, 6), 0.0)
+        ks = []
+        for T in (np.where(fuel, 300.0, 0.0), profile, np.full(N, 900.0)):
+            T = np.ascontiguousarray(T, dtype=np.float64)
+            lib.pampa_set_field(T.ctypes.data_as(pd), b"temperature", ctypes.byref(err)); assert err.value == 0
+            lib.pampa_solve_steady_state(ctypes.byref(err)); assert err.value == 0
+            k = lib.pampa_get_keff(ctypes.byref(err))
+            phi = np.zeros(N * deck.G)
+            lib.pampa_get_field(phi.ctypes.data_as(pd), b"scalar-flux", ctypes.byref(err)); assert err.value == 0
+            sol = oracle_solve(T)
+            assert abs(k - sol.keff) < 1e-5, (k, sol.keff)
+            assert util.rel_l2(phi.reshape(N, deck.G), sol.phi) < 1e-5
+            assert util.max_rel(phi.reshape(N, deck.G), sol.phi) < 1e-4
+            ks.append(k)
+        assert ks[0] > ks[1] > ks[2]                     # hotter fuel: more absorption, less fission
+        assert abs(ks[0] - 0.9708) < 5e-3                # cold = the reference's slab problem without the LS term
+        lib.pampa_finalize_steady_state(ctypes.byref(err)); assert err.value == 0
+    finally:
+        os.chdir(cwd)
