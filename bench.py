@@ -52,7 +52,21 @@ def parse():
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sharded-vs-one-GPU check of multi-GPU runs")
     ap.add_argument("--opts", default="{}", help="JSON of pampa_sn_options overrides")
-    return ap.parse_args()
+    ap.add_argument("--config", default=None, choices=["c4", "c5"],
+                    help="c4: the default (BASELINE configs[3], the line of record); c5: BASELINE configs[4], synthetic "
+                         "unstructured extruded hexagonal core, 200 467 hexagons x 200 layers = 40.1M cells, S12, 16 groups, "
+                         "meant for --gpus 8 (energy-group sharding, 2 groups per GPU); the angular flux is not kept "
+                         "(store_psi = 0: 860 GB of psi do not fit 8 x 180 GB next to the step-major arrays) and the "
+                         "k-eff solve is skipped (its history vectors would not fit either)")
+    a = ap.parse_args()
+    if a.config == "c5":
+        a.mesh, a.rings, a.order, a.groups = "hex", 258, 12, 16
+        a.size = [1, 1, 200]
+        o = json.loads(a.opts)
+        o.setdefault("store_psi", 0)
+        a.opts = json.dumps(o)
+        a.no_solve = True
+    return a
 
 
 def workload_name(a):

@@ -166,11 +166,13 @@ struct pampa_sn_handle {
       gp.nmat = nmat;
       gp.uniform_dz = uniform_dz;
       gp.corr_off = d_corr ? (int64_t)(d_corr - d_psi) : 0;
+      gp.np_stride = np_stride;
       { const char* e = std::getenv("PAMPA_SN_DBG"); gp.dbg = e ? std::atoi(e) : 0; }
       return gp;
    }
    int bcz_refl[2] = {0, 0};
    int uniform_dz = 1;
+   int np_stride = 0;                    // patches per (chunk, block) in the dataflow progress counters
 };
 
 #define SN_FAIL(h, msg) do { (h)->err = (msg); return 1; } while (0)
@@ -900,6 +902,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          if (!h->flows.empty()) {
             int np_max = pl.npatch_b;
             for (const Tiling& tg : pl.tilings) np_max = std::max(np_max, tg.npatch);
+            h->np_stride = np_max;
             h->flow_ctl_count = 16 + (int64_t)pl.chunks.size() * nblk * np_max;
             if (dev_alloc(h, &h->d_flow_ctl, h->flow_ctl_count)) return 1;
          }

@@ -837,7 +837,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
    double* psi_gl = ch->psi + (int64_t)gb * npatch * NS * rowg;
    const int kdir = zdir >= 0 ? 1 : -1;
    const int kstart = zdir >= 0 ? 0 : nz - 1;
-   int* my_progress = progress + ((int64_t)tk.chunk * nblk + gb) * npatch + tk.patch;
+   int* my_progress = progress + ((int64_t)tk.chunk * nblk + gb) * gp.np_stride + tk.patch;
 
    if (lane_thread) {
       // ---------------------------------------------------------------- the 256 lanes of the patch
@@ -1031,7 +1031,7 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
             const int up = pay >> 8;
             const int dlv = (int)cl->lvl[pay] - rlv[e];
             gsrc[e] = psi_gl + ((int64_t)up * NS + dlv) * rowg + (inl ? (pay & (PS - 1)) : goff + (int)cl->eidx[pay]);
-            flag[e] = progress + ((int64_t)tk.chunk * nblk + gb) * npatch + up;
+            flag[e] = progress + ((int64_t)tk.chunk * nblk + gb) * gp.np_stride + up;
             need0[e] = dlv + 1;                        // rows the upwind task must have completed for step 0
          } else if (kind[e] == SRC_REFL) {
             ax[e] = pay >> SRC_AXIS_SHIFT; rf[e] = pay & ((1 << SRC_AXIS_SHIFT) - 1);
@@ -1048,7 +1048,12 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
             double* dst = bufs + ((st - 1) & (D - 1)) * ROWS + PS + PEDGE + hl + 32 * e;
             if (kind[e] == SRC_GLOBAL) {
                const int need = st + need0[e];
-               while (seen[e] < need) seen[e] = ld_acquire_gpu(flag[e]);
+               // (watchdog: a dependency that never completes aborts the launch instead of hanging the device --
+               // a legitimate wait lasts at most one task, milliseconds; 2^26 polls are tens of seconds)
+               for (unsigned spins = 0; seen[e] < need; spins++) {
+                  seen[e] = ld_acquire_gpu(flag[e]);
+                  if (spins > (1u << 26)) __trap();
+               }
 #pragma unroll
                for (int d = 0; d < DT; d++) cp_async8(dst + d * PSXS, gsrc[e] + (int64_t)st * rowg + d * gstr);
             } else if (EXTRAS) {
@@ -1093,7 +1098,8 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
          if (hl == 0) {
             if (step + 1 < nsteps) mbar_wait(&s_bar[(step + 1) & (DQ - 1)], ((step + 1) / DQ) & 1);
             // buffer (step+1)&3 is rewritten in the next step: its row, step - 3, must have left smem
-            while (ld_acquire_cta_smem(&s_rows_read) < step - 2) {}
+            for (unsigned spins = 0; ld_acquire_cta_smem(&s_rows_read) < step - 2; spins++)
+               if (spins > (1u << 28)) __trap();
          }
          pipe_barrier();                               // end of step: row `step` is complete in smem
          if (hl == 0) st_release_cta_smem(&s_rows_done, step + 1);
@@ -1116,7 +1122,8 @@ sn_sweep_flow_kernel(const SweepGlobals gp, const Task* __restrict__ tasks, int*
       const int pub = ((gp.dbg >> 4) & 0xff) ? ((gp.dbg >> 4) & 0xff) : 16;
       const unsigned bytes = row_cols * sizeof(double);
       for (int step = 0; step < nsteps; step++) {
-         while (ld_acquire_cta_smem(&s_rows_done) <= step) {}
+         for (unsigned spins = 0; ld_acquire_cta_smem(&s_rows_done) <= step; spins++)
+            if (spins > (1u << 28)) __trap();
          const double* src = bufs + (step & (D - 1)) * ROWS + src_off;
          double* dst = psi_rows + (int64_t)step * rowg;
 #pragma unroll

@@ -94,6 +94,8 @@ struct SweepGlobals {
    int64_t Sb;
    int32_t G, Gown, M, nz, Kc, has_z, nrf, nls;
    int32_t gm;                // owned groups per block (ClassDev::gm, the same for every class)
+   int32_t np_stride;         // patches per (chunk, block) in the progress-counter array: the largest patch count of
+                              // any shared tiling (classes on different tilings have different patch counts)
    int32_t bcz_minus_refl, bcz_plus_refl;   // 1 if that z boundary is reflective
    int32_t store_psi;
    int32_t nmat;

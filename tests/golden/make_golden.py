@@ -40,12 +40,12 @@ DELTA = {"pwr_cartesian_s2_delta01_lsoff": 0.1}
 CASES["pwr_cartesian_s2_delta01_lsoff"] = ("pwr-iaea-benchmark/cartesian-sn/input.pmp", None, None, "off", None)
 
 
-def hex_core_deck(groups):
+def hex_core_deck(groups, cells="hex-cells"):
     """BASELINE config 3: the reference ships no SN input for hex-core, so this authors one on its
     hex-cells mesh (test/hex-core/hex-cells-diffusion-3d/mesh.pmp: 163 hexagons x 16 layers) with the
     materials of that directory's input.pmp:5-10, S8, vacuum on every boundary, LS off."""
     base = os.path.join(REF, "hex-core")
-    mesh = orc.read_unstructured_mesh(os.path.join(base, "hex-cells-diffusion-3d", "mesh.pmp"))
+    mesh = orc.read_unstructured_mesh(os.path.join(base, cells + "-diffusion-3d", "mesh.pmp"))
     names = ["fuel", "fuel", "fuel", "fuel", "reflector", "reflector"]
     xs = [orc.read_material(os.path.join(base, "materials", "%s-%d-groups.pmp" % (n, groups))) for n in names]
     bcs = [0] * (1 + len(mesh.boundaries))
@@ -60,10 +60,13 @@ def main(only=None):
     cases["hex_core_s8_2g"] = ("hex-core:2", None, None, "off", None)
     # BASELINE config 3 with the reference's own 11-group graphite-moderated data (upscatter, c ~ 0.95)
     cases["hex_core_s8_11g"] = ("hex-core:11", None, None, "off", None)
+    # the same core with every hexagon cut into six triangles (test/hex-core/tri-cells-diffusion-3d/mesh.pmp:
+    # 978 triangles x 16 layers), S4 to keep the fixture small
+    cases["hex_core_tri_s4_2g"] = ("hex-core:2:tri-cells", None, None, "off", 4)
     for name, (deck_path, line, gold, ls_mode, order) in cases.items():
         if only and name not in only:
             continue
-        deck = (hex_core_deck(int(deck_path.split(":")[1])) if deck_path.startswith("hex-core")
+        deck = (hex_core_deck(int(deck_path.split(":")[1]), *deck_path.split(":")[2:]) if deck_path.startswith("hex-core")
                 else orc.read_deck(os.path.join(REF, deck_path)))
         if order is not None:
             deck.order = order

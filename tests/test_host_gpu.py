@@ -142,7 +142,8 @@ def test_default_face_interpolation(decks, tmp_path):
         text = text.replace("least-squares-boundary-interpolation 1", "least-squares-boundary-interpolation 0")
         open(case / "input.pmp", "w").write(text)
         if edit_mesh:
-            open(case / "mesh.pmp", "w").write(edit_mesh(open(case / "mesh.pmp").read()))
+            mesh_text = edit_mesh(open(case / "mesh.pmp").read())
+            open(case / "mesh.pmp", "w").write(mesh_text)
         return case
 
     case = variant("slab_s2", "slab_reflected", lambda m: m.replace("bc -x vacuum", "bc -x reflective").replace("bc +x vacuum", "bc +x reflective"))
