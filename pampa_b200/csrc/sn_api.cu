@@ -1119,14 +1119,18 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
    // the lagged LS boundary term depends on the angular flux of the previous sweep, which is not
    // part of the mixed state: keep the history short there (1-D / 2-D problems only)
    if (h->nls > 0 && depth > 3) depth = 3;
-   // same for the deferred correction of delta < 1, which is formed from the previous sweep's angular flux
-   if (h->d_corr && depth > 3) depth = 3;
+   // The deferred correction of delta < 1 is formed from the previous sweep's angular flux too, and it is not a
+   // small term (the iteration matrix of the lagged part has a spectral radius of ~0.9 at delta = 0.1): mixing
+   // iterates whose hidden state differs can diverge (seen on a slab between reflective boundaries), so those
+   // problems run the plain iteration unless an acceleration depth is asked for explicitly
+   if (h->d_corr) depth = h->opts.anderson_depth > 0 ? std::min(depth, 3) : -1;
    int it = 0;
    bool converged = false;
    h->psi_scale_factor = 1.0;
    double power_integral = 0.0, min_phi = 0.0;
 
-   if (depth < 1) {
+   // plain power iteration; the convergence test reads the scalars of iteration i while i + 1 is in the queue
+   auto plain_iteration = [&]() -> int {
       while (it < max_it) {
          if (do_source(h) || do_sweep(h) || do_reduce(h, 1)) return 1;
          it++;
@@ -1136,6 +1140,12 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
          if (it > 1 && std::fabs(h->sc.dk) < tol_k && dphi < tol_phi) { converged = true; break; }
       }
       power_integral = h->sc.power; min_phi = h->sc.min_phi;
+      h->psi_scale_factor = 1.0;
+      return 0;
+   };
+
+   if (depth < 1) {
+      if (plain_iteration()) return 1;
    } else {
       // Anderson-accelerated fixed-point iteration on x = phi (constant production) and k.  All the bookkeeping
       // (Gram matrix, window, weights, k) is in the device-resident AAState: the host enqueues iteration after
@@ -1208,9 +1218,25 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
       for (auto& e : ev) if (e) cudaEventDestroy(e);
       if (rc) return 1;
       if (es != cudaSuccess) SN_FAIL(h, std::string("CUDA error in the k-eff iteration: ") + cudaGetErrorString(es));
-      if (it > 0) {
+      if (it > 0 && (h->h_aa_ring[it & 1].failed || failed)) {
+         // the accelerated iteration broke down (NaN or a non-positive production after mixing): start again from a
+         // flat flux with the plain iteration, which cannot
+         if (h->opts.verbose) std::printf("pampa_sn: accelerated iteration failed after %d iterations, restarting plain\n", it);
+         SN_CUDA(h, cudaMemsetAsync(h->d_phi, 0, (size_t)nphi * sizeof(double), h->stream));
+         launch_fill_phi(h->d_phi_new, h->d_mats, 1.0, h->G, nslab, h->stream);
+         if (h->d_psi) SN_CUDA(h, cudaMemsetAsync(h->d_psi, 0, (size_t)h->psi_count * sizeof(double), h->stream));
+         for (int b = 0; b < 2; b++) {
+            if (h->d_bnd[b]) SN_CUDA(h, cudaMemsetAsync(h->d_bnd[b], 0, (size_t)h->bnd_count * sizeof(double), h->stream));
+            if (h->d_bndz[b]) SN_CUDA(h, cudaMemsetAsync(h->d_bndz[b], 0, (size_t)h->bndz_count * sizeof(double), h->stream));
+         }
+         if (h->d_ls_rhs) SN_CUDA(h, cudaMemsetAsync(h->d_ls_rhs, 0, (size_t)h->M * h->G * h->nls * sizeof(double), h->stream));
+         const double one = 1.0;
+         SN_CUDA(h, cudaMemcpyAsync(&h->d_sc->keff, &one, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+         SN_CUDA(h, cudaStreamSynchronize(h->stream));
+         if (do_reduce(h, 0)) return 1;
+         if (plain_iteration()) return 1;
+      } else if (it > 0) {
          const AAState& last = h->h_aa_ring[it & 1];     // the state the device fields are in
-         if (last.failed || failed) SN_FAIL(h, "the power iteration diverged");
          converged = converged || last.converged != 0;
          h->sc.keff = last.kn;
          h->psi_scale_factor = last.inv;

@@ -234,7 +234,7 @@ def test_single_sweep_hex_s12_16g():
     """BASELINE config 5 in small: hexagonal prisms, S12 (168 directions), 16 groups.  One sweep with a frozen
     source against the sparse LU of the oracle's operator, and a k-eff solve against the oracle's eigenpair."""
     rng = np.random.default_rng(12)
-    em, xs, quad, op = _hex_problem(4, 4, 16, 12, seed=54321)
+    em, xs, quad, op = _hex_problem(3, 3, 16, 12, seed=54321)
     assert len(quad.weights) == 168
     import scipy.sparse.linalg as spla
     N, G, M = op.N, op.G, op.M
@@ -327,10 +327,10 @@ def test_delta_hex_3d():
 
 def test_reduced_c4_matches_cpu_port():
     """BASELINE config 4 itself has no independent answer at 216^3 (the oracle cannot run there): the same
-    generator at 48^3 cells, S8, 8 groups, converged on the device (Anderson) and by the oracle's C port (plain
+    generator at 40^3 cells, S8, 8 groups, converged on the device (Anderson) and by the oracle's C port (plain
     power iteration on the host cores) must give the same k and flux."""
     from oracle import sweep_cpu
-    n, G = 48, 8
+    n, G = 40, 8
     mesh, xs = syn.checkerboard_core(n, n, n, num_groups=G)
     quad = syn.level_symmetric(8)
     dev = pb.SNDevice(mesh, xs, quad)
@@ -342,7 +342,7 @@ def test_reduced_c4_matches_cpu_port():
                              quad.weights)
     kc, phic, itc = cpu.solve(tol_k=1e-11, tol_phi=1e-10, max_it=20000)
     phic = phic.transpose(1, 2, 3, 0)
-    print("48^3 core: device k %.10f in %d iterations, CPU port k %.10f in %d" % (k, it, kc, itc))
+    print("%d^3 core: device k %.10f in %d iterations, CPU port k %.10f in %d" % (n, k, it, kc, itc))
     assert abs(k - kc) < TOL_K * kc
     a, b = phi / np.linalg.norm(phi), phic / np.linalg.norm(phic)
     assert util.rel_l2(a, b) < TOL_L2
