@@ -209,6 +209,7 @@ typedef struct {
                                         congruent cells has one per pair of lattice directions) */
    int64_t flow_classes;             /* ordering classes the one-launch dataflow kernel can sweep */
    int64_t lattice;                  /* 1: unstructured mesh recognised as a lattice of congruent cells */
+   double  last_solve_ms;            /* device time of the last pampa_sn_solve_keff (events on the launching stream) */
 } pampa_sn_info;
 int pampa_sn_get_info(pampa_sn_handle* h, pampa_sn_info* info);
 

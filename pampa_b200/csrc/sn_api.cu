@@ -144,7 +144,7 @@ struct pampa_sn_handle {
    double scale = 1.0;
    double keff = 1.0;
    bool solved = false;
-   double last_sweep_ms = 0, last_source_ms = 0, last_reduce_ms = 0;
+   double last_sweep_ms = 0, last_source_ms = 0, last_reduce_ms = 0, last_solve_ms = 0;
    // pampa_sn_iterate_timed: events around the sweep-kernel launches alone (after the shear pass,
    // before the un-shear pass), one pair per iteration
    std::vector<cudaEvent_t>* kernel_events = nullptr;
@@ -1128,6 +1128,7 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
    bool converged = false;
    h->psi_scale_factor = 1.0;
    double power_integral = 0.0, min_phi = 0.0;
+   SN_CUDA(h, cudaEventRecord(h->ev0, h->stream));
 
    // plain power iteration; the convergence test reads the scalars of iteration i while i + 1 is in the queue
    auto plain_iteration = [&]() -> int {
@@ -1243,6 +1244,9 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
          power_integral = last.power_integral; min_phi = last.min_phi;
       }
    }
+   SN_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+   SN_CUDA(h, cudaStreamSynchronize(h->stream));
+   { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->last_solve_ms = ms; }
    if (check_async(h, "the k-eff iteration")) return 1;
    h->keff = h->sc.keff;
    if (keff) *keff = h->sc.keff;
@@ -1465,7 +1469,7 @@ int pampa_sn_get_info(pampa_sn_handle* h, pampa_sn_info* info) {
    info->device_bytes = h->device_bytes;
    info->timed_kernel_ms = h->timed_kernel_ms;
    info->last_sweep_ms = h->last_sweep_ms; info->last_source_ms = h->last_source_ms;
-   info->last_reduce_ms = h->last_reduce_ms;
+   info->last_reduce_ms = h->last_reduce_ms; info->last_solve_ms = h->last_solve_ms;
    info->kernel_launches = h->launches;
    return 0;
 }

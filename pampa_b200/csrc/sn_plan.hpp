@@ -189,19 +189,37 @@ inline bool detect_lattice(const pampa_sn_mesh& ms, std::vector<int>& qr, std::v
    double bdet = 0.0;
    for (const Vec2& v : o) {                            // the neighbour offset that spans the smallest cell with a
       const double det = a.x * v.y - a.y * v.x;
-      if (std::fabs(det) > 1.0e-6 * la * la && (bdet == 0.0 || std::fabs(det) < std::fabs(bdet) - 1.0e-9 * la * la)) { b = v; bdet = det; }
+      const double lv = std::sqrt(v.x * v.x + v.y * v.y);
+      if (std::fabs(det) > 0.1 * la * lv &&              // not (anti)parallel to a, rounded coordinates included
+          (bdet == 0.0 || std::fabs(det) < std::fabs(bdet) * (1.0 - 1.0e-3))) { b = v; bdet = det; }
    }
    if (bdet == 0.0) return false;
+   // Integer coordinates by walking the neighbour graph: every step is the offset to a face neighbour, a small
+   // lattice vector that rounds safely even when the file carries three decimals (the reference's own mesh writer
+   // does); rounding absolute positions instead would accumulate the error of a and b over the width of the mesh.
    qr.assign((size_t)2 * nxy, 0);
-   std::map<std::pair<int, int>, int> seen;
-   for (int c = 0; c < nxy; c++) {
-      const double dx = ms.xy_cx[c] - ms.xy_cx[c0], dy = ms.xy_cy[c] - ms.xy_cy[c0];
-      const double q = (dx * b.y - dy * b.x) / bdet, r = (a.x * dy - a.y * dx) / bdet;
-      const double qi = std::nearbyint(q), ri = std::nearbyint(r);
-      if (std::fabs(q - qi) > 1.0e-5 || std::fabs(r - ri) > 1.0e-5 || std::fabs(qi) > 1.0e8 || std::fabs(ri) > 1.0e8) return false;
-      qr[2 * c] = (int)qi; qr[2 * c + 1] = (int)ri;
-      if (!seen.emplace(std::make_pair((int)qi, (int)ri), c).second) return false;
+   std::vector<char> visited(nxy, 0);
+   std::vector<int> queue;
+   queue.reserve(nxy);
+   queue.push_back(c0); visited[c0] = 1;
+   for (size_t head = 0; head < queue.size(); head++) {
+      const int c = queue[head];
+      for (int f = 0; f < ms.xy_num_faces[c]; f++) {
+         const int nb = ms.xy_neighbor[(size_t)c * F + f];
+         if (nb < 0) continue;
+         const double dx = ms.xy_cx[nb] - ms.xy_cx[c], dy = ms.xy_cy[nb] - ms.xy_cy[c];
+         const double q = (dx * b.y - dy * b.x) / bdet, r = (a.x * dy - a.y * dx) / bdet;
+         const double qi = std::nearbyint(q), ri = std::nearbyint(r);
+         if (std::fabs(q - qi) > 0.05 || std::fabs(r - ri) > 0.05 || std::fabs(qi) > 1.0 || std::fabs(ri) > 1.0) return false;
+         const int nq = qr[2 * c] + (int)qi, nr = qr[2 * c + 1] + (int)ri;
+         if (!visited[nb]) { visited[nb] = 1; qr[2 * nb] = nq; qr[2 * nb + 1] = nr; queue.push_back(nb); }
+         else if (qr[2 * nb] != nq || qr[2 * nb + 1] != nr) return false;
+      }
    }
+   if ((int)queue.size() != nxy) return false;           // disconnected mesh
+   std::map<std::pair<int, int>, int> seen;
+   for (int c = 0; c < nxy; c++)
+      if (!seen.emplace(std::make_pair(qr[2 * c], qr[2 * c + 1]), c).second) return false;
    std::map<std::pair<int, int>, int> dirs;
    for (int c = 0; c < nxy; c++)
       for (int f = 0; f < ms.xy_num_faces[c]; f++) {
@@ -323,6 +341,19 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
                for (int c = 0; c < nxy; c++) { ab[2*c] -= amin; ab[2*c+1] -= bmin; }
                pl.tilings.push_back(tile_from_coords(ab.data(), ti, tj, false));
             }
+         // Lanes of the other tilings in the order of the base slots: the shear passes move q and phi between the
+         // base numbering and a tiling's by gather / scatter, and a rhombic tile cuts every row of a base tile in
+         // one contiguous run, so sorted lanes turn most of those accesses into whole sectors (the sweep itself
+         // does not care how the lanes of a patch are numbered).
+         for (size_t tg = 1; tg < pl.tilings.size(); tg++) {
+            Tiling& t = pl.tilings[tg];
+            std::vector<std::vector<std::pair<int32_t, int>>> members(t.npatch);
+            for (int c = 0; c < nxy; c++) members[t.slot_of_xy[c] / P].push_back({pl.tilings[0].slot_of_xy[c], c});
+            for (int p = 0; p < t.npatch; p++) {
+               std::sort(members[p].begin(), members[p].end());
+               for (size_t l = 0; l < members[p].size(); l++) t.slot_of_xy[members[p][l].second] = p * P + (int)l;
+            }
+         }
       }
       if (pl.tilings.empty()) {
          pl.lattice = 0;

@@ -36,10 +36,11 @@ def _check_solution(dev, k, sol_keff, sol_phi, sol_power):
 
 @pytest.mark.parametrize("name", ["slabs_s2", "slabs_s4", "pwr_cartesian_s2", "pwr_unstructured_s2",
                                   "pwr_cartesian_s2_lsoff", "pwr_cartesian_s8_lsoff", "pwr_cartesian_s8",
-                                  "hex_core_s8_2g", "hex_core_s8_11g"])
+                                  "hex_core_s8_2g", "hex_core_s8_11g", "hex_core_tri_s4_2g"])
 def test_reference_cases(name):
     """The SN cases the reference ships (test/check_ref.txt:32,53,234,415), BASELINE configs 2 (the PWR deck as
-    shipped, LS on, at S8) and 3 (hex-core at S8 with the reference's 2- and 11-group data) and two variants."""
+    shipped, LS on, at S8) and 3 (hex-core at S8 with the reference's 2- and 11-group data on its hex-cells mesh,
+    and at S4 on its tri-cells mesh) and two variants."""
     em, xs, quad, ls, z = util.load_golden(name)
     dev, k, it = _solve(em, xs, quad, ls)
     gold = float(z["golden_keff"])
