@@ -28,6 +28,7 @@ double pampa_get_keff(int* error);
 int pampa_debug_describe(const char* deck, double* out16);
 int pampa_debug_write_mesh_vtk(const char* deck, const char* prefix);
 int pampa_debug_write_ptc(const char* prefix, int n, const double* v, long count);
+int pampa_debug_write_mesh_data(const char* deck, const char* filename, int digits);   /* src/Mesh.cxx:408-569 */
 
 #ifdef __cplusplus
 }

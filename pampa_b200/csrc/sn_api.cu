@@ -1242,6 +1242,18 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
          h->sc.keff = last.kn;
          h->psi_scale_factor = last.inv;
          power_integral = last.power_integral; min_phi = last.min_phi;
+         // A mixed iterate is a combination with weights of both signs: where the flux is many decades below its
+         // maximum (deep in a reflector, far corners) it can be negative by less than the tolerance, and so is the
+         // sweep result there.  The eigenvector is positive, and the plain iteration keeps what is positive positive:
+         // a few unaccelerated iterations remove the undershoot (the reference rejects any negative flux,
+         // src/NeutronicSolver.cxx:67).
+         for (int polish = 0; converged && min_phi < 0.0 && polish < 200 && it < max_it; polish++) {
+            if (do_source(h) || do_sweep(h) || do_reduce(h, 1)) return 1;
+            it++;
+            if (sync_scalars(h)) return 1;
+            power_integral = h->sc.power; min_phi = h->sc.min_phi;
+            h->psi_scale_factor = 1.0;
+         }
       }
    }
    SN_CUDA(h, cudaEventRecord(h->ev1, h->stream));

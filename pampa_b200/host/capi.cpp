@@ -123,6 +123,22 @@ int pampa_debug_write_mesh_vtk(const char* deck, const char* prefix) {
    return rc;
 }
 
+/* Test hook (no GPU needed): parse a deck and write every array of its mesh in the reference's plain-text format
+ * (Mesh::writeData, src/Mesh.cxx:408-569) -- the file `mesh partitioned <file>` reads back. */
+int pampa_debug_write_mesh_data(const char* deck, const char* filename, int digits) {
+   pampa::Mesh* mesh = nullptr;
+   std::vector<pampa::Material*> materials;
+   std::vector<pampa::Solver*> solvers;
+   std::vector<double> dt;
+   pampa::Parser parser;
+   int rc = parser.read(std::string(deck), &mesh, materials, solvers, dt);
+   if (!rc && mesh) rc = mesh->writeData(std::string(filename), digits);
+   delete mesh;
+   for (auto* m : materials) delete m;
+   for (auto* s : solvers) delete s;
+   return rc;
+}
+
 /* Test hook: write `count` doubles as <prefix>_<n>.ptc whatever the `petsc dump` switch says. */
 int pampa_debug_write_ptc(const char* prefix, int n, const double* v, long count) {
    const bool on = pampa::ptc::dump;

@@ -2,6 +2,8 @@
 #include "vtk.hpp"
 
 #include <algorithm>
+#include <cmath>
+#include <iomanip>
 
 namespace pampa {
 
@@ -334,6 +336,196 @@ int UnstructuredExtrudedMesh::build() {
          faces.ptr.push_back((int)faces.areas.size());
       }
    if (!has_z_faces) dz.clear();
+   return 0;
+}
+
+// ------------------------------------------------------------------------------ mesh data / partitioned
+int Mesh::writeData(const std::string& filename, int digits) const {
+   std::ofstream file(filename, std::ios_base::out);
+   PAMPA_CHECK(!file.is_open(), "unable to open " + filename);
+   if (digits < 0) file << std::fixed << std::setprecision(3);       // the reference's own precision
+   else file << std::setprecision(digits);
+   const int np = getNumPoints();
+   file << "points " << np << std::endl;
+   for (int i = 0; i < np; i++) file << points[3 * i] << " " << points[3 * i + 1] << " " << points[3 * i + 2] << std::endl;
+   file << std::endl;
+   file << "cells " << num_cells << " " << 0 << " " << num_cells << std::endl;
+   file << "cell-points " << num_cells << " " << cell_points.size() << std::endl;
+   for (int i = 0; i < num_cells; i++) {
+      for (int j = cell_point_ptr[i]; j < cell_point_ptr[i + 1]; j++) file << (j > cell_point_ptr[i] ? " " : "") << cell_points[j];
+      file << std::endl;
+   }
+   file << std::endl;
+   file << "cell-volumes " << num_cells << std::endl;
+   for (int i = 0; i < num_cells; i++) file << cells.volumes[i] << std::endl;
+   file << std::endl;
+   file << "cell-centroids " << num_cells << std::endl;
+   for (int i = 0; i < num_cells; i++)
+      file << cells.centroids[3 * (size_t)i] << " " << cells.centroids[3 * (size_t)i + 1] << " " << cells.centroids[3 * (size_t)i + 2] << std::endl;
+   file << std::endl;
+   file << "cell-materials " << num_cells << std::endl;
+   for (int i = 0; i < num_cells; i++) file << cells.materials[i] + 1 << std::endl;
+   file << std::endl;
+   file << "cell-global-indices " << num_cells << std::endl;
+   for (int i = 0; i < num_cells; i++) file << i << std::endl;
+   file << std::endl;
+   file << "faces " << num_cells << std::endl;
+   for (int i = 0; i < num_cells; i++) file << faces.num_faces(i) << std::endl;
+   file << std::endl;
+   const size_t nf = faces.areas.size();
+   file << "face-areas " << num_cells << " " << nf << std::endl;
+   for (int i = 0; i < num_cells; i++) {
+      for (int f = faces.ptr[i]; f < faces.ptr[i + 1]; f++) file << (f > faces.ptr[i] ? " " : "") << faces.areas[f];
+      file << std::endl;
+   }
+   file << std::endl;
+   file << "face-centroids " << num_cells << " " << 3 * nf << std::endl;
+   for (size_t f = 0; f < nf; f++) file << faces.centroids[3 * f] << " " << faces.centroids[3 * f + 1] << " " << faces.centroids[3 * f + 2] << std::endl;
+   file << std::endl;
+   file << "face-normals " << num_cells << " " << 3 * nf << std::endl;
+   for (size_t f = 0; f < nf; f++) file << faces.normals[3 * f] << " " << faces.normals[3 * f + 1] << " " << faces.normals[3 * f + 2] << std::endl;
+   file << std::endl;
+   file << "face-neighbors " << num_cells << " " << nf << std::endl;
+   for (int i = 0; i < num_cells; i++) {
+      for (int f = faces.ptr[i]; f < faces.ptr[i + 1]; f++) file << (f > faces.ptr[i] ? " " : "") << faces.neighbors[f];
+      file << std::endl;
+   }
+   file << std::endl;
+   for (const std::string& b : boundaries) file << "boundary " << b << std::endl;
+   for (size_t i = 1; i < bcs.size(); i++) {
+      file << "bc " << boundaries[i - 1];
+      switch (bcs[i].type) {
+         case BC::VACUUM: file << " vacuum"; break;
+         case BC::REFLECTIVE: file << " reflective"; break;
+         case BC::ROBIN: file << " robin"; break;
+         case BC::DIRICHLET: file << " dirichlet"; break;
+         case BC::ADIABATIC: file << " adiabatic"; break;
+         case BC::CONVECTION: file << " convection"; break;
+         default: file << " none"; break;
+      }
+      for (double x : bcs[i].parameters) file << " " << x;
+      file << std::endl;
+   }
+   file << std::endl;
+   return 0;
+}
+
+int PartitionedMesh::read(const std::string& filename) {
+   std::ifstream file(filename, std::ios_base::in);
+   PAMPA_CHECK(!file.is_open(), "unable to open " + filename);
+   int nf_total = 0;
+   std::vector<int> nfaces;
+   while (true) {
+      std::vector<std::string> line = input::get_next_line(file);
+      if (line.empty()) break;
+      const std::string& k = line[0];
+      auto rows = [&](int want) -> int {                 // "<keyword> <rows> [<total>]": check the row count
+         int n;
+         PAMPA_CHECK(line.size() < 2 || input::read(n, want, want, line[1]), "wrong number of rows for keyword '" + k + "'");
+         return 0;
+      };
+      if (k == "points") {
+         int np;
+         PAMPA_CHECK(line.size() != 2 || input::read(np, 1, INT_MAX, line[1]), "wrong number of points");
+         PAMPA_CHECK(input::read(points, np, 3, -DBL_MAX, DBL_MAX, file), "wrong point data");
+      } else if (k == "cells") {
+         PAMPA_CHECK(line.size() != 4, "wrong number of arguments for keyword '" + k + "'");
+         PAMPA_CHECK(input::read(num_cells, 1, INT_MAX, line[1]), "wrong number of cells");
+         PAMPA_CHECK(input::read(num_ghost_cells, 0, INT_MAX, line[2]), "wrong number of ghost cells");
+         PAMPA_CHECK(input::read(num_cells_global, 1, INT_MAX, line[3]), "wrong global number of cells");
+         PAMPA_CHECK(num_ghost_cells != 0 || num_cells_global != num_cells,
+                     "this file is one rank's part of a domain decomposition (it has ghost cells): the sweeps of this "
+                     "build are sharded by angle set and energy group over the whole mesh, give the original mesh");
+      } else if (k == "cell-points") {
+         int total;
+         PAMPA_CHECK(line.size() != 3 || rows(num_cells) || input::read(total, 1, INT_MAX, line[2]), "wrong number of cell points");
+         PAMPA_CHECK(input::read(cell_point_ptr, cell_points, num_cells, total, 0, INT_MAX, file), "wrong cell-point data");
+      } else if (k == "cell-volumes") {
+         PAMPA_CHECK(line.size() != 2 || rows(num_cells), "wrong number of cell volumes");
+         PAMPA_CHECK(input::read(cells.volumes, num_cells, 0.0, DBL_MAX, file), "wrong cell-volume data");
+      } else if (k == "cell-centroids") {
+         PAMPA_CHECK(line.size() != 2 || rows(num_cells), "wrong number of cell centroids");
+         PAMPA_CHECK(input::read(cells.centroids, num_cells, 3, -DBL_MAX, DBL_MAX, file), "wrong cell-centroid data");
+      } else if (k == "cell-materials") {
+         PAMPA_CHECK(line.size() != 2 || rows(num_cells), "wrong number of cell materials");
+         PAMPA_CHECK(input::read(cells.materials, num_cells, 1, INT_MAX, file), "wrong cell-material data");
+         for (int& m : cells.materials) m--;
+      } else if (k == "cell-nodal-indices" || k == "cell-global-indices") {
+         std::vector<int> v;
+         PAMPA_CHECK(line.size() != 2 || rows(num_cells), "wrong number of cell indices");
+         PAMPA_CHECK(input::read(v, num_cells, 0, INT_MAX, file), "wrong cell-index data");
+         if (k == "cell-global-indices") cells.global_indices = v;
+      } else if (k == "faces") {
+         PAMPA_CHECK(line.size() != 2 || rows(num_cells), "wrong number of cells");
+         PAMPA_CHECK(input::read(nfaces, num_cells, 1, INT_MAX, file), "wrong face data");
+         faces.ptr.assign(num_cells + 1, 0);
+         for (int i = 0; i < num_cells; i++) { faces.ptr[i + 1] = faces.ptr[i] + nfaces[i]; num_faces_max = std::max(num_faces_max, nfaces[i]); }
+         nf_total = faces.ptr[num_cells];
+      } else if (k == "face-areas") {
+         PAMPA_CHECK(line.size() != 3 || rows(num_cells) || nf_total == 0, "wrong number of face areas");
+         PAMPA_CHECK(input::read(faces.areas, nf_total, 0.0, DBL_MAX, file), "wrong face-area data");
+      } else if (k == "face-centroids" || k == "face-normals") {
+         PAMPA_CHECK(line.size() != 3 || rows(num_cells) || nf_total == 0, "wrong number of face vectors");
+         PAMPA_CHECK(input::read(k == "face-centroids" ? faces.centroids : faces.normals, nf_total, 3, -DBL_MAX, DBL_MAX, file),
+                     "wrong face-vector data");
+      } else if (k == "face-neighbors") {
+         PAMPA_CHECK(line.size() != 3 || rows(num_cells) || nf_total == 0, "wrong number of face neighbors");
+         PAMPA_CHECK(input::read(faces.neighbors, nf_total, -INT_MAX, INT_MAX, file), "wrong face-neighbor data");
+      } else if (k == "boundary") {
+         PAMPA_CHECK(line.size() != 2, "wrong number of arguments for keyword '" + k + "'");
+         boundaries.push_back(line[1]);
+      } else if (k == "bc") {
+         PAMPA_CHECK(readBC(line, file), "wrong boundary condition");
+      } else {
+         PAMPA_CHECK(true, "unrecognized keyword '" + k + "'");
+      }
+   }
+   return 0;
+}
+
+int PartitionedMesh::build() {
+   const size_t nf = faces.ptr.empty() ? 0 : (size_t)faces.ptr[num_cells];
+   PAMPA_CHECK(num_cells < 1 || (int)cells.volumes.size() != num_cells || cells.centroids.size() != 3 * (size_t)num_cells ||
+               (int)cells.materials.size() != num_cells || nf == 0 || faces.areas.size() != nf ||
+               faces.centroids.size() != 3 * nf || faces.normals.size() != 3 * nf || faces.neighbors.size() != nf,
+               "missing mesh data");
+   if (bcs.empty()) bcs.resize(1 + boundaries.size());
+   if (cells.global_indices.empty()) { cells.global_indices.resize(num_cells); for (int i = 0; i < num_cells; i++) cells.global_indices[i] = i; }
+   // extruded structure: cells whose -z face is a boundary (or that have no z faces at all) form the first layer,
+   // and cell i + num_xy_cells sits on top of cell i
+   auto zface = [&](int f) { return std::fabs(faces.normals[3 * (size_t)f + 2]) > 0.5; };
+   has_z_faces = false;
+   bool has_y = false;
+   for (size_t f = 0; f < nf; f++) { has_z_faces |= zface((int)f); has_y |= std::fabs(faces.normals[3 * f + 1]) > 0.5; }
+   num_dims = has_z_faces ? 3 : (has_y ? 2 : 1);
+   if (!has_z_faces) { num_xy_cells = num_cells; num_layers = 1; dz.clear(); return 0; }
+   num_xy_cells = 0;
+   for (int i = 0; i < num_cells; i++) {
+      bool bottom = false;
+      for (int f = faces.ptr[i]; f < faces.ptr[i + 1]; f++)
+         if (zface(f) && faces.normals[3 * (size_t)f + 2] < 0.0 && faces.neighbors[f] < 0) bottom = true;
+      if (!bottom) break;
+      num_xy_cells++;
+   }
+   PAMPA_CHECK(num_xy_cells < 1 || num_cells % num_xy_cells != 0, "the mesh is not an extruded mesh");
+   num_layers = num_cells / num_xy_cells;
+   dz.assign(num_layers, 0.0);
+   for (int k = 0; k < num_layers; k++)
+      for (int c = 0; c < num_xy_cells; c++) {
+         const int i = k * num_xy_cells + c;
+         double area_z = 0.0;
+         for (int f = faces.ptr[i]; f < faces.ptr[i + 1]; f++) {
+            if (!zface(f)) continue;
+            const bool up = faces.normals[3 * (size_t)f + 2] > 0.0;
+            const int want = up ? (k + 1 < num_layers ? i + num_xy_cells : -1) : (k > 0 ? i - num_xy_cells : -1);
+            PAMPA_CHECK(want >= 0 ? faces.neighbors[f] != want : faces.neighbors[f] >= 0, "the mesh is not an extruded mesh");
+            if (up) area_z = faces.areas[f];
+         }
+         PAMPA_CHECK(!(area_z > 0.0), "the mesh is not an extruded mesh");
+         const double h = cells.volumes[i] / area_z;
+         if (c == 0) dz[k] = h;
+         PAMPA_CHECK(std::fabs(h - dz[k]) > 1.0e-6 * dz[k], "the mesh is not an extruded mesh");
+      }
    return 0;
 }
 

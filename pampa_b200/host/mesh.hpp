@@ -4,6 +4,8 @@
 //   CartesianMesh               src/CartesianMesh.cxx:19-414  (face order -y,+x,+y,-x,-z,+z;
 //                               material 0 = void cell; boundary names -x,+x,-y,+y,-z,+z)
 //   UnstructuredExtrudedMesh    src/UnstructuredExtrudedMesh.cxx:19-364 (CCW polygons x layers)
+//   PartitionedMesh             src/PartitionedMesh.cxx:4-263 (the per-cell dump Mesh::writeData produces,
+//                               src/Mesh.cxx:408-569); whole-domain files only, see the class
 #pragma once
 
 #include "input.hpp"
@@ -49,6 +51,9 @@ class Mesh {
    const std::vector<int>& getCellPointPtr() const { return cell_point_ptr; }
    const std::vector<int>& getCellPoints() const { return cell_points; }
    int PAMPA_WARN_UNUSED writeVTK(const std::string& prefix, int n) const;
+   // every array of the mesh in the reference's plain-text format (src/Mesh.cxx:408-569, what `mesh partitioned`
+   // reads back); `digits` < 0 writes the reference's fixed 3 decimals, otherwise that many significant digits
+   int PAMPA_WARN_UNUSED writeData(const std::string& filename, int digits = 17) const;
    void addBoundary(const std::string& name) { boundaries.push_back(name); }
 
    // extruded structure (read-only accessors the reference keeps private:
@@ -99,6 +104,20 @@ class UnstructuredExtrudedMesh : public Mesh {
    std::vector<int> xy_cell_ptr, xy_cell_points;        // CCW point lists
    std::vector<std::string> xy_boundary_names;
    std::vector<std::vector<int>> xy_boundary_points;
+};
+
+// A mesh given cell by cell (volumes, centroids, face areas / centroids / normals / neighbours): the format the
+// reference writes for every rank of a domain-decomposed run and as mesh_data.pmp of any run.  This build does not
+// decompose the domain (the sweeps are sharded by angle set and energy group instead), so only whole-domain files
+// (no ghost cells) are accepted; the extruded structure the device layer needs -- cells ordered layer by layer,
+// z faces between consecutive layers -- is recovered from the face tables and checked.
+class PartitionedMesh : public Mesh {
+  public:
+   int PAMPA_WARN_UNUSED read(const std::string& filename) override;
+   int PAMPA_WARN_UNUSED build() override;
+
+  private:
+   int num_ghost_cells = 0, num_cells_global = 0;
 };
 
 }   // namespace pampa

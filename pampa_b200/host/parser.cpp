@@ -15,9 +15,7 @@ int Parser::read(const std::string& filename, Mesh** mesh, std::vector<Material*
          PAMPA_CHECK(line.size() != 3, "wrong number of arguments for keyword '" + k + "'");
          if (line[1] == "cartesian") *mesh = new CartesianMesh();
          else if (line[1] == "unstructured") *mesh = new UnstructuredExtrudedMesh();
-         else if (line[1] == "partitioned")
-            PAMPA_CHECK(true, "partitioned meshes belong to the reference's MPI domain decomposition, which this "
-                              "build replaces by angle/group sharding over GPUs: give the original mesh instead");
+         else if (line[1] == "partitioned") *mesh = new PartitionedMesh();   // whole-domain files only (mesh.hpp)
          else PAMPA_CHECK(true, "wrong mesh type");
          PAMPA_CHECK((*mesh)->read(line[2]), "unable to read the mesh from " + line[2]);
          PAMPA_CHECK((*mesh)->build(), "unable to build the mesh");

@@ -266,3 +266,42 @@ def test_host_fails_loudly_without_gpu(decks):
     r = subprocess.run([exe, "input.pmp"], cwd=os.path.join(decks, "slab_s2"), capture_output=True, text=True)
     assert r.returncode != 0
     assert "no CUDA device" in r.stdout and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.parametrize("case", ["slab_s2", "pwr_cartesian_s2", "pwr_unstructured_s2"])
+def test_partitioned_mesh_round_trip(decks, case, tmp_path):
+    """Mesh::writeData (src/Mesh.cxx:408-569) / `mesh partitioned` (src/PartitionedMesh.cxx:4-263): every array of a
+    mesh written in the reference's plain-text format and read back gives the same discrete mesh -- the digest of the
+    deck that points at the written file equals the digest of the original deck -- at full precision and, to the
+    three decimals it keeps, in the reference's own fixed format."""
+    import shutil
+    lib = ctypes.CDLL(os.path.join(ROOT, "pampa_b200", "lib", "libpampa.so"))
+    lib.pampa_debug_describe.restype = ctypes.c_int
+    lib.pampa_debug_describe.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
+    lib.pampa_debug_write_mesh_data.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    work = tmp_path / case
+    shutil.copytree(os.path.join(decks, case), work)
+    cwd = os.getcwd()
+    os.chdir(work)
+    try:
+        ref = (ctypes.c_double * 16)()
+        assert lib.pampa_debug_describe(b"input.pmp", ref) == 0
+        for digits, tol in ((17, 1e-13), (-1, 2e-3)):
+            assert lib.pampa_debug_write_mesh_data(b"input.pmp", b"mesh_data.pmp", digits) == 0
+            written = open("mesh_data.pmp").read()
+            assert written.startswith("points ") and "\ncells %d 0 %d\n" % (int(ref[0]), int(ref[0])) in written
+            text = open("input.pmp").read()
+            kind = "cartesian" if "mesh cartesian" in text else "unstructured"
+            open("input_part.pmp", "w").write(text.replace("mesh %s mesh.pmp" % kind, "mesh partitioned mesh_data.pmp"))
+            got = (ctypes.c_double * 16)()
+            assert lib.pampa_debug_describe(b"input_part.pmp", got) == 0
+            for a in range(16):
+                assert abs(got[a] - ref[a]) <= tol * max(1.0, abs(ref[a])), (digits, a, got[a], ref[a])
+        # one rank's part of a domain decomposition (ghost cells) is refused with an explanation
+        text = open("mesh_data.pmp").read()
+        n = int(ref[0])
+        open("mesh_ghost.pmp", "w").write(text.replace("cells %d 0 %d" % (n, n), "cells %d 3 %d" % (n, 2 * n)))
+        open("input_ghost.pmp", "w").write(open("input_part.pmp").read().replace("mesh_data.pmp", "mesh_ghost.pmp"))
+        assert lib.pampa_debug_describe(b"input_ghost.pmp", got) != 0
+    finally:
+        os.chdir(cwd)

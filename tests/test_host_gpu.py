@@ -223,3 +223,27 @@ def test_temperature_feedback(decks):
         lib.pampa_finalize_steady_state(ctypes.byref(err)); assert err.value == 0
     finally:
         os.chdir(cwd)
+
+
+@pytest.mark.parametrize("case", ["slab_s2", "pwr_cartesian_s2", "pwr_unstructured_s2"])
+def test_partitioned_mesh_solve(decks, case, tmp_path):
+    """`mesh partitioned <file>` on the whole-domain dump of a mesh (Mesh::writeData): the extruded structure is
+    recovered from the face tables and the solve prints the reference's golden for the original deck."""
+    import shutil
+    lib = ctypes.CDLL(os.path.join(ROOT, "pampa_b200", "lib", "libpampa.so"))
+    lib.pampa_debug_write_mesh_data.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    work = tmp_path / case
+    shutil.copytree(os.path.join(decks, case), work)
+    cwd = os.getcwd()
+    os.chdir(work)
+    try:
+        assert lib.pampa_debug_write_mesh_data(b"input.pmp", b"mesh_data.pmp", 17) == 0
+    finally:
+        os.chdir(cwd)
+    text = open(work / "input.pmp").read()
+    kind = "cartesian" if "mesh cartesian" in text else "unstructured"
+    open(work / "input.pmp", "w").write(text.replace("mesh %s mesh.pmp" % kind, "mesh partitioned mesh_data.pmp"))
+    exe = os.path.join(ROOT, "pampa_b200", "bin", "pampa")
+    r = subprocess.run([exe, "input.pmp"], cwd=work, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout == EXPECTED % CASES[case][0], r.stdout
