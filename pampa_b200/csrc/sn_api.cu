@@ -1170,6 +1170,7 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
       for (int j = 0; j < AA_SLOTS; j++) st0.age[j] = -1;
       st0.kn = h->sc.keff; st0.prod_x = h->sc.production; st0.best = 1.0e300; st0.inv = 1.0;
       st0.tol_k = tol_k; st0.tol_phi = tol_phi; st0.slots = slots;
+      st0.ncells = (double)pl.nxy * pl.nz * h->G;
       // the first iterations only settle k and the gross flux shape: mixing them in could slow the acceleration
       // down, so the history may start after `aa_start` plain steps (measured: no benefit at depth 7, default 0)
       { const char* e = std::getenv("PAMPA_SN_AA_START"); st0.aa_start = e ? std::atoi(e) : 0; }
@@ -1211,6 +1212,9 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
          if (it >= 2) {
             cudaEventSynchronize(ev[(it - 1) & 1]);
             const AAState& prev = h->h_aa_ring[(it - 1) & 1];
+            if (h->opts.verbose > 1)
+               std::printf("pampa_sn: it %d k %.12f dk %.3e res %.3e min phi %.3e negatives %d hold %d\n", prev.it, prev.kn,
+                           prev.dk, prev.res, prev.min_phi, prev.negatives, prev.hold);
             if (prev.failed) { failed = true; break; }
             if (prev.converged) { converged = true; break; }
          }

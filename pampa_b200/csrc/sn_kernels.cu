@@ -1738,7 +1738,14 @@ __global__ void sn_aa_solve_kernel(AAState* __restrict__ s, const double* __rest
    s->res = res; s->dk = dk;
    if (!(res == res)) { s->failed = 1; s->mix[cur] = 1.0; return; }
    double kn;
-   if (s->it > 1 && fabs(dk) < s->tol_k && res < s->tol_phi) {
+   // Every eigenvector with a non-zero production is a fixed point of the normalised map, and a quasi-Newton
+   // iteration can home in on any of them; the plain iteration cannot (it converges to the positive, dominant one).
+   // A sweep result with a negative flux well below rounding (seen on a core with reflective sides, where the
+   // first harmonics are close to the fundamental) means the mixed iterate has left the positive cone: drop the
+   // history and take a few plain steps before accelerating again.  Convergence is accepted from a positive state.
+   const bool negative = s->min_phi < -1.0e-12 * sqrt(s->phi2 * s->inv * s->inv / fmax(1.0, s->ncells));
+   if (negative) { s->hold = 8; s->negatives++; for (int j = 0; j < slots; j++) if (j != cur) s->age[j] = -1; s->best = 1.0e300; }
+   if (s->it > 1 && fabs(dk) < s->tol_k && res < s->tol_phi && !negative) {
       s->converged = 1;
       s->mix[cur] = 1.0; kn = s->kg[cur];
    } else {
@@ -1750,6 +1757,7 @@ __global__ void sn_aa_solve_kernel(AAState* __restrict__ s, const double* __rest
       double alpha[AA_SLOTS];
       for (int a = 0; a < slots; a++) { const int j = (cur - a + slots) % slots; if (s->age[j] >= 0) idx[n++] = j; }
       if (s->it < s->aa_start) n = 1;                   // plain step
+      if (s->hold > 0) { n = 1; s->hold--; s->age[cur] = -1; }   // (plain steps are not kept in the history either)
       while (n > 1 && !aa_weights(s->M, idx, n, alpha)) n--;
       if (n <= 1) { n = 1; alpha[0] = 1.0; }
       kn = 0.0;

@@ -162,9 +162,12 @@ struct AAState {
    double best, res, dk;           // smallest residual so far, last residual, last k change
    double power_integral, min_phi, phi2;
    double tol_k, tol_phi;
+   double ncells;                  // flux entries (cells x groups): scale of the negative-flux test
    int32_t age[AA_SLOTS];          // iteration that filled each slot (-1: empty)
    int32_t cur, slots, it, nvisit;
-   int32_t converged, failed, aa_start, pad_;
+   int32_t converged, failed, aa_start;
+   int32_t hold;                   // plain steps left after a sweep result with negative flux (see sn_aa_solve_kernel)
+   int32_t negatives, pad_[3];     // such events so far
 };
 // (every launcher below takes the device-resident AAState: slot, window and weights are read on the device)
 void launch_aa_begin(AAState* st_dev, const double* sums, cudaStream_t st);

@@ -9,7 +9,7 @@ bcs = {"-x": pb.BC_REFLECTIVE, "-y": pb.BC_REFLECTIVE}
 mesh, xs = syn.checkerboard_core(n, n, n, num_groups=8, bcs=bcs)
 quad = syn.level_symmetric(8)
 for depth in (0, 3, -1):
-    dev = pb.SNDevice(mesh, xs, quad, anderson_depth=depth, verbose=1)
+    dev = pb.SNDevice(mesh, xs, quad, anderson_depth=depth, verbose=2 if depth == 0 else 1)
     t0 = time.time()
     try:
         k, it = dev.solve_keff(tol_k=1e-10, tol_phi=1e-9)
