@@ -337,11 +337,18 @@ def run_b200(a, rank, world, local_rank):
     b_alg = 16.0 + 16.0 / M
     # the dominant kernel timed alone: CUDA events on the launching stream around the sweep-kernel
     # launches of every timed step (after the shear pass, before the un-shear pass)
-    kernel_ms = dev.info()["timed_kernel_ms"]
+    inf = dev.info()
+    kernel_ms = inf["timed_kernel_ms"]
+    phase = [inf["timed_source_ms"], sweep_ms, kernel_ms, inf["timed_reduce_ms"], inf["timed_exchange_ms"]]
     if dist is not None:
-        t = torch.tensor([kernel_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([kernel_ms] + phase, dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         kernel_ms = float(t[0])
+        phase = [float(x) for x in t[1:]]
+    # device time per step of each phase (CUDA events on the launching stream, max over the ranks)
+    step_phases_ms = {"source": phase[0] / a.steps, "shear + sweep + un-shear": phase[1] / a.steps,
+                      "sweep kernel alone": phase[2] / a.steps, "reduce + scalars + exchange": phase[3] / a.steps,
+                      "flux-moment exchange alone": phase[4] / a.steps}
     achieved = U_own * a.steps * b_alg / (kernel_ms * 1e-3) / 1e9
     achieved_sweep = U_own * a.steps * b_alg / (sweep_ms * 1e-3) / 1e9
     # DRAM bytes per launch from the committed ncu --set full capture of this very configuration (one GPU, default
@@ -453,7 +460,8 @@ def run_b200(a, rank, world, local_rank):
                 "config": {"workload": workload_name(a), "parallelism": "%s sharding x%d" % ("energy-group" if opts["shard_mode"] == 1 else "angle-set", world),
                            "l2_policy": "working set (%.1f GB) far exceeds the 126 MB L2" % (info0["device_bytes"] / 1e9),
                            "keff_after_steps": k, "options": json.loads(a.opts)},
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "keff_solve": keff_solve,
+                "roofline": roofline, "step_phases_ms": step_phases_ms, "cpu_baseline": cpu_baseline, "e2e": e2e,
+                "keff_solve": keff_solve,
                 "sharded_parity": parity,
                 "gpu_launches": launches,
                 "clocks": clocks}

@@ -210,6 +210,9 @@ typedef struct {
    int64_t flow_classes;             /* ordering classes the one-launch dataflow kernel can sweep */
    int64_t lattice;                  /* 1: unstructured mesh recognised as a lattice of congruent cells */
    double  last_solve_ms;            /* device time of the last pampa_sn_solve_keff (events on the launching stream) */
+   /* last pampa_sn_iterate_timed, summed over its iterations: the source kernel; everything after the sweep
+    * (reduction, scalar collective, k update, flux-moment exchange); the flux-moment exchange alone */
+   double  timed_source_ms, timed_reduce_ms, timed_exchange_ms;
 } pampa_sn_info;
 int pampa_sn_get_info(pampa_sn_handle* h, pampa_sn_info* info);
 

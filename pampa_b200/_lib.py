@@ -53,7 +53,8 @@ class Info(C.Structure):
                 ("sweep_launches", i64), ("sweep_tasks", i64), ("num_classes", i64), ("num_chunks", i64),
                 ("tile_classes", i64), ("device_bytes", i64), ("last_sweep_ms", f64), ("last_source_ms", f64),
                 ("last_reduce_ms", f64), ("kernel_launches", i64), ("timed_kernel_ms", f64), ("num_tilings", i64),
-                ("flow_classes", i64), ("lattice", i64), ("last_solve_ms", f64)]
+                ("flow_classes", i64), ("lattice", i64), ("last_solve_ms", f64),
+                ("timed_source_ms", f64), ("timed_reduce_ms", f64), ("timed_exchange_ms", f64)]
 
 
 # every symbol include/pampa_sn.h declares: name -> (restype, argtypes)

@@ -148,7 +148,8 @@ struct pampa_sn_handle {
    // pampa_sn_iterate_timed: events around the sweep-kernel launches alone (after the shear pass,
    // before the un-shear pass), one pair per iteration
    std::vector<cudaEvent_t>* kernel_events = nullptr;
-   double timed_kernel_ms = 0;
+   std::vector<cudaEvent_t>* exchange_events = nullptr;   // around the flux-moment allgather of a sharded run
+   double timed_kernel_ms = 0, timed_source_ms = 0, timed_reduce_ms = 0, timed_exchange_ms = 0;
    std::vector<double> h_temperature, h_delayed;
    NcclComm comm = nullptr;
 
@@ -473,7 +474,10 @@ int do_reduce(pampa_sn_handle* h, int update_k) {
    if (reduce_sums(h, 1)) return 1;
    launch_update_k(h->d_sums, h->d_sc, update_k, h->stream);
    h->launches++;
-   return gather_phi(h);
+   if (h->exchange_events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); h->exchange_events->push_back(e); }
+   const int rc = gather_phi(h);
+   if (h->exchange_events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); h->exchange_events->push_back(e); }
+   return rc;
 }
 
 int check_async(pampa_sn_handle* h, const char* what) {
@@ -1073,32 +1077,44 @@ int pampa_sn_iterate(pampa_sn_handle* h, int32_t iterations, double* keff) {
 int pampa_sn_iterate_timed(pampa_sn_handle* h, int32_t iterations, double* keff, double* total_ms,
                            double* sweep_ms) {
    SN_CUDA(h, cudaSetDevice(h->device));
-   std::vector<cudaEvent_t> ev(2 * (size_t)iterations + 2);
+   // per iteration: [start] source [a] sweep [b] reduce + exchange [c]
+   std::vector<cudaEvent_t> ev(3 * (size_t)iterations + 2);
    for (auto& e : ev) SN_CUDA(h, cudaEventCreate(&e));
    int rc = 0;
-   std::vector<cudaEvent_t> kev;
+   std::vector<cudaEvent_t> kev, xev;
    SN_CUDA(h, cudaStreamSynchronize(h->stream));
    h->kernel_events = &kev;
+   h->exchange_events = &xev;
    cudaEventRecord(ev[0], h->stream);
    for (int it = 0; it < iterations && !rc; it++) {
       rc = do_source(h);
-      cudaEventRecord(ev[2 + 2 * it], h->stream);
+      cudaEventRecord(ev[2 + 3 * it], h->stream);
       if (!rc) rc = do_sweep(h);
-      cudaEventRecord(ev[3 + 2 * it], h->stream);
+      cudaEventRecord(ev[3 + 3 * it], h->stream);
       if (!rc) rc = do_reduce(h, 1);
+      cudaEventRecord(ev[4 + 3 * it], h->stream);
    }
    cudaEventRecord(ev[1], h->stream);
    h->kernel_events = nullptr;
+   h->exchange_events = nullptr;
    if (!rc) rc = sync_scalars(h);
-   h->timed_kernel_ms = 0;
+   h->timed_kernel_ms = 0; h->timed_exchange_ms = 0; h->timed_source_ms = 0; h->timed_reduce_ms = 0;
    for (size_t i = 0; i + 1 < kev.size() && !rc; i += 2) {
       float t = 0; cudaEventElapsedTime(&t, kev[i], kev[i + 1]); h->timed_kernel_ms += t;
    }
+   for (size_t i = 0; i + 1 < xev.size() && !rc; i += 2) {
+      float t = 0; cudaEventElapsedTime(&t, xev[i], xev[i + 1]); h->timed_exchange_ms += t;
+   }
    for (auto& e : kev) cudaEventDestroy(e);
+   for (auto& e : xev) cudaEventDestroy(e);
    if (!rc) {
       float ms = 0, sw = 0, t = 0;
       cudaEventElapsedTime(&ms, ev[0], ev[1]);
-      for (int it = 0; it < iterations; it++) { cudaEventElapsedTime(&t, ev[2 + 2 * it], ev[3 + 2 * it]); sw += t; }
+      for (int it = 0; it < iterations; it++) {
+         cudaEventElapsedTime(&t, ev[2 + 3 * it], ev[3 + 3 * it]); sw += t;
+         cudaEventElapsedTime(&t, it == 0 ? ev[0] : ev[4 + 3 * (it - 1)], ev[2 + 3 * it]); h->timed_source_ms += t;
+         cudaEventElapsedTime(&t, ev[3 + 3 * it], ev[4 + 3 * it]); h->timed_reduce_ms += t;
+      }
       if (total_ms) *total_ms = ms;
       if (sweep_ms) *sweep_ms = sw;
       h->keff = h->sc.keff;
@@ -1486,6 +1502,8 @@ int pampa_sn_get_info(pampa_sn_handle* h, pampa_sn_info* info) {
    info->timed_kernel_ms = h->timed_kernel_ms;
    info->last_sweep_ms = h->last_sweep_ms; info->last_source_ms = h->last_source_ms;
    info->last_reduce_ms = h->last_reduce_ms; info->last_solve_ms = h->last_solve_ms;
+   info->timed_source_ms = h->timed_source_ms; info->timed_reduce_ms = h->timed_reduce_ms;
+   info->timed_exchange_ms = h->timed_exchange_ms;
    info->kernel_launches = h->launches;
    return 0;
 }
