@@ -65,6 +65,7 @@ struct pampa_sn_handle {
    cudaStream_t cls_stream[NSTREAMS] = {};
    cudaEvent_t ev_fork = nullptr, ev_join[NSTREAMS] = {};
    std::vector<void*> allocs;
+   std::vector<void*> ipc_mapped;        // peer buffers opened with cudaIpcOpenMemHandle
    int64_t device_bytes = 0;
    int64_t launches = 0;
 
@@ -94,6 +95,13 @@ struct pampa_sn_handle {
    double* d_stage = nullptr;           // device staging buffer of the field import / export calls
    int64_t stage_count = 0;
    bool group_gather = false;           // group-sharded run with the in-place allgather of phi
+   // peer-to-peer delivery of the flux moments (group-sharded runs, all ranks on one node): the iterate is
+   // double-buffered and the reduction pass stores the new slabs straight into the other buffer of every peer
+   bool p2p = false;
+   double* d_phi_buf[2] = {nullptr, nullptr};   // d_phi is d_phi_buf[phi_cur]
+   int phi_cur = 0;
+   double* peer_phi[2][PEER_MAX] = {};   // the two buffers of the other ranks (IPC mappings)
+   int npeers = 0;
    int nblocks_reduce = 0;
    ReduceScalars* d_sc = nullptr;
    ClassDev* d_classes = nullptr;
@@ -429,7 +437,7 @@ int exchange_boundaries(pampa_sn_handle* h) {
 //                        and the new phi is completed with an in-place allgather of the group slabs
 //                        (half the wire bytes of the allreduce, and source / reduce are sharded too).
 // exchange (sharded runs) + block reduction of the sweep result into d_sums[5]
-int reduce_sums(pampa_sn_handle* h, int rotate) {
+int reduce_sums(pampa_sn_handle* h, int rotate, bool* pushed = nullptr) {
    const Plan& pl = h->plan;
    const int64_t slab = (int64_t)pl.nz * pl.Sb;
    if (h->comm && !h->group_gather) {
@@ -438,8 +446,19 @@ int reduce_sums(pampa_sn_handle* h, int rotate) {
    }
    if (h->comm && exchange_boundaries(h)) return 1;
    const int owned_only = (h->comm && h->group_gather) ? 1 : 0;
-   launch_reduce(h->d_phi, h->d_phi_new, h->d_mats, h->d_nusf, h->d_kapsf, h->d_area, h->d_dz, pl.has_z, h->G,
-                 pl.nz, pl.Sb, h->d_gloc, owned_only, rotate, h->d_partials, h->nblocks_reduce, h->d_sums, h->stream);
+   if (pushed) *pushed = false;
+   if (owned_only && rotate && h->p2p && pushed) {
+      // reduction of the owned groups that also delivers them to every rank's other iterate buffer
+      const int out = 1 - h->phi_cur;
+      launch_reduce_push(h->d_phi, h->d_phi_new, h->d_phi_buf[out], h->peer_phi[out], h->npeers, h->d_mats, h->d_nusf,
+                         h->d_kapsf, h->d_area, h->d_dz, pl.has_z, h->G, pl.nz, pl.Sb, h->d_gloc, h->d_partials,
+                         h->nblocks_reduce, h->d_sums, h->stream);
+      h->phi_cur = out;
+      h->d_phi = h->d_phi_buf[out];
+      *pushed = true;
+   } else
+      launch_reduce(h->d_phi, h->d_phi_new, h->d_mats, h->d_nusf, h->d_kapsf, h->d_area, h->d_dz, pl.has_z, h->G,
+                    pl.nz, pl.Sb, h->d_gloc, owned_only, rotate, h->d_partials, h->nblocks_reduce, h->d_sums, h->stream);
    h->launches += 2;
    if (owned_only) {
       // one collective for the five scalars (four sums and a minimum): allgather, combined in rank order
@@ -471,11 +490,12 @@ int gather_phi(pampa_sn_handle* h) {
 //                        and the new phi is completed with an in-place allgather of the group slabs
 //                        (half the wire bytes of the allreduce, and source / reduce are sharded too).
 int do_reduce(pampa_sn_handle* h, int update_k) {
-   if (reduce_sums(h, 1)) return 1;
+   bool pushed = false;
+   if (reduce_sums(h, 1, &pushed)) return 1;
    launch_update_k(h->d_sums, h->d_sc, update_k, h->stream);
    h->launches++;
    if (h->exchange_events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); h->exchange_events->push_back(e); }
-   const int rc = gather_phi(h);
+   const int rc = pushed ? 0 : gather_phi(h);            // (pushed: the scalar collective was the barrier)
    if (h->exchange_events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); h->exchange_events->push_back(e); }
    return rc;
 }
@@ -656,6 +676,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       // flux arrays
       const int64_t nphi = (int64_t)h->G * nz * Sb;
       if (dev_alloc(h, &h->d_phi, nphi) || dev_alloc(h, &h->d_phi_new, nphi) || dev_alloc(h, &h->d_q, nphi)) return 1;
+      h->d_phi_buf[0] = h->d_phi; h->phi_cur = 0;
       int64_t psi_doubles = 0;
       std::vector<int64_t> psi_off(pl.chunks.size(), -1);
       for (size_t c = 0; c < pl.chunks.size(); c++)
@@ -976,6 +997,7 @@ int pampa_sn_destroy(pampa_sn_handle* h) {
    cudaSetDevice(h->device);
    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
    if (h->stream) cudaStreamSynchronize(h->stream);
+   for (void* p : h->ipc_mapped) cudaIpcCloseMemHandle(p);
    for (void* p : h->allocs) cudaFree(p);
    if (h->d_stage) cudaFree(h->d_stage);
    if (h->h_aa_ring) cudaFreeHost(h->h_aa_ring);
@@ -1473,6 +1495,58 @@ int pampa_sn_comm_init(pampa_sn_handle* h, const void* id, int32_t id_bytes) {
    int r = g_nccl.CommInitRank(&h->comm, h->opts.num_ranks, uid, h->opts.rank);
    if (r != 0) SN_FAIL(h, std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
    h->group_gather = h->opts.shard_mode == 1 && h->G % h->opts.num_ranks == 0;
+   // Peer-to-peer delivery of the flux moments: map the two iterate buffers of every other rank (CUDA IPC; the
+   // handles travel through an allgather on the new communicator).  Any failure -- ranks on different nodes, IPC
+   // not permitted, PAMPA_SN_NO_P2P=1 -- leaves the NCCL allgather in place, on every rank alike.
+   h->p2p = false;
+   if (h->group_gather && h->opts.num_ranks - 1 <= PEER_MAX && !std::getenv("PAMPA_SN_NO_P2P")) {
+      const int R = h->opts.num_ranks;
+      const int64_t nphi = (int64_t)h->G * h->plan.nz * h->plan.Sb;
+      if (!h->d_phi_buf[1]) {
+         if (dev_alloc(h, &h->d_phi_buf[1], nphi)) return 1;
+         SN_CUDA(h, cudaMemsetAsync(h->d_phi_buf[1], 0, (size_t)nphi * sizeof(double), h->stream));
+      }
+      struct Pack { cudaIpcMemHandle_t hnd[2]; int32_t ok; int32_t pad[15]; };
+      static_assert(sizeof(Pack) % 8 == 0, "pack size");
+      Pack mine;
+      std::memset(&mine, 0, sizeof(mine));
+      mine.ok = cudaIpcGetMemHandle(&mine.hnd[0], h->d_phi_buf[0]) == cudaSuccess &&
+                cudaIpcGetMemHandle(&mine.hnd[1], h->d_phi_buf[1]) == cudaSuccess;
+      cudaGetLastError();
+      Pack* d_all = nullptr;
+      std::vector<Pack> all(R);
+      SN_CUDA(h, cudaMalloc((void**)&d_all, sizeof(Pack) * R));
+      SN_CUDA(h, cudaMemcpyAsync(d_all + h->opts.rank, &mine, sizeof(Pack), cudaMemcpyHostToDevice, h->stream));
+      int rr = g_nccl.AllGather(d_all + h->opts.rank, d_all, sizeof(Pack) / 8, NCCL_FLOAT64, h->comm, h->stream);
+      if (rr != 0) { cudaFree(d_all); return nccl_fail(h, rr, "the allgather of the IPC handles"); }
+      SN_CUDA(h, cudaMemcpyAsync(all.data(), d_all, sizeof(Pack) * R, cudaMemcpyDeviceToHost, h->stream));
+      SN_CUDA(h, cudaStreamSynchronize(h->stream));
+      cudaFree(d_all);
+      bool ok = true;
+      for (int p = 0; p < R; p++) ok = ok && all[p].ok;
+      int np = 0;
+      for (int p = 0; p < R && ok; p++) {
+         if (p == h->opts.rank) continue;
+         for (int b = 0; b < 2 && ok; b++) {
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[p].hnd[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); }
+            else { h->peer_phi[b][np] = (double*)ptr; h->ipc_mapped.push_back(ptr); }
+         }
+         np++;
+      }
+      // every rank must take the same path: agree on success with a one-value collective
+      double flag = ok ? 1.0 : 0.0, *d_flag = nullptr;
+      SN_CUDA(h, cudaMalloc((void**)&d_flag, sizeof(double)));
+      SN_CUDA(h, cudaMemcpyAsync(d_flag, &flag, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      rr = g_nccl.AllReduce(d_flag, d_flag, 1, NCCL_FLOAT64, NCCL_MIN, h->comm, h->stream);
+      if (rr == 0) { cudaMemcpyAsync(&flag, d_flag, sizeof(double), cudaMemcpyDeviceToHost, h->stream); cudaStreamSynchronize(h->stream); }
+      cudaFree(d_flag);
+      if (rr != 0) return nccl_fail(h, rr, "the peer-access agreement");
+      h->p2p = flag > 0.5;
+      h->npeers = h->p2p ? R - 1 : 0;
+      if (h->opts.verbose) std::printf("pampa_sn: rank %d: flux-moment exchange by %s\n", h->opts.rank,
+                                       h->p2p ? "peer-to-peer stores fused into the reduction pass" : "NCCL allgather");
+   }
    return 0;
 }
 

@@ -1532,6 +1532,58 @@ sn_reduce_kernel(double* __restrict__ phi, double* __restrict__ phi_new,
       for (int j = 0; j < 5; j++) partials[(size_t)j * gridDim.x + blockIdx.x] = sh[j][0];
 }
 
+// Group-sharded runs with peer access: the reduction pass of the owned groups also delivers the new flux moments
+// -- into the other buffer of this rank (the iterate is double-buffered: an iteration reads one buffer and
+// everybody writes the other, so a fast peer can never overwrite what a slow rank still reads) and, with plain
+// stores over NVLink, into that buffer of every peer.  The exchange rides on a pass that has to stream the slab
+// anyway, and the separate allgather disappears; the scalar collective that follows is the barrier after which the
+// buffer is complete on every rank.
+struct PeerPhi { double* p[PEER_MAX]; };
+__global__ void __launch_bounds__(256)
+sn_reduce_push_kernel(const double* __restrict__ phi, double* __restrict__ phi_new, double* __restrict__ phi_out,
+                      PeerPhi peers, int npeers, const int32_t* __restrict__ mats, const double* __restrict__ nusf,
+                      const double* __restrict__ kapsf, const double* __restrict__ area,
+                      const double* __restrict__ dz, int has_z, int G, int nz, int64_t Sb,
+                      const int32_t* __restrict__ gloc, double* __restrict__ partials) {
+   const int64_t n = (int64_t)nz * Sb;
+   double prod = 0.0, pow_ = 0.0, d2 = 0.0, p2 = 0.0, mn = 1.0e300;
+   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+        idx += (int64_t)gridDim.x * blockDim.x) {
+      const int mat = mats[idx];
+      const int k = (int)(idx / Sb);
+      const double vol = mat < 0 ? 0.0 : area[idx - (int64_t)k * Sb] * (has_z ? dz[k] : 1.0);
+      for (int g = 0; g < G; g++) {
+         if (gloc[g] < 0) continue;
+         const int64_t a = (int64_t)g * n + idx;
+         const double pn = mat < 0 ? 0.0 : phi_new[a], po = mat < 0 ? 0.0 : phi[a];
+         phi_out[a] = pn;                                  // holes carry zeros everywhere
+#pragma unroll
+         for (int r = 0; r < PEER_MAX; r++) if (r < npeers) __stcs(peers.p[r] + a, pn);
+         if (mat < 0) continue;
+         phi_new[a] = 0.0;
+         prod = fma(vol * nusf[mat * G + g], pn, prod);
+         pow_ = fma(vol * kapsf[mat * G + g], pn, pow_);
+         d2 = fma(pn - po, pn - po, d2);
+         p2 = fma(pn, pn, p2);
+         mn = fmin(mn, pn);
+      }
+   }
+   __threadfence_system();                                 // peer stores performed before the kernel ends
+   __shared__ double sh[5][256];
+   sh[0][threadIdx.x] = prod; sh[1][threadIdx.x] = pow_; sh[2][threadIdx.x] = d2;
+   sh[3][threadIdx.x] = p2; sh[4][threadIdx.x] = mn;
+   __syncthreads();
+   for (int off = 128; off > 0; off >>= 1) {
+      if ((int)threadIdx.x < off) {
+         for (int j = 0; j < 4; j++) sh[j][threadIdx.x] += sh[j][threadIdx.x + off];
+         sh[4][threadIdx.x] = fmin(sh[4][threadIdx.x], sh[4][threadIdx.x + off]);
+      }
+      __syncthreads();
+   }
+   if (threadIdx.x == 0)
+      for (int j = 0; j < 5; j++) partials[(size_t)j * gridDim.x + blockIdx.x] = sh[j][0];
+}
+
 // Deterministic final sum of the block partials into sums[5] = {production, power, ||dphi||^2,
 // ||phi||^2, min phi}; group-sharded runs allreduce sums before the k update.
 __global__ void sn_reduce_final_kernel(const double* __restrict__ partials, int nblocks, double* sums) {
@@ -1590,6 +1642,17 @@ void launch_reduce(double* phi, double* phi_new, const int32_t* mats, const doub
                    int nblocks, double* sums, cudaStream_t st) {
    sn_reduce_kernel<<<nblocks, 256, 0, st>>>(phi, phi_new, mats, nusf, kapsf, area, dz, has_z, G,
                                              nz, Sb, gloc, owned_only, rotate, partials);
+   sn_reduce_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, sums);
+}
+
+void launch_reduce_push(const double* phi, double* phi_new, double* phi_out, double* const* peer_out, int npeers,
+                        const int32_t* mats, const double* nusf, const double* kapsf, const double* area,
+                        const double* dz, int has_z, int G, int nz, int64_t Sb, const int32_t* gloc, double* partials,
+                        int nblocks, double* sums, cudaStream_t st) {
+   PeerPhi pp{};
+   for (int r = 0; r < PEER_MAX; r++) pp.p[r] = r < npeers ? peer_out[r] : nullptr;
+   sn_reduce_push_kernel<<<nblocks, 256, 0, st>>>(phi, phi_new, phi_out, pp, npeers, mats, nusf, kapsf, area, dz, has_z,
+                                                  G, nz, Sb, gloc, partials);
    sn_reduce_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, sums);
 }
 

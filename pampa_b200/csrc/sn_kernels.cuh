@@ -147,6 +147,13 @@ void launch_reduce(double* phi, double* phi_new, const int32_t* mats, const doub
                    const double* kapsf, const double* area, const double* dz, int has_z, int G,
                    int nz, int64_t Sb, const int32_t* gloc, int owned_only, int rotate, double* partials,
                    int nblocks, double* sums, cudaStream_t st);
+// group-sharded runs with peer access: reduction of the owned groups + delivery of the new flux moments into the
+// other iterate buffer of this rank (phi_out) and of every peer (peer_out[0 .. npeers)), see sn_kernels.cu
+constexpr int PEER_MAX = 7;
+void launch_reduce_push(const double* phi, double* phi_new, double* phi_out, double* const* peer_out, int npeers,
+                        const int32_t* mats, const double* nusf, const double* kapsf, const double* area,
+                        const double* dz, int has_z, int G, int nz, int64_t Sb, const int32_t* gloc, double* partials,
+                        int nblocks, double* sums, cudaStream_t st);
 // Anderson acceleration (history of up to 8 iterates, see sn_api.cu: pampa_sn_solve_keff)
 constexpr int AA_SLOTS = 8;
 // The whole bookkeeping of the accelerated iteration lives on the device, so that pampa_sn_solve_keff enqueues
