@@ -1238,12 +1238,20 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
             if (r != 0) { rc = nccl_fail(h, r, "the Anderson allreduce"); break; }
          }
          launch_aa_solve(h->d_aa_state, h->d_aa_dots, h->d_sc, h->stream);
-         launch_aa_mix(h->d_phi, h->d_mats, h->d_gloc, owned_only, h->G, nslab, gptr, h->d_aa_state, h->nblocks_reduce,
-                       h->stream);
+         // group-sharded with peer access: the next iterate goes into the other buffer here and on every peer
+         // (the mix pass stores it), and a one-value collective is the barrier before anybody reads it
+         const bool push = owned_only && h->p2p;
+         const int out = push ? 1 - h->phi_cur : h->phi_cur;
+         launch_aa_mix(h->d_phi_buf[out], h->d_mats, h->d_gloc, owned_only, h->G, nslab, gptr, h->d_aa_state,
+                       h->nblocks_reduce, push ? h->peer_phi[out] : nullptr, h->npeers, h->stream);
+         if (push) { h->phi_cur = out; h->d_phi = h->d_phi_buf[out]; }
          h->launches += 2;
          if (h->bnd_count > 0) launch_vec_mix(h->d_bnd[h->bnd_cur], bptr, h->d_aa_state, h->bnd_count, h->stream);
          if (h->bndz_count > 0) launch_vec_mix(h->d_bndz[h->bnd_cur], bzptr, h->d_aa_state, h->bndz_count, h->stream);
-         if ((rc = gather_phi(h))) break;
+         if (push) {
+            int r = g_nccl.AllReduce(h->d_aa_dots, h->d_aa_dots, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);   // barrier
+            if (r != 0) { rc = nccl_fail(h, r, "the barrier after the peer-to-peer exchange"); break; }
+         } else if ((rc = gather_phi(h))) break;
          // snapshot of the state after this iteration; looked at one iteration later
          cudaMemcpyAsync(&h->h_aa_ring[it & 1], h->d_aa_state, sizeof(AAState), cudaMemcpyDeviceToHost, h->stream);
          cudaEventRecord(ev[it & 1], h->stream);

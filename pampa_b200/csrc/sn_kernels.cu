@@ -1834,10 +1834,12 @@ void launch_aa_solve(AAState* st_dev, const double* dots, ReduceScalars* sc, cud
    sn_aa_solve_kernel<<<1, 32, 0, st>>>(st_dev, dots, sc);
 }
 
-// x_next = sum_j alpha_j g_j  (sum alpha = 1, so the production of x_next is that of the iterates)
+// x_next = sum_j alpha_j g_j  (sum alpha = 1, so the production of x_next is that of the iterates); group-sharded
+// runs with peer access store it into the same buffer of every peer as well (npeers > 0, see sn_reduce_push_kernel)
 __global__ void __launch_bounds__(256)
 sn_aa_mix_kernel(double* __restrict__ phi, const int32_t* __restrict__ mats, const int32_t* __restrict__ gloc,
-                 int owned_only, int G, int64_t n, AAHist hist, const AAState* __restrict__ state) {
+                 int owned_only, int G, int64_t n, AAHist hist, const AAState* __restrict__ state, PeerPhi peers,
+                 int npeers) {
    double alpha[AA_MAX];
 #pragma unroll
    for (int j = 0; j < AA_MAX; j++) alpha[j] = state->mix[j];
@@ -1852,8 +1854,11 @@ sn_aa_mix_kernel(double* __restrict__ phi, const int32_t* __restrict__ mats, con
          for (int j = 0; j < AA_MAX; j++)
             if (alpha[j] != 0.0) v = fma(alpha[j], hist.g[j][a], v);
          phi[a] = v;
+#pragma unroll
+         for (int r = 0; r < PEER_MAX; r++) if (r < npeers) __stcs(peers.p[r] + a, v);
       }
    }
+   if (npeers > 0) __threadfence_system();
 }
 
 // plain vector helpers for the boundary-flux part of the Anderson state
@@ -1901,10 +1906,13 @@ void launch_aa_store(const double* phi, double* phi_new, const int32_t* gloc, in
 }
 
 void launch_aa_mix(double* phi, const int32_t* mats, const int32_t* gloc, int owned_only, int G, int64_t n,
-                   double* const* hist_g, const AAState* st_dev, int nblocks, cudaStream_t st) {
+                   double* const* hist_g, const AAState* st_dev, int nblocks, double* const* peer_out, int npeers,
+                   cudaStream_t st) {
    AAHist h{};
    for (int j = 0; j < AA_MAX; j++) { h.f[j] = nullptr; h.g[j] = hist_g[j]; }
-   sn_aa_mix_kernel<<<nblocks, 256, 0, st>>>(phi, mats, gloc, owned_only, G, n, h, st_dev);
+   PeerPhi pp{};
+   for (int r = 0; r < PEER_MAX; r++) pp.p[r] = (peer_out && r < npeers) ? peer_out[r] : nullptr;
+   sn_aa_mix_kernel<<<nblocks, 256, 0, st>>>(phi, mats, gloc, owned_only, G, n, h, st_dev, pp, peer_out ? npeers : 0);
 }
 
 // ------------------------------------------------------------------------------------ LS term

@@ -185,7 +185,8 @@ void launch_aa_solve(AAState* st_dev, const double* dots, ReduceScalars* sc, cud
 void launch_scale_copy_slot(double* const* hist, const double* src, const AAState* st_dev, int64_t n, cudaStream_t st);
 void launch_vec_mix(double* out, double* const* hist, const AAState* st_dev, int64_t n, cudaStream_t st);
 void launch_aa_mix(double* phi, const int32_t* mats, const int32_t* gloc, int owned_only, int G, int64_t n,
-                   double* const* hist_g, const AAState* st_dev, int nblocks, cudaStream_t st);
+                   double* const* hist_g, const AAState* st_dev, int nblocks, double* const* peer_out, int npeers,
+                   cudaStream_t st);   // peer_out: the same iterate buffer of the other ranks (nullptr: none)
 void launch_update_k(const double* sums, ReduceScalars* sc, int update_k, cudaStream_t st);
 void launch_combine_sums(const double* all, int nranks, double* sums, cudaStream_t st);   // [rank][5] -> [5]
 

@@ -57,13 +57,12 @@ def main():
     ref = None
     if rank == 0:
         one = pb.SNDevice(mesh, xs, quad, device=local)
+        # a few plain source iterations from a given iterate on the fresh handle: the path the benchmark times (in a
+        # group-sharded run the reduction pass delivers the flux moments to the peers itself, peer-to-peer)
+        one.set("flux-moments", np.linspace(0.5, 1.5, mesh.num_cells * G))
+        plain = [one.iterate(5), one.get("flux-moments")]
         k1, it1 = one.solve_keff(tol_k=1e-11, tol_phi=1e-9)
-        ref = [k1, one.get("scalar-flux"), one.get("power")]
-        # a few plain source iterations from a perturbed iterate: the path the benchmark times (in a group-sharded
-        # run the reduction pass delivers the flux moments to the peers itself, peer-to-peer)
-        start = np.linspace(0.5, 1.5, mesh.num_cells * G)
-        one.set("flux-moments", start)
-        ref += [one.iterate(5), one.get("flux-moments")]
+        ref = [k1, one.get("scalar-flux"), one.get("power")] + plain
         one.close()
     dev = pb.SNDevice(mesh, xs, quad, device=local, rank=rank, num_ranks=world, shard_mode=a.shard_mode)
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -71,20 +70,20 @@ def main():
         uid.copy_(torch.frombuffer(bytearray(pb.nccl_unique_id()), dtype=torch.uint8))
     dist.broadcast(uid, 0)
     dev.comm_init(bytes(uid.cpu().numpy().tobytes()))
+    dev.set("flux-moments", np.linspace(0.5, 1.5, mesh.num_cells * G))
+    kp = dev.iterate(5)
+    phip = dev.get("flux-moments")
     k, it = dev.solve_keff(tol_k=1e-11, tol_phi=1e-9)
     phi, q = dev.get("scalar-flux"), dev.get("power")
     ks = torch.tensor([k], dtype=torch.float64, device="cuda")
     dist.all_reduce(ks, op=dist.ReduceOp.MAX)
     assert abs(float(ks[0]) - k) < 1e-14          # every rank holds the same k
-    dev.set("flux-moments", np.linspace(0.5, 1.5, mesh.num_cells * G))
-    kp = dev.iterate(5)
-    phip = dev.get("flux-moments")
     if rank == 0:
         assert abs(k - ref[0]) < 1e-9, (k, ref[0])
         assert np.linalg.norm(phi - ref[1]) / np.linalg.norm(ref[1]) < 1e-7
         assert np.linalg.norm(q - ref[2]) / np.linalg.norm(ref[2]) < 1e-7
-        assert abs(kp - ref[3]) < 1e-12 * abs(ref[3]), (kp, ref[3])
-        assert np.linalg.norm(phip - ref[4]) / np.linalg.norm(ref[4]) < 1e-12
+        assert abs(kp - ref[3]) < 1e-11 * abs(ref[3]), (kp, ref[3])
+        assert np.linalg.norm(phip - ref[4]) / np.linalg.norm(ref[4]) < 1e-11
         print("NCCL_OK keff %.9f iterations %d (1 GPU: %.9f)" % (k, it, ref[0]))
     dev.close()
     dist.destroy_process_group()
