@@ -98,6 +98,9 @@ struct pampa_sn_handle {
    // peer-to-peer delivery of the flux moments (group-sharded runs, all ranks on one node): the iterate is
    // double-buffered and the reduction pass stores the new slabs straight into the other buffer of every peer
    bool p2p = false;
+   bool fuse_next = false;               // the next sweep may fuse the reduction into its un-shear pass
+   bool fused_done = false;              // ... and did: d_sums holds this rank's sums, the iterate buffers are swapped
+   double* d_fuse_partials = nullptr;    // [5][npatch_b * G]
    double* d_phi_buf[2] = {nullptr, nullptr};   // d_phi is d_phi_buf[phi_cur]
    int phi_cur = 0;
    double* peer_phi[2][PEER_MAX] = {};   // the two buffers of the other ranks (IPC mappings)
@@ -182,6 +185,7 @@ struct pampa_sn_handle {
    int bcz_refl[2] = {0, 0};
    int uniform_dz = 1;
    int np_stride = 0;                    // patches per (chunk, block) in the dataflow progress counters
+   int unshear_last_zpass = 0;           // z direction of the un-shear pass that completes a column
 };
 
 #define SN_FAIL(h, msg) do { (h)->err = (msg); return 1; } while (0)
@@ -356,6 +360,22 @@ int sweep_launches(pampa_sn_handle* h) {
    if (h->kernel_events) {
       cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); h->kernel_events->push_back(e);
    }
+   // Fused tail of the iteration (plain source iterations, every class on the base tiling's dataflow kernel, one GPU
+   // or a group-sharded run with peer access): the un-shear pass also reduces and delivers the new flux moments.
+   const bool sharded_ok = h->opts.num_ranks == 1 || (h->comm && h->group_gather && h->p2p);
+   if (h->fuse_next && sharded_ok && h->groups_generic == 0 && h->tilings.size() == 1 && h->tilings[0].nchunks > 0 &&
+       h->d_phi_buf[1] && h->d_fuse_partials && !std::getenv("PAMPA_SN_NO_FUSE")) {
+      const TilingDev& tg = h->tilings[0];
+      const int out = 1 - h->phi_cur;
+      launch_unshear_phi_fused(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.npatch, 1, h->unshear_last_zpass,
+                               h->d_phi, h->d_phi_buf[out], h->peer_phi[out], h->npeers, h->d_mats, h->d_nusf, h->d_kapsf,
+                               h->d_area, h->d_dz, h->plan.has_z, h->d_fuse_partials, h->d_sums, h->stream);
+      h->launches += 2;
+      h->phi_cur = out;
+      h->d_phi = h->d_phi_buf[out];
+      h->fused_done = true;
+      return 0;
+   }
    // every owned chunk on the tile kernels: nothing else adds to phi_new, the first pass may overwrite it
    bool overwrite = h->groups_generic == 0;
    for (const TilingDev& tg : h->tilings)
@@ -372,8 +392,10 @@ int sweep_launches(pampa_sn_handle* h) {
 // and kernel variant, thousands per sweep) are launch-bound, so their sequence -- fixed for the life of the
 // handle but for the two boundary buffers that alternate -- is captured once per buffer parity into a CUDA
 // graph, fork / join over the class streams included, and replayed.
-int do_sweep(pampa_sn_handle* h) {
+int do_sweep(pampa_sn_handle* h, bool fuse = false) {
    const bool graphed = h->use_graph && !h->graph_failed;
+   h->fuse_next = fuse && !graphed;
+   h->fused_done = false;
    if (!graphed) {
       if (sweep_launches(h)) return 1;
    } else {
@@ -437,17 +459,25 @@ int exchange_boundaries(pampa_sn_handle* h) {
 //                        and the new phi is completed with an in-place allgather of the group slabs
 //                        (half the wire bytes of the allreduce, and source / reduce are sharded too).
 // exchange (sharded runs) + block reduction of the sweep result into d_sums[5]
-int reduce_sums(pampa_sn_handle* h, int rotate, bool* pushed = nullptr) {
+// after_sweep = false: phi_new holds a field every rank already has in full (pampa_sn_set), not this rank's share of
+// a sweep, so the angle-set allreduce of phi_new and of the boundary fluxes must not run (they would multiply by
+// the number of ranks)
+int reduce_sums(pampa_sn_handle* h, int rotate, bool* pushed = nullptr, bool after_sweep = true) {
    const Plan& pl = h->plan;
    const int64_t slab = (int64_t)pl.nz * pl.Sb;
-   if (h->comm && !h->group_gather) {
+   if (h->comm && !h->group_gather && after_sweep) {
       int r = g_nccl.AllReduce(h->d_phi_new, h->d_phi_new, (size_t)(h->G * slab), NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
       if (r != 0) return nccl_fail(h, r, "the flux-moment allreduce");
    }
-   if (h->comm && exchange_boundaries(h)) return 1;
+   if (h->comm && after_sweep && exchange_boundaries(h)) return 1;
    const int owned_only = (h->comm && h->group_gather) ? 1 : 0;
    if (pushed) *pushed = false;
-   if (owned_only && rotate && h->p2p && pushed) {
+   if (h->fused_done) {
+      // the sweep's un-shear pass already reduced (d_sums) and delivered the flux moments (buffers swapped)
+      h->fused_done = false;
+      if (!rotate || !pushed) SN_FAIL(h, "internal: fused sweep followed by a non-rotating reduction");
+      *pushed = true;
+   } else if (owned_only && rotate && h->p2p && pushed) {
       // reduction of the owned groups that also delivers them to every rank's other iterate buffer
       const int out = 1 - h->phi_cur;
       launch_reduce_push(h->d_phi, h->d_phi_new, h->d_phi_buf[out], h->peer_phi[out], h->npeers, h->d_mats, h->d_nusf,
@@ -456,10 +486,12 @@ int reduce_sums(pampa_sn_handle* h, int rotate, bool* pushed = nullptr) {
       h->phi_cur = out;
       h->d_phi = h->d_phi_buf[out];
       *pushed = true;
-   } else
+      h->launches += 2;
+   } else {
       launch_reduce(h->d_phi, h->d_phi_new, h->d_mats, h->d_nusf, h->d_kapsf, h->d_area, h->d_dz, pl.has_z, h->G,
                     pl.nz, pl.Sb, h->d_gloc, owned_only, rotate, h->d_partials, h->nblocks_reduce, h->d_sums, h->stream);
-   h->launches += 2;
+      h->launches += 2;
+   }
    if (owned_only) {
       // one collective for the five scalars (four sums and a minimum): allgather, combined in rank order
       int r = g_nccl.AllGather(h->d_sums, h->d_sums_all, 5, NCCL_FLOAT64, h->comm, h->stream);
@@ -489,9 +521,9 @@ int gather_phi(pampa_sn_handle* h) {
 //  * group sharding:     every rank reduces the groups it swept, the five scalars are allreduced,
 //                        and the new phi is completed with an in-place allgather of the group slabs
 //                        (half the wire bytes of the allreduce, and source / reduce are sharded too).
-int do_reduce(pampa_sn_handle* h, int update_k) {
+int do_reduce(pampa_sn_handle* h, int update_k, bool after_sweep = true) {
    bool pushed = false;
-   if (reduce_sums(h, 1, &pushed)) return 1;
+   if (reduce_sums(h, 1, &pushed, after_sweep)) return 1;
    launch_update_k(h->d_sums, h->d_sc, update_k, h->stream);
    h->launches++;
    if (h->exchange_events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); h->exchange_events->push_back(e); }
@@ -971,6 +1003,18 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       // stay independent within a sweep; streams are used unless the option turns them off
       h->multi_stream = (pl.classes.size() > 1 || h->flows.size() > 1) && !h->opts.single_stream;
 
+      // fused tail of the iteration: second iterate buffer (one GPU: here; sharded: pampa_sn_comm_init) and the
+      // partials of the un-shear CTAs
+      h->unshear_last_zpass = 0;
+      for (int32_t c : fast_chunks) if (pl.classes[pl.chunks[c].cls].zdir < 0) h->unshear_last_zpass = 1;
+      if (h->groups_generic == 0 && pl.tilings.size() == 1 && !fast_chunks.empty()) {
+         if (dev_alloc(h, &h->d_fuse_partials, 5LL * pl.npatch_b * h->G)) return 1;
+         if (h->opts.num_ranks == 1) {
+            if (dev_alloc(h, &h->d_phi_buf[1], nphi)) return 1;
+            SN_CUDA(h, cudaMemsetAsync(h->d_phi_buf[1], 0, (size_t)nphi * sizeof(double), h->stream));
+         }
+      }
+
       // reduction scratch and iteration state
       h->nblocks_reduce = (int)std::min<int64_t>(((int64_t)nz * Sb + 255) / 256, 148 * 8);
       if (dev_alloc(h, &h->d_partials, 5LL * h->nblocks_reduce) || dev_alloc(h, &h->d_sc, 1) ||
@@ -1088,7 +1132,7 @@ int pampa_sn_reduce(pampa_sn_handle* h, double* production, double* power, doubl
 int pampa_sn_iterate(pampa_sn_handle* h, int32_t iterations, double* keff) {
    SN_CUDA(h, cudaSetDevice(h->device));
    for (int it = 0; it < iterations; it++) {
-      if (do_source(h) || do_sweep(h) || do_reduce(h, 1)) return 1;
+      if (do_source(h) || do_sweep(h, true) || do_reduce(h, 1)) return 1;
    }
    if (sync_scalars(h)) return 1;
    h->keff = h->sc.keff;
@@ -1111,7 +1155,7 @@ int pampa_sn_iterate_timed(pampa_sn_handle* h, int32_t iterations, double* keff,
    for (int it = 0; it < iterations && !rc; it++) {
       rc = do_source(h);
       cudaEventRecord(ev[2 + 3 * it], h->stream);
-      if (!rc) rc = do_sweep(h);
+      if (!rc) rc = do_sweep(h, true);
       cudaEventRecord(ev[3 + 3 * it], h->stream);
       if (!rc) rc = do_reduce(h, 1);
       cudaEventRecord(ev[4 + 3 * it], h->stream);
@@ -1171,7 +1215,7 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
    // plain power iteration; the convergence test reads the scalars of iteration i while i + 1 is in the queue
    auto plain_iteration = [&]() -> int {
       while (it < max_it) {
-         if (do_source(h) || do_sweep(h) || do_reduce(h, 1)) return 1;
+         if (do_source(h) || do_sweep(h, true) || do_reduce(h, 1)) return 1;
          it++;
          if (sync_scalars(h)) return 1;
          const double dphi = h->sc.phi2 > 0 ? std::sqrt(h->sc.dphi2 / h->sc.phi2) : 0.0;
@@ -1284,7 +1328,7 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
          const double one = 1.0;
          SN_CUDA(h, cudaMemcpyAsync(&h->d_sc->keff, &one, sizeof(double), cudaMemcpyHostToDevice, h->stream));
          SN_CUDA(h, cudaStreamSynchronize(h->stream));
-         if (do_reduce(h, 0)) return 1;
+         if (do_reduce(h, 0, false)) return 1;
          if (plain_iteration()) return 1;
       } else if (it > 0) {
          const AAState& last = h->h_aa_ring[it & 1];     // the state the device fields are in
@@ -1298,7 +1342,7 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
          // a few unaccelerated iterations remove the undershoot (the reference rejects any negative flux,
          // src/NeutronicSolver.cxx:67).
          for (int polish = 0; converged && min_phi < 0.0 && polish < 200 && it < max_it; polish++) {
-            if (do_source(h) || do_sweep(h) || do_reduce(h, 1)) return 1;
+            if (do_source(h) || do_sweep(h, true) || do_reduce(h, 1)) return 1;
             it++;
             if (sync_scalars(h)) return 1;
             power_integral = h->sc.power; min_phi = h->sc.min_phi;
@@ -1481,7 +1525,7 @@ int pampa_sn_set(pampa_sn_handle* h, const char* name, const double* in) {
          cudaMemcpyAsync(d_in, in, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->stream);
       cudaMemsetAsync(h->d_phi, 0, (size_t)h->G * h->plan.nz * h->plan.Sb * sizeof(double), h->stream);
       launch_import_phi(h->d_phi_new, h->d_slot_of_xy, h->G, h->plan.nz, h->plan.nxy, h->plan.Sb, d_in, h->stream);
-      if (do_reduce(h, 0)) return 1;
+      if (do_reduce(h, 0, false)) return 1;
       if (sync_scalars(h)) return 1;
       return check_async(h, "field import");
    }

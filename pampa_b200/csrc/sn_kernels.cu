@@ -1316,16 +1316,39 @@ void launch_shear_q(const SweepGlobals& gp, const ClassDev* d_classes, const int
                                                                          npatch_b, cell_of);
 }
 
+__global__ void sn_reduce_final_kernel(const double* __restrict__ partials, int nblocks, double* sums);
+
 // phi_new[g][k][slot] += sum over the fast chunks of their step-major partial moments (streamed the
 // same way: a layer of a column is complete once every class's level has passed it).  The chunk rows
 // of two consecutive steps are loaded into registers before the shared-memory accumulation so that
 // 2 x UNSHEAR_NC independent global loads are in flight per thread.
 constexpr int UNSHEAR_NC = 8;
+struct PeerPhi { double* p[PEER_MAX]; };
 
+// FUSED: the last pass of the kernel holds the final flux moments of a (patch, group) column in registers, so it
+// also does what the reduction pass would do next -- production / power integrals, flux-change norms, minimum --
+// and delivers the value: into the other iterate buffer of this rank and, in a group-sharded run with peer access,
+// into that buffer of every other rank with plain stores over NVLink.  The transfer then overlaps the HBM reads of
+// the partial-moment rows, tile by tile, instead of following the pass as a collective.
+struct UnshearFuse {
+   const double* phi_old;        // current iterate (read for the flux-change norm)
+   double* phi_out;              // other iterate buffer of this rank
+   PeerPhi peers;                // ... of the other ranks
+   int npeers;
+   const int32_t* mats;          // [nz][Sb]
+   const double *nusf, *kapsf;   // [mat][G]
+   const double *area, *dz;
+   int has_z;
+   int last_zpass, last_c0;      // the pass that completes the column
+   double* partials;             // [5][gridDim.x]
+};
+
+template <bool FUSED>
 __global__ void __launch_bounds__(PS)
 sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks,
                       const ClassDev* __restrict__ classes, const int32_t* __restrict__ fast_chunks,
-                      int nfast, int npatch_b, int overwrite_first, const int32_t* __restrict__ cell_of) {
+                      int nfast, int npatch_b, int overwrite_first, const int32_t* __restrict__ cell_of,
+                      const UnshearFuse fz) {
    extern __shared__ __align__(16) unsigned char shear_raw[];
    double (*ring)[PS] = reinterpret_cast<double (*)[PS]>(shear_raw);      // [SHEAR_RING][PS]
    bool overwrite = overwrite_first != 0;   // phi_new holds nothing yet: the first pass stores instead of adding
@@ -1333,7 +1356,14 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
    const int patch = blockIdx.x % npatch_b;
    const int g = blockIdx.x / npatch_b;
    const int gl = gp.gloc[g];
-   if (gl < 0) return;
+   if (gl < 0) {
+      if (FUSED && t == 0) {               // neutral partials of a group another rank owns
+         for (int j = 0; j < 4; j++) fz.partials[(size_t)j * gridDim.x + blockIdx.x] = 0.0;
+         fz.partials[(size_t)4 * gridDim.x + blockIdx.x] = 1.0e300;
+      }
+      return;
+   }
+   double prod = 0.0, pow_ = 0.0, d2 = 0.0, p2 = 0.0, mn = 1.0e300;
    const int64_t slot = (int64_t)patch * PS + t;
    const int64_t bslot = cell_of ? cell_of[slot] : slot;     // base slot of this lane (-1: hole of another tiling)
    const bool live = bslot >= 0;
@@ -1390,7 +1420,27 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
                const int ad = s + u - (maxlev - 1);      // complete for every chunk and lane
                if (ad >= 0 && ad < nz) {
                   const int k = zpass == 0 ? ad : nz - 1 - ad;
-                  if (live) pg[(int64_t)k * gp.Sb] = old[u] + ring[ad & (SHEAR_RING - 1)][t];
+                  const double v = old[u] + ring[ad & (SHEAR_RING - 1)][t];
+                  if (FUSED && zpass == fz.last_zpass && c0 == fz.last_c0) {
+                     if (live) {
+                        const int64_t cell = (int64_t)k * gp.Sb + bslot;
+                        const int64_t a = (int64_t)g * nz * gp.Sb + cell;
+                        const int mat = fz.mats[cell];
+                        const double pn = mat < 0 ? 0.0 : v;
+                        fz.phi_out[a] = pn;
+#pragma unroll
+                        for (int r = 0; r < PEER_MAX; r++) if (r < fz.npeers) __stcs(fz.peers.p[r] + a, pn);
+                        if (mat >= 0) {
+                           const double po = fz.phi_old[a];
+                           const double vol = fz.area[bslot] * (fz.has_z ? fz.dz[k] : 1.0);
+                           prod = fma(vol * fz.nusf[mat * gp.G + g], pn, prod);
+                           pow_ = fma(vol * fz.kapsf[mat * gp.G + g], pn, pow_);
+                           d2 = fma(pn - po, pn - po, d2);
+                           p2 = fma(pn, pn, p2);
+                           mn = fmin(mn, pn);
+                        }
+                     }
+                  } else if (live) pg[(int64_t)k * gp.Sb] = v;
                   ring[ad & (SHEAR_RING - 1)][t] = 0.0;
                }
             }
@@ -1398,22 +1448,58 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
          overwrite = false;
       }
    }
+   if (FUSED) {
+      if (fz.npeers > 0) __threadfence_system();          // peer stores performed before the kernel ends
+      __syncthreads();                                    // the ring is free: reuse it for the block reduction
+      double (*sh)[PS] = ring;
+      sh[0][t] = prod; sh[1][t] = pow_; sh[2][t] = d2; sh[3][t] = p2; sh[4][t] = mn;
+      __syncthreads();
+      for (int off = PS / 2; off > 0; off >>= 1) {
+         if (t < off) {
+            for (int j = 0; j < 4; j++) sh[j][t] += sh[j][t + off];
+            sh[4][t] = fmin(sh[4][t], sh[4][t + off]);
+         }
+         __syncthreads();
+      }
+      if (t == 0)
+         for (int j = 0; j < 5; j++) fz.partials[(size_t)j * gridDim.x + blockIdx.x] = sh[j][0];
+   }
 }
 
 void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
                         const int32_t* d_fast_chunks, int nfast, int npatch_b, int overwrite_first,
                         const int32_t* cell_of, cudaStream_t st) {
    if (nfast <= 0) return;
-   sn_unshear_phi_kernel<<<npatch_b * gp.G, PS, SHEAR_RING * PS * sizeof(double), st>>>(
-      gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, cell_of);
+   sn_unshear_phi_kernel<false><<<npatch_b * gp.G, PS, SHEAR_RING * PS * sizeof(double), st>>>(
+      gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, cell_of, UnshearFuse{});
+}
+
+// the same pass with the reduction and the delivery of the flux moments fused into its last sweep over the column
+// (base tiling only); the block partials land in partials[5][npatch_b * G], summed by the caller into sums[5]
+void launch_unshear_phi_fused(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
+                              const int32_t* d_fast_chunks, int nfast, int npatch_b, int overwrite_first, int last_zpass,
+                              const double* phi_old, double* phi_out, double* const* peer_out, int npeers,
+                              const int32_t* mats, const double* nusf, const double* kapsf, const double* area,
+                              const double* dz, int has_z, double* partials, double* sums, cudaStream_t st) {
+   UnshearFuse fz{};
+   fz.phi_old = phi_old; fz.phi_out = phi_out; fz.npeers = npeers;
+   for (int r = 0; r < PEER_MAX; r++) fz.peers.p[r] = r < npeers ? peer_out[r] : nullptr;
+   fz.mats = mats; fz.nusf = nusf; fz.kapsf = kapsf; fz.area = area; fz.dz = dz; fz.has_z = has_z;
+   fz.last_zpass = last_zpass; fz.last_c0 = ((nfast - 1) / UNSHEAR_NC) * UNSHEAR_NC;
+   fz.partials = partials;
+   const int nblocks = npatch_b * gp.G;
+   sn_unshear_phi_kernel<true><<<nblocks, PS, SHEAR_RING * PS * sizeof(double), st>>>(
+      gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, nullptr, fz);
+   sn_reduce_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, sums);
 }
 
 cudaError_t configure_shear_kernels() {
    cudaError_t e = cudaFuncSetAttribute(sn_shear_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(ShearSmem));
    if (e != cudaSuccess) return e;
-   return cudaFuncSetAttribute(sn_unshear_phi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)sizeof(ShearSmem));
+   e = cudaFuncSetAttribute(sn_unshear_phi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShearSmem));
+   if (e != cudaSuccess) return e;
+   return cudaFuncSetAttribute(sn_unshear_phi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShearSmem));
 }
 
 // ------------------------------------------------------------------------------------ source
@@ -1538,7 +1624,6 @@ sn_reduce_kernel(double* __restrict__ phi, double* __restrict__ phi_new,
 // stores over NVLink, into that buffer of every peer.  The exchange rides on a pass that has to stream the slab
 // anyway, and the separate allgather disappears; the scalar collective that follows is the barrier after which the
 // buffer is complete on every rank.
-struct PeerPhi { double* p[PEER_MAX]; };
 __global__ void __launch_bounds__(256)
 sn_reduce_push_kernel(const double* __restrict__ phi, double* __restrict__ phi_new, double* __restrict__ phi_out,
                       PeerPhi peers, int npeers, const int32_t* __restrict__ mats, const double* __restrict__ nusf,

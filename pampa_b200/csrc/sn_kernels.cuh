@@ -12,6 +12,7 @@ namespace pampa_sn {
 constexpr int PS = 256;       // patch slots = sweep CTA size
 constexpr int PEDGE = 32;     // compact copies of the lanes other patches read, behind each psi row
 constexpr int PSX = PS + PEDGE;
+constexpr int PEER_MAX = 7;   // other ranks of a node whose iterate buffers a kernel stores into (8 GPUs)
 
 // Step-major ("sheared") arrays.  The pipeline step of (lane, layer) is kp + lvl(lane), kp = position of
 // the layer in sweep order: the lanes of a CTA work on different layers in the same step (wavefront skew),
@@ -139,6 +140,13 @@ void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const 
                         const int32_t* d_fast_chunks, int nfast, int npatch, int overwrite_first,
                         const int32_t* cell_of, cudaStream_t st);
 
+// un-shear with the reduction pass and the delivery of the flux moments fused into its last sweep over a column
+void launch_unshear_phi_fused(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
+                              const int32_t* d_fast_chunks, int nfast, int npatch, int overwrite_first, int last_zpass,
+                              const double* phi_old, double* phi_out, double* const* peer_out, int npeers,
+                              const int32_t* mats, const double* nusf, const double* kapsf, const double* area,
+                              const double* dz, int has_z, double* partials, double* sums, cudaStream_t st);
+
 void launch_source(const double* phi, double* q, const int32_t* mats, const double* sig_s,
                    const double* chi, const double* nusf, const ReduceScalars* sc, const int32_t* gloc,
                    int G, int nmat, int nz, int64_t Sb, cudaStream_t st);
@@ -149,7 +157,6 @@ void launch_reduce(double* phi, double* phi_new, const int32_t* mats, const doub
                    int nblocks, double* sums, cudaStream_t st);
 // group-sharded runs with peer access: reduction of the owned groups + delivery of the new flux moments into the
 // other iterate buffer of this rank (phi_out) and of every peer (peer_out[0 .. npeers)), see sn_kernels.cu
-constexpr int PEER_MAX = 7;
 void launch_reduce_push(const double* phi, double* phi_new, double* phi_out, double* const* peer_out, int npeers,
                         const int32_t* mats, const double* nusf, const double* kapsf, const double* area,
                         const double* dz, int has_z, int G, int nz, int64_t Sb, const int32_t* gloc, double* partials,
