@@ -1344,7 +1344,7 @@ struct UnshearFuse {
 };
 
 template <bool FUSED>
-__global__ void __launch_bounds__(PS)
+__global__ void __launch_bounds__(PS, 3)
 sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks,
                       const ClassDev* __restrict__ classes, const int32_t* __restrict__ fast_chunks,
                       int nfast, int npatch_b, int overwrite_first, const int32_t* __restrict__ cell_of,
@@ -1367,6 +1367,7 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
    const int64_t slot = (int64_t)patch * PS + t;
    const int64_t bslot = cell_of ? cell_of[slot] : slot;     // base slot of this lane (-1: hole of another tiling)
    const bool live = bslot >= 0;
+   const double area_l = (FUSED && live) ? fz.area[bslot] : 0.0;
    const int nz = gp.nz;
    double* pg = gp.phi_new + (int64_t)g * nz * gp.Sb + (live ? bslot : 0);
    for (int zpass = 0; zpass < 2; zpass++) {
@@ -1405,10 +1406,19 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
             // the (up to two) layers this pair of steps completes: their current phi_new values are
             // loaded with the chunk rows, not after them (nothing to load in the pass that overwrites)
             double old[2];
+            double pov[2];                                 // fused pass: previous iterate and material of those layers
+            int matv[2];
+            const bool fuse_pass = FUSED && zpass == fz.last_zpass && c0 == fz.last_c0;
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                const int ad = s + u - (maxlev - 1);
-               old[u] = (!overwrite && live && ad >= 0 && ad < nz) ? pg[(int64_t)(zpass == 0 ? ad : nz - 1 - ad) * gp.Sb] : 0.0;
+               const bool in = live && ad >= 0 && ad < nz;
+               const int64_t kk = zpass == 0 ? ad : nz - 1 - ad;
+               old[u] = (!overwrite && in) ? pg[kk * gp.Sb] : 0.0;
+               if (FUSED) {
+                  matv[u] = (fuse_pass && in) ? fz.mats[kk * gp.Sb + bslot] : -1;
+                  pov[u] = (fuse_pass && in) ? fz.phi_old[(int64_t)g * nz * gp.Sb + kk * gp.Sb + bslot] : 0.0;
+               }
             }
 #pragma unroll
             for (int u = 0; u < 2; u++) {
@@ -1421,18 +1431,17 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
                if (ad >= 0 && ad < nz) {
                   const int k = zpass == 0 ? ad : nz - 1 - ad;
                   const double v = old[u] + ring[ad & (SHEAR_RING - 1)][t];
-                  if (FUSED && zpass == fz.last_zpass && c0 == fz.last_c0) {
+                  if (FUSED && fuse_pass) {
                      if (live) {
-                        const int64_t cell = (int64_t)k * gp.Sb + bslot;
-                        const int64_t a = (int64_t)g * nz * gp.Sb + cell;
-                        const int mat = fz.mats[cell];
+                        const int64_t a = (int64_t)g * nz * gp.Sb + (int64_t)k * gp.Sb + bslot;
+                        const int mat = matv[u];
                         const double pn = mat < 0 ? 0.0 : v;
                         fz.phi_out[a] = pn;
 #pragma unroll
                         for (int r = 0; r < PEER_MAX; r++) if (r < fz.npeers) __stcs(fz.peers.p[r] + a, pn);
                         if (mat >= 0) {
-                           const double po = fz.phi_old[a];
-                           const double vol = fz.area[bslot] * (fz.has_z ? fz.dz[k] : 1.0);
+                           const double po = pov[u];
+                           const double vol = area_l * (fz.has_z ? fz.dz[k] : 1.0);
                            prod = fma(vol * fz.nusf[mat * gp.G + g], pn, prod);
                            pow_ = fma(vol * fz.kapsf[mat * gp.G + g], pn, pow_);
                            d2 = fma(pn - po, pn - po, d2);

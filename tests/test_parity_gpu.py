@@ -388,6 +388,10 @@ def test_sweep_schedule_independence(monkeypatch):
     mesh, xs = syn.checkerboard_core(64, 64, 96, num_groups=G)
     quad = syn.level_symmetric(4)
     ref = None
+    # (the fused tail of the iteration sums the k integrals per un-shear CTA, the separate reduction pass -- which
+    # graph-replayed plans such as wave_launch use -- per grid-stride block: same flux, last bits of k differ;
+    # the schedules are compared under one reduction, test_fused_tail_matches_separate_passes compares the two)
+    monkeypatch.setenv("PAMPA_SN_NO_FUSE", "1")
     for opts, dbg in (({"wave_launch": 1}, None), ({}, None), ({"group_merge": 8}, None), ({"group_merge": 8}, "16"),
                       ({"group_merge": 1}, "16"), ({"group_merge": 3, "store_psi": 0}, "16"),
                       ({"inline_edges": 1}, "16")):
@@ -406,7 +410,35 @@ def test_sweep_schedule_independence(monkeypatch):
             assert np.array_equal(phi, ref[1]), (opts, dbg)
 
 
-def test_full_size_properties():
+def test_fused_tail_matches_separate_passes(monkeypatch):
+    """Plain source iterations end with un-shear, reduction and rotation of the iterate; the dataflow path fuses the
+    three into the last un-shear sweep of a column (and, sharded, the delivery to the peers).  Same flux moments bit
+    for bit after one iteration, k to rounding (the integrals are summed in another order), and still after five."""
+    G = 8
+    mesh, xs = syn.checkerboard_core(64, 48, 40, num_groups=G)
+    quad = syn.level_symmetric(4)
+    out = {}
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("PAMPA_SN_NO_FUSE", raising=False)
+        else:
+            monkeypatch.setenv("PAMPA_SN_NO_FUSE", "1")
+        dev = pb.SNDevice(mesh, xs, quad)
+        k1 = dev.iterate(1)
+        p1 = dev.get("flux-moments")
+        k5 = dev.iterate(4)
+        p5 = dev.get("flux-moments")
+        sol = dev.solve_keff(tol_k=1e-10, tol_phi=1e-9)
+        dev.close()
+        out[fused] = (k1, p1, k5, p5, sol[0])
+    a, b = out[True], out[False]
+    assert np.array_equal(a[1], b[1])
+    assert abs(a[0] - b[0]) < 1e-13 * abs(b[0])
+    assert abs(a[2] - b[2]) < 1e-13 * abs(b[2]) and util.max_rel(a[3], b[3]) < 1e-12
+    assert abs(a[4] - b[4]) < 1e-9
+
+
+def test_full_size_properties(monkeypatch):
     """BASELINE config 4 at its own size (216^3 cells, S8, 8 groups; the oracle cannot run there): properties that
     do not depend on the size.  The checkerboard core, its vacuum boundaries and the level-symmetric quadrature are
     invariant under x <-> y, x <-> z and the three reflections, so the flux moments of any number of source
@@ -415,6 +447,7 @@ def test_full_size_properties():
     n, G = 216, 8
     mesh, xs = syn.checkerboard_core(n, n, n, num_groups=G)
     quad = syn.level_symmetric(8)
+    monkeypatch.setenv("PAMPA_SN_NO_FUSE", "1")          # one reduction order for the bit-for-bit comparison below
     dev = pb.SNDevice(mesh, xs, quad)
     assert dev.info()["updates_per_sweep"] == n ** 3 * 80 * G
     k = dev.iterate(2)
