@@ -373,6 +373,12 @@ def run_b200(a, rank, world, local_rank):
                 # the same algorithmic bytes over shear + sweep kernel + un-shear (the layout passes
                 # the step-major arrays cost), and that fraction of the peak
                 "sweep_ms_per_step": sweep_ms / a.steps, "frac_with_layout_passes": achieved_sweep / peak}
+    if not int(json.loads(a.opts).get("store_psi", 1)):
+        # the angular flux is not kept: the 8 B psi store of the formula is not made (only the edge copies other
+        # patches read), so `achieved` is a throughput stated on the psi-stored byte count, not a bandwidth claim
+        roofline["psi_stored"] = False
+        roofline["note"] = ("store_psi = 0: achieved / frac are updates/s x the psi-stored 16 + 16/M bytes, for comparison "
+                            "with psi-stored runs; the kernel does not write the psi rows, so it is not a DRAM-bandwidth figure")
 
     # end to end through the C ABI with host buffers: one solve-like call = upload of the cross
     # sections and of the flux iterate, K source iterations, download of scalar flux and power
