@@ -98,8 +98,9 @@ struct pampa_sn_handle {
    // peer-to-peer delivery of the flux moments (group-sharded runs, all ranks on one node): the iterate is
    // double-buffered and the reduction pass stores the new slabs straight into the other buffer of every peer
    bool p2p = false;
-   bool fuse_next = false;               // the next sweep may fuse the reduction into its un-shear pass
-   bool fused_done = false;              // ... and did: d_sums holds this rank's sums, the iterate buffers are swapped
+   int fuse_next = 0;                    // the next sweep may fuse the reduction into its last un-shear pass: 1 = and
+                                         // rotate / deliver the iterate, 2 = in place (phi_new keeps the result)
+   int fused_done = 0;                   // ... and did (same codes): d_sums holds this rank's sums
    double* d_fuse_partials = nullptr;    // [5][npatch_b * G]
    double* d_phi_buf[2] = {nullptr, nullptr};   // d_phi is d_phi_buf[phi_cur]
    int phi_cur = 0;
@@ -360,20 +361,39 @@ int sweep_launches(pampa_sn_handle* h) {
    if (h->kernel_events) {
       cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); h->kernel_events->push_back(e);
    }
-   // Fused tail of the iteration (plain source iterations, every class on the base tiling's dataflow kernel, one GPU
-   // or a group-sharded run with peer access): the un-shear pass also reduces and delivers the new flux moments.
-   const bool sharded_ok = h->opts.num_ranks == 1 || (h->comm && h->group_gather && h->p2p);
-   if (h->fuse_next && sharded_ok && h->groups_generic == 0 && h->tilings.size() == 1 && h->tilings[0].nchunks > 0 &&
-       h->d_phi_buf[1] && h->d_fuse_partials && !std::getenv("PAMPA_SN_NO_FUSE")) {
+   // Fused tail of the iteration (every class on a dataflow kernel, one GPU or a group-sharded run): the last un-shear
+   // pass -- the base tiling's, after those of the other tilings -- holds the final flux moments of a column in
+   // registers and also reduces them.  Mode 1 (plain source iterations; sharded: needs peer access) writes them into
+   // the other iterate buffer, here and on every peer; mode 2 (accelerated iterations, whose next iterate is a mix)
+   // leaves them in phi_new.
+   const int fuse = h->fuse_next;
+   bool can_fuse = fuse && h->groups_generic == 0 && h->tilings[0].nchunks > 0 && h->d_fuse_partials &&
+                   !std::getenv("PAMPA_SN_NO_FUSE");
+   if (fuse == 1) can_fuse = can_fuse && h->d_phi_buf[1] && (h->opts.num_ranks == 1 || (h->comm && h->group_gather && h->p2p));
+   if (fuse == 2) can_fuse = can_fuse && (!h->comm || h->group_gather);
+   if (can_fuse) {
+      bool overwrite = true;
+      for (size_t t = 1; t < h->tilings.size(); t++) {
+         const TilingDev& tg = h->tilings[t];
+         if (tg.nchunks <= 0) continue;
+         launch_unshear_phi(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.npatch, overwrite ? 1 : 0,
+                            tg.d_cell_of, h->stream);
+         overwrite = false;
+         h->launches++;
+      }
       const TilingDev& tg = h->tilings[0];
       const int out = 1 - h->phi_cur;
-      launch_unshear_phi_fused(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.npatch, 1, h->unshear_last_zpass,
-                               h->d_phi, h->d_phi_buf[out], h->peer_phi[out], h->npeers, h->d_mats, h->d_nusf, h->d_kapsf,
+      double* phi_out = fuse == 1 ? h->d_phi_buf[out] : h->d_phi_new;
+      launch_unshear_phi_fused(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.npatch, overwrite ? 1 : 0,
+                               h->unshear_last_zpass, h->d_phi, phi_out, fuse == 1 ? h->peer_phi[out] : nullptr,
+                               fuse == 1 ? h->npeers : 0, h->d_mats, h->d_nusf, h->d_kapsf,
                                h->d_area, h->d_dz, h->plan.has_z, h->d_fuse_partials, h->d_sums, h->stream);
       h->launches += 2;
-      h->phi_cur = out;
-      h->d_phi = h->d_phi_buf[out];
-      h->fused_done = true;
+      if (fuse == 1) {
+         h->phi_cur = out;
+         h->d_phi = h->d_phi_buf[out];
+      }
+      h->fused_done = fuse;
       return 0;
    }
    // every owned chunk on the tile kernels: nothing else adds to phi_new, the first pass may overwrite it
@@ -392,10 +412,10 @@ int sweep_launches(pampa_sn_handle* h) {
 // and kernel variant, thousands per sweep) are launch-bound, so their sequence -- fixed for the life of the
 // handle but for the two boundary buffers that alternate -- is captured once per buffer parity into a CUDA
 // graph, fork / join over the class streams included, and replayed.
-int do_sweep(pampa_sn_handle* h, bool fuse = false) {
+int do_sweep(pampa_sn_handle* h, int fuse = 0) {
    const bool graphed = h->use_graph && !h->graph_failed;
-   h->fuse_next = fuse && !graphed;
-   h->fused_done = false;
+   h->fuse_next = graphed ? 0 : fuse;
+   h->fused_done = 0;
    if (!graphed) {
       if (sweep_launches(h)) return 1;
    } else {
@@ -472,11 +492,15 @@ int reduce_sums(pampa_sn_handle* h, int rotate, bool* pushed = nullptr, bool aft
    if (h->comm && after_sweep && exchange_boundaries(h)) return 1;
    const int owned_only = (h->comm && h->group_gather) ? 1 : 0;
    if (pushed) *pushed = false;
-   if (h->fused_done) {
+   if (h->fused_done == 1) {
       // the sweep's un-shear pass already reduced (d_sums) and delivered the flux moments (buffers swapped)
-      h->fused_done = false;
+      h->fused_done = 0;
       if (!rotate || !pushed) SN_FAIL(h, "internal: fused sweep followed by a non-rotating reduction");
       *pushed = true;
+   } else if (h->fused_done == 2) {
+      // ... reduced only: phi_new holds the sweep result, d_sums this rank's sums
+      h->fused_done = 0;
+      if (rotate) SN_FAIL(h, "internal: in-place fused sweep followed by a rotating reduction");
    } else if (owned_only && rotate && h->p2p && pushed) {
       // reduction of the owned groups that also delivers them to every rank's other iterate buffer
       const int out = 1 - h->phi_cur;
@@ -1006,8 +1030,9 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       // fused tail of the iteration: second iterate buffer (one GPU: here; sharded: pampa_sn_comm_init) and the
       // partials of the un-shear CTAs
       h->unshear_last_zpass = 0;
-      for (int32_t c : fast_chunks) if (pl.classes[pl.chunks[c].cls].zdir < 0) h->unshear_last_zpass = 1;
-      if (h->groups_generic == 0 && pl.tilings.size() == 1 && !fast_chunks.empty()) {
+      for (int32_t c : fast_chunks)
+         if (pl.classes[pl.chunks[c].cls].tiling == 0 && pl.classes[pl.chunks[c].cls].zdir < 0) h->unshear_last_zpass = 1;
+      if (h->groups_generic == 0 && h->tilings[0].nchunks > 0) {
          if (dev_alloc(h, &h->d_fuse_partials, 5LL * pl.npatch_b * h->G)) return 1;
          if (h->opts.num_ranks == 1) {
             if (dev_alloc(h, &h->d_phi_buf[1], nphi)) return 1;
@@ -1132,7 +1157,7 @@ int pampa_sn_reduce(pampa_sn_handle* h, double* production, double* power, doubl
 int pampa_sn_iterate(pampa_sn_handle* h, int32_t iterations, double* keff) {
    SN_CUDA(h, cudaSetDevice(h->device));
    for (int it = 0; it < iterations; it++) {
-      if (do_source(h) || do_sweep(h, true) || do_reduce(h, 1)) return 1;
+      if (do_source(h) || do_sweep(h, 1) || do_reduce(h, 1)) return 1;
    }
    if (sync_scalars(h)) return 1;
    h->keff = h->sc.keff;
@@ -1155,7 +1180,7 @@ int pampa_sn_iterate_timed(pampa_sn_handle* h, int32_t iterations, double* keff,
    for (int it = 0; it < iterations && !rc; it++) {
       rc = do_source(h);
       cudaEventRecord(ev[2 + 3 * it], h->stream);
-      if (!rc) rc = do_sweep(h, true);
+      if (!rc) rc = do_sweep(h, 1);
       cudaEventRecord(ev[3 + 3 * it], h->stream);
       if (!rc) rc = do_reduce(h, 1);
       cudaEventRecord(ev[4 + 3 * it], h->stream);
@@ -1215,7 +1240,7 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
    // plain power iteration; the convergence test reads the scalars of iteration i while i + 1 is in the queue
    auto plain_iteration = [&]() -> int {
       while (it < max_it) {
-         if (do_source(h) || do_sweep(h, true) || do_reduce(h, 1)) return 1;
+         if (do_source(h) || do_sweep(h, 1) || do_reduce(h, 1)) return 1;
          it++;
          if (sync_scalars(h)) return 1;
          const double dphi = h->sc.phi2 > 0 ? std::sqrt(h->sc.dphi2 / h->sc.phi2) : 0.0;
@@ -1245,6 +1270,9 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
       }
       if (!h->h_aa_ring) SN_CUDA(h, cudaHostAlloc((void**)&h->h_aa_ring, 2 * sizeof(AAState), cudaHostAllocDefault));
       const int owned_only = (h->comm && h->group_gather) ? 1 : 0;
+      // phi_new must be cleared for the next sweep only where something accumulates into it (generic kernels) or a
+      // rank of an angle-sharded run may own no chunk at all; otherwise the first un-shear pass overwrites it
+      const int zero_new = (h->groups_generic == 0 && h->nfast_chunks > 0 && (!h->comm || h->group_gather)) ? 0 : 1;
       if (sync_scalars(h)) return 1;
       if (!(h->sc.production > 0.0)) SN_FAIL(h, "zero fission production: no fissile material in the mesh");
       AAState st0;
@@ -1268,10 +1296,10 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
       int rc = 0;
       bool failed = false;
       while (it < max_it && !rc) {
-         if ((rc = do_source(h) || do_sweep(h) || reduce_sums(h, 0))) break;
+         if ((rc = do_source(h) || do_sweep(h, 2) || reduce_sums(h, 0))) break;
          it++;
          launch_aa_begin(h->d_aa_state, h->d_sums, h->stream);
-         launch_aa_store(h->d_phi, h->d_phi_new, h->d_gloc, owned_only, h->G, nslab, fptr, gptr, h->d_aa_state,
+         launch_aa_store(h->d_phi, h->d_phi_new, h->d_gloc, owned_only, zero_new, h->G, nslab, fptr, gptr, h->d_aa_state,
                          h->d_aa_partials, h->nblocks_reduce, h->d_aa_dots, h->stream);
          h->launches += 3;
          // the lagged boundary fluxes are part of the fixed-point state: same normalisation, same mixing
@@ -1342,7 +1370,7 @@ int pampa_sn_solve_keff(pampa_sn_handle* h, double tol_k, double tol_phi, int32_
          // a few unaccelerated iterations remove the undershoot (the reference rejects any negative flux,
          // src/NeutronicSolver.cxx:67).
          for (int polish = 0; converged && min_phi < 0.0 && polish < 200 && it < max_it; polish++) {
-            if (do_source(h) || do_sweep(h, true) || do_reduce(h, 1)) return 1;
+            if (do_source(h) || do_sweep(h, 1) || do_reduce(h, 1)) return 1;
             it++;
             if (sync_scalars(h)) return 1;
             power_integral = h->sc.power; min_phi = h->sc.min_phi;

@@ -1787,7 +1787,7 @@ void launch_aa_begin(AAState* st_dev, const double* sums, cudaStream_t st) { sn_
 // test: phi and phi_new are zero there, so g, f and the dot products get zeros.
 __global__ void __launch_bounds__(256)
 sn_aa_store_kernel(const double* __restrict__ phi, double* __restrict__ phi_new,
-                   const int32_t* __restrict__ gloc, int owned_only, int G, int64_t n,
+                   const int32_t* __restrict__ gloc, int owned_only, int zero_new, int G, int64_t n,
                    AAHist hist, const AAState* __restrict__ state, double* __restrict__ partials) {
    const int cur = state->cur, nhist = state->nvisit;
    const double inv_prod = state->inv;
@@ -1810,7 +1810,7 @@ sn_aa_store_kernel(const double* __restrict__ phi, double* __restrict__ phi_new,
          hf[j] = (j < nhist && j != cur) ? *reinterpret_cast<const double2*>(hist.f[j] + a) : make_double2(0.0, 0.0);
       const double2 xg = make_double2(p.x * inv_prod, p.y * inv_prod);
       const double2 f = make_double2(xg.x - x.x, xg.y - x.y);
-      *reinterpret_cast<double2*>(phi_new + a) = make_double2(0.0, 0.0);
+      if (zero_new) *reinterpret_cast<double2*>(phi_new + a) = make_double2(0.0, 0.0);   // (sweeps that accumulate)
       *reinterpret_cast<double2*>(gc + a) = xg;
       *reinterpret_cast<double2*>(fc + a) = f;
 #pragma unroll
@@ -1931,26 +1931,30 @@ void launch_aa_solve(AAState* st_dev, const double* dots, ReduceScalars* sc, cud
 // x_next = sum_j alpha_j g_j  (sum alpha = 1, so the production of x_next is that of the iterates); group-sharded
 // runs with peer access store it into the same buffer of every peer as well (npeers > 0, see sn_reduce_push_kernel)
 __global__ void __launch_bounds__(256)
-sn_aa_mix_kernel(double* __restrict__ phi, const int32_t* __restrict__ mats, const int32_t* __restrict__ gloc,
+sn_aa_mix_kernel(double* __restrict__ phi, const int32_t* __restrict__ gloc,
                  int owned_only, int G, int64_t n, AAHist hist, const AAState* __restrict__ state, PeerPhi peers,
                  int npeers) {
+   // Streamed like sn_aa_store_kernel: two doubles per thread, the loads of every slot in the window issued before
+   // the first use (slots outside the window have a zero weight and are not read).  Holes need no test: every
+   // stored iterate is zero there.
    double alpha[AA_MAX];
 #pragma unroll
    for (int j = 0; j < AA_MAX; j++) alpha[j] = state->mix[j];
-   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-        idx += (int64_t)gridDim.x * blockDim.x) {
-      if (mats[idx] < 0) continue;
-      for (int g = 0; g < G; g++) {
-         if (owned_only && gloc[g] < 0) continue;
-         const int64_t a = (int64_t)g * n + idx;
-         double v = 0.0;
+   const int64_t total = (int64_t)G * n;                 // n = layers x (patches x 256): even
+   for (int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; a < total;
+        a += (int64_t)gridDim.x * blockDim.x * 2) {
+      if (owned_only && gloc[a / n] < 0) continue;
+      double2 hg[AA_MAX];
 #pragma unroll
-         for (int j = 0; j < AA_MAX; j++)
-            if (alpha[j] != 0.0) v = fma(alpha[j], hist.g[j][a], v);
-         phi[a] = v;
+      for (int j = 0; j < AA_MAX; j++)
+         hg[j] = alpha[j] != 0.0 ? *reinterpret_cast<const double2*>(hist.g[j] + a) : make_double2(0.0, 0.0);
+      double2 v = make_double2(0.0, 0.0);
 #pragma unroll
-         for (int r = 0; r < PEER_MAX; r++) if (r < npeers) __stcs(peers.p[r] + a, v);
-      }
+      for (int j = 0; j < AA_MAX; j++) { v.x = fma(alpha[j], hg[j].x, v.x); v.y = fma(alpha[j], hg[j].y, v.y); }
+      *reinterpret_cast<double2*>(phi + a) = v;
+#pragma unroll
+      for (int r = 0; r < PEER_MAX; r++)
+         if (r < npeers) __stcs(reinterpret_cast<double2*>(peers.p[r] + a), v);
    }
    if (npeers > 0) __threadfence_system();
 }
@@ -1990,12 +1994,12 @@ void launch_vec_mix(double* out, double* const* hist, const AAState* st_dev, int
    sn_vec_mix_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(out, h, st_dev, n);
 }
 
-void launch_aa_store(const double* phi, double* phi_new, const int32_t* gloc, int owned_only, int G, int64_t n,
+void launch_aa_store(const double* phi, double* phi_new, const int32_t* gloc, int owned_only, int zero_new, int G, int64_t n,
                      double* const* hist_f, double* const* hist_g, const AAState* st_dev, double* partials,
                      int nblocks, double* dots, cudaStream_t st) {
    AAHist h{};
    for (int j = 0; j < AA_MAX; j++) { h.f[j] = hist_f[j]; h.g[j] = hist_g[j]; }
-   sn_aa_store_kernel<<<nblocks, 256, 0, st>>>(phi, phi_new, gloc, owned_only, G, n, h, st_dev, partials);
+   sn_aa_store_kernel<<<nblocks, 256, 0, st>>>(phi, phi_new, gloc, owned_only, zero_new, G, n, h, st_dev, partials);
    sn_aa_dots_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, dots);
 }
 
@@ -2006,7 +2010,7 @@ void launch_aa_mix(double* phi, const int32_t* mats, const int32_t* gloc, int ow
    for (int j = 0; j < AA_MAX; j++) { h.f[j] = nullptr; h.g[j] = hist_g[j]; }
    PeerPhi pp{};
    for (int r = 0; r < PEER_MAX; r++) pp.p[r] = (peer_out && r < npeers) ? peer_out[r] : nullptr;
-   sn_aa_mix_kernel<<<nblocks, 256, 0, st>>>(phi, mats, gloc, owned_only, G, n, h, st_dev, pp, peer_out ? npeers : 0);
+   sn_aa_mix_kernel<<<nblocks, 256, 0, st>>>(phi, gloc, owned_only, G, n, h, st_dev, pp, peer_out ? npeers : 0);
 }
 
 // ------------------------------------------------------------------------------------ LS term

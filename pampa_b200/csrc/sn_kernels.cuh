@@ -185,7 +185,7 @@ struct AAState {
 };
 // (every launcher below takes the device-resident AAState: slot, window and weights are read on the device)
 void launch_aa_begin(AAState* st_dev, const double* sums, cudaStream_t st);
-void launch_aa_store(const double* phi, double* phi_new, const int32_t* gloc, int owned_only, int G, int64_t n,
+void launch_aa_store(const double* phi, double* phi_new, const int32_t* gloc, int owned_only, int zero_new, int G, int64_t n,
                      double* const* hist_f, double* const* hist_g, const AAState* st_dev, double* partials,
                      int nblocks, double* dots, cudaStream_t st);
 void launch_aa_solve(AAState* st_dev, const double* dots, ReduceScalars* sc, cudaStream_t st);
