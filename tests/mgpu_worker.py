@@ -16,7 +16,14 @@ sys.path.insert(0, ROOT)
 from pampa_b200 import problem as pb, synthetic as syn  # noqa: E402
 
 
-def problem():
+def problem(kind="cartesian"):
+    if kind == "hex":
+        # hexagonal lattice: three rhombic tilings, the three-face dataflow kernel, the fused tail of the iteration
+        # with the base tiling's pass last (vacuum boundaries: the largest eigenvalue is well separated)
+        G = 4
+        mesh, xs, _ = syn.hex_core(14, 12, pitch=1.2, dz=1.5, num_groups=G, seed=7)
+        xs.nu_sigma_fission[0] *= 4.0; xs.kappa_sigma_fission[0] *= 4.0
+        return mesh, xs, syn.level_symmetric(4), G
     nx, ny, nz, G = 24, 20, 12, 4
     mats = np.zeros((nz, ny, nx), dtype=int)
     mats[:, :, 16:] = 1; mats[:, 14:, :] = 1; mats[9:] = 1
@@ -31,9 +38,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--backend", default="nccl")
     ap.add_argument("--shard-mode", type=int, default=0)
+    ap.add_argument("--mesh", default="cartesian", choices=["cartesian", "hex"])
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    mesh, xs, quad, G = problem()
+    mesh, xs, quad, G = problem(a.mesh)
     total = mesh.num_cells * len(quad.weights) * G
     if a.backend == "gloo":
         dist.init_process_group("gloo")

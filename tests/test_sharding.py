@@ -22,10 +22,11 @@ def test_sharding_host_logic_gloo(mode):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [0, 1])
-def test_sharded_solve_matches_single_gpu(mode):
+@pytest.mark.parametrize("mode,mesh", [(0, "cartesian"), (1, "cartesian"), (1, "hex")])
+def test_sharded_solve_matches_single_gpu(mode, mesh):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _torchrun(2, 29621 + mode, "--backend", "nccl", "--shard-mode", str(mode))
+    r = _torchrun(2, 29621 + mode + (4 if mesh == "hex" else 0), "--backend", "nccl", "--shard-mode", str(mode),
+                  "--mesh", mesh)
     assert r.returncode == 0 and "NCCL_OK" in r.stdout, r.stdout + r.stderr
