@@ -48,7 +48,8 @@ struct LaunchGroup { int wave, cls, kind, dt, fin, ring; bool extras; int64_t of
 // one dataflow launch: every tile-class task of one chunk size, in ticket (topological) order
 struct FlowLaunch { int dt, fin; int64_t offset; int count; std::vector<double> mw; int nch; };
 // fast classes / chunks of one shared tiling (the shear passes run once per tiling)
-struct TilingDev { int npatch = 0; int32_t* d_cell_of = nullptr; int32_t *d_classes = nullptr, *d_chunks = nullptr; int nclasses = 0, nchunks = 0; };
+struct TilingDev { int npatch = 0; int32_t* d_cell_of = nullptr; int32_t *d_classes = nullptr, *d_chunks = nullptr; int nclasses = 0, nchunks = 0;
+                   int zsplit = 1; };   // slabs per column of this tiling's un-shear pass (unshear_zsplit)
 
 }  // namespace
 
@@ -377,7 +378,7 @@ int sweep_launches(pampa_sn_handle* h) {
          const TilingDev& tg = h->tilings[t];
          if (tg.nchunks <= 0) continue;
          launch_unshear_phi(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.npatch, overwrite ? 1 : 0,
-                            tg.d_cell_of, h->stream);
+                            tg.d_cell_of, tg.zsplit, h->stream);
          overwrite = false;
          h->launches++;
       }
@@ -387,7 +388,7 @@ int sweep_launches(pampa_sn_handle* h) {
       launch_unshear_phi_fused(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.npatch, overwrite ? 1 : 0,
                                h->unshear_last_zpass, h->d_phi, phi_out, fuse == 1 ? h->peer_phi[out] : nullptr,
                                fuse == 1 ? h->npeers : 0, h->d_mats, h->d_nusf, h->d_kapsf,
-                               h->d_area, h->d_dz, h->plan.has_z, h->d_fuse_partials, h->d_sums, h->stream);
+                               h->d_area, h->d_dz, h->plan.has_z, h->d_fuse_partials, h->d_sums, tg.zsplit, h->stream);
       h->launches += 2;
       if (fuse == 1) {
          h->phi_cur = out;
@@ -401,7 +402,7 @@ int sweep_launches(pampa_sn_handle* h) {
    for (const TilingDev& tg : h->tilings)
       if (tg.nchunks > 0) {
          launch_unshear_phi(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.npatch, overwrite ? 1 : 0,
-                            tg.d_cell_of, h->stream);
+                            tg.d_cell_of, tg.zsplit, h->stream);
          overwrite = false;
          h->launches++;
       }
@@ -926,6 +927,8 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       }
       h->tilings.assign(pl.tilings.size(), TilingDev{});
       h->nfast_classes = 0; h->nfast_chunks = (int)fast_chunks.size();
+      int num_sms = 148;
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, h->device);
       for (size_t tg = 0; tg < pl.tilings.size(); tg++) {
          TilingDev& td = h->tilings[tg];
          td.npatch = pl.tilings[tg].npatch;
@@ -937,6 +940,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          std::stable_sort(chunk_list.begin(), chunk_list.end(), [&](int32_t a, int32_t b) {
             return (pl.classes[pl.chunks[a].cls].zdir < 0) < (pl.classes[pl.chunks[b].cls].zdir < 0); });
          td.nclasses = (int)cls_list.size(); td.nchunks = (int)chunk_list.size();
+         td.zsplit = unshear_zsplit(td.npatch * h->Gown, pl.nz, num_sms);
          h->nfast_classes += td.nclasses;
          if (dev_upload(h, &td.d_classes, cls_list) || dev_upload(h, &td.d_chunks, chunk_list)) return 1;
          if (tg > 0 && td.nclasses > 0) {     // slot of this tiling -> base slot (the classes on it share the map)
@@ -1033,7 +1037,7 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
       for (int32_t c : fast_chunks)
          if (pl.classes[pl.chunks[c].cls].tiling == 0 && pl.classes[pl.chunks[c].cls].zdir < 0) h->unshear_last_zpass = 1;
       if (h->groups_generic == 0 && h->tilings[0].nchunks > 0) {
-         if (dev_alloc(h, &h->d_fuse_partials, 5LL * pl.npatch_b * h->G)) return 1;
+         if (dev_alloc(h, &h->d_fuse_partials, 5LL * pl.npatch_b * h->G * UNSHEAR_ZSPLIT_MAX)) return 1;
          if (h->opts.num_ranks == 1) {
             if (dev_alloc(h, &h->d_phi_buf[1], nphi)) return 1;
             SN_CUDA(h, cudaMemsetAsync(h->d_phi_buf[1], 0, (size_t)nphi * sizeof(double), h->stream));

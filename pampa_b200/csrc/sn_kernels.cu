@@ -1356,10 +1356,13 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
    const int patch = blockIdx.x % npatch_b;
    const int g = blockIdx.x / npatch_b;
    const int gl = gp.gloc[g];
+   // blockIdx.y: slab of layers [k0, k1) of the column this CTA completes (launch_unshear_phi*: a rank that owns few
+   // (patch, group) columns splits them in z to fill the SMs; the rows that straddle two slabs are read by both)
+   const int nblk_all = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
    if (gl < 0) {
       if (FUSED && t == 0) {               // neutral partials of a group another rank owns
-         for (int j = 0; j < 4; j++) fz.partials[(size_t)j * gridDim.x + blockIdx.x] = 0.0;
-         fz.partials[(size_t)4 * gridDim.x + blockIdx.x] = 1.0e300;
+         for (int j = 0; j < 4; j++) fz.partials[(size_t)j * nblk_all + bid] = 0.0;
+         fz.partials[(size_t)4 * nblk_all + bid] = 1.0e300;
       }
       return;
    }
@@ -1369,8 +1372,11 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
    const bool live = bslot >= 0;
    const double area_l = (FUSED && live) ? fz.area[bslot] : 0.0;
    const int nz = gp.nz;
+   const int k0 = (int)((int64_t)blockIdx.y * nz / gridDim.y), k1 = (int)((int64_t)(blockIdx.y + 1) * nz / gridDim.y);
    double* pg = gp.phi_new + (int64_t)g * nz * gp.Sb + (live ? bslot : 0);
    for (int zpass = 0; zpass < 2; zpass++) {
+      // the slab in sweep order of this z direction: layer index a <-> k = a (+z) or nz - 1 - a (-z)
+      const int a_lo = zpass == 0 ? k0 : nz - k1, a_hi = zpass == 0 ? k1 : nz - k0;
       for (int c0 = 0; c0 < nfast; c0 += UNSHEAR_NC) {
          // up to UNSHEAR_NC chunks of this z direction, starting the search at chunk c0
          const double* base[UNSHEAR_NC];
@@ -1394,14 +1400,14 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
          }
          if (!found) continue;                            // uniform over the CTA
          for (int r = 0; r < SHEAR_RING; r++) ring[r][t] = 0.0;
-         const int nrow = nz + maxlev - 1;
-         for (int s = 0; s < nrow; s += 2) {
+         const int nrow = a_hi + maxlev - 1;
+         for (int s = a_lo; s < nrow; s += 2) {
             double v0[UNSHEAR_NC], v1[UNSHEAR_NC];
 #pragma unroll
             for (int j = 0; j < UNSHEAR_NC; j++) {
                const int a0 = s - lv[j], a1 = s + 1 - lv[j];
-               v0[j] = (a0 >= 0 && a0 < nz) ? __ldcs(base[j] + (int64_t)s * PS) : 0.0;
-               v1[j] = (a1 >= 0 && a1 < nz) ? __ldcs(base[j] + (int64_t)(s + 1) * PS) : 0.0;
+               v0[j] = (a0 >= a_lo && a0 < a_hi) ? __ldcs(base[j] + (int64_t)s * PS) : 0.0;
+               v1[j] = (a1 >= a_lo && a1 < a_hi) ? __ldcs(base[j] + (int64_t)(s + 1) * PS) : 0.0;
             }
             // the (up to two) layers this pair of steps completes: their current phi_new values are
             // loaded with the chunk rows, not after them (nothing to load in the pass that overwrites)
@@ -1412,7 +1418,7 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                const int ad = s + u - (maxlev - 1);
-               const bool in = live && ad >= 0 && ad < nz;
+               const bool in = live && ad >= a_lo && ad < a_hi;
                const int64_t kk = zpass == 0 ? ad : nz - 1 - ad;
                old[u] = (!overwrite && in) ? pg[kk * gp.Sb] : 0.0;
                if (FUSED) {
@@ -1425,10 +1431,10 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
 #pragma unroll
                for (int j = 0; j < UNSHEAR_NC; j++) {
                   const int a = s + u - lv[j];
-                  if (a >= 0 && a < nz) ring[a & (SHEAR_RING - 1)][t] += (u == 0 ? v0[j] : v1[j]);
+                  if (a >= a_lo && a < a_hi) ring[a & (SHEAR_RING - 1)][t] += (u == 0 ? v0[j] : v1[j]);
                }
                const int ad = s + u - (maxlev - 1);      // complete for every chunk and lane
-               if (ad >= 0 && ad < nz) {
+               if (ad >= a_lo && ad < a_hi) {
                   const int k = zpass == 0 ? ad : nz - 1 - ad;
                   const double v = old[u] + ring[ad & (SHEAR_RING - 1)][t];
                   if (FUSED && fuse_pass) {
@@ -1471,15 +1477,35 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
          __syncthreads();
       }
       if (t == 0)
-         for (int j = 0; j < 5; j++) fz.partials[(size_t)j * gridDim.x + blockIdx.x] = sh[j][0];
+         for (int j = 0; j < 5; j++) fz.partials[(size_t)j * nblk_all + bid] = sh[j][0];
    }
+}
+
+// Slabs per column for the un-shear passes.  The kernel is latency-bound per CTA (a column is streamed in order, two
+// steps of loads in flight), so its time goes like waves of resident CTAs x rows per CTA; a rank of a sharded run
+// that owns few (patch, group) columns -- 196 at C4 on 8 GPUs, for 444 slots -- splits them in z.  A slab reads
+// nz / n + levels - 1 rows.  PAMPA_SN_UNSHEAR_ZSPLIT forces a value (tests).
+int unshear_zsplit(int active_columns, int nz, int num_sms) {
+   if (const char* e = std::getenv("PAMPA_SN_UNSHEAR_ZSPLIT")) {
+      const int v = std::atoi(e);
+      if (v >= 1) return std::min(v, std::max(1, nz));
+   }
+   const int slots = 3 * std::max(1, num_sms), levels = 31;
+   int best = 1;
+   int64_t best_cost = INT64_MAX;
+   for (int n = 1; n <= UNSHEAR_ZSPLIT_MAX && nz / n >= 16; n++) {
+      const int64_t waves = ((int64_t)active_columns * n + slots - 1) / slots;
+      const int64_t cost = waves * ((nz + n - 1) / n + levels - 1);
+      if (cost < best_cost) { best_cost = cost; best = n; }
+   }
+   return best;
 }
 
 void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
                         const int32_t* d_fast_chunks, int nfast, int npatch_b, int overwrite_first,
-                        const int32_t* cell_of, cudaStream_t st) {
+                        const int32_t* cell_of, int zsplit, cudaStream_t st) {
    if (nfast <= 0) return;
-   sn_unshear_phi_kernel<false><<<npatch_b * gp.G, PS, SHEAR_RING * PS * sizeof(double), st>>>(
+   sn_unshear_phi_kernel<false><<<dim3(npatch_b * gp.G, std::max(1, zsplit)), PS, SHEAR_RING * PS * sizeof(double), st>>>(
       gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, cell_of, UnshearFuse{});
 }
 
@@ -1489,15 +1515,16 @@ void launch_unshear_phi_fused(const SweepGlobals& gp, const ChunkDev* d_chunks, 
                               const int32_t* d_fast_chunks, int nfast, int npatch_b, int overwrite_first, int last_zpass,
                               const double* phi_old, double* phi_out, double* const* peer_out, int npeers,
                               const int32_t* mats, const double* nusf, const double* kapsf, const double* area,
-                              const double* dz, int has_z, double* partials, double* sums, cudaStream_t st) {
+                              const double* dz, int has_z, double* partials, double* sums, int zsplit, cudaStream_t st) {
    UnshearFuse fz{};
    fz.phi_old = phi_old; fz.phi_out = phi_out; fz.npeers = npeers;
    for (int r = 0; r < PEER_MAX; r++) fz.peers.p[r] = r < npeers ? peer_out[r] : nullptr;
    fz.mats = mats; fz.nusf = nusf; fz.kapsf = kapsf; fz.area = area; fz.dz = dz; fz.has_z = has_z;
    fz.last_zpass = last_zpass; fz.last_c0 = ((nfast - 1) / UNSHEAR_NC) * UNSHEAR_NC;
    fz.partials = partials;
-   const int nblocks = npatch_b * gp.G;
-   sn_unshear_phi_kernel<true><<<nblocks, PS, SHEAR_RING * PS * sizeof(double), st>>>(
+   zsplit = std::max(1, std::min(zsplit, UNSHEAR_ZSPLIT_MAX));
+   const int nblocks = npatch_b * gp.G * zsplit;         // (partials: 5 x npatch_b x G x UNSHEAR_ZSPLIT_MAX doubles)
+   sn_unshear_phi_kernel<true><<<dim3(npatch_b * gp.G, zsplit), PS, SHEAR_RING * PS * sizeof(double), st>>>(
       gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, nullptr, fz);
    sn_reduce_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, sums);
 }

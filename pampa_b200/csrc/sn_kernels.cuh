@@ -138,14 +138,17 @@ void launch_shear_q(const SweepGlobals& gp, const ClassDev* d_classes, const int
                     int nfast, int npatch, const int32_t* cell_of, cudaStream_t st);
 void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
                         const int32_t* d_fast_chunks, int nfast, int npatch, int overwrite_first,
-                        const int32_t* cell_of, cudaStream_t st);
+                        const int32_t* cell_of, int zsplit, cudaStream_t st);
+// slabs per column (grid y) of the un-shear passes for a rank that owns `active_columns` (patch, group) columns
+constexpr int UNSHEAR_ZSPLIT_MAX = 8;
+int unshear_zsplit(int active_columns, int nz, int num_sms);
 
 // un-shear with the reduction pass and the delivery of the flux moments fused into its last sweep over a column
 void launch_unshear_phi_fused(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
                               const int32_t* d_fast_chunks, int nfast, int npatch, int overwrite_first, int last_zpass,
                               const double* phi_old, double* phi_out, double* const* peer_out, int npeers,
                               const int32_t* mats, const double* nusf, const double* kapsf, const double* area,
-                              const double* dz, int has_z, double* partials, double* sums, cudaStream_t st);
+                              const double* dz, int has_z, double* partials, double* sums, int zsplit, cudaStream_t st);
 
 void launch_source(const double* phi, double* q, const int32_t* mats, const double* sig_s,
                    const double* chi, const double* nusf, const ReduceScalars* sc, const int32_t* gloc,

@@ -424,11 +424,17 @@ def test_fused_tail_matches_separate_passes(monkeypatch, kind):
         mesh, xs, _ = syn.hex_core(24, 40, pitch=1.0, dz=1.0, num_groups=G, seed=54321)
     quad = syn.level_symmetric(4)
     out = {}
-    for fused in (True, False):
+    # (fused?, slabs per column of the un-shear passes: a rank that owns few columns splits them in z, forced here)
+    variants = ((True, None), (False, None), (True, "3"), (False, "2"))
+    for fused, zsplit in variants:
         if fused:
             monkeypatch.delenv("PAMPA_SN_NO_FUSE", raising=False)
         else:
             monkeypatch.setenv("PAMPA_SN_NO_FUSE", "1")
+        if zsplit is None:
+            monkeypatch.delenv("PAMPA_SN_UNSHEAR_ZSPLIT", raising=False)
+        else:
+            monkeypatch.setenv("PAMPA_SN_UNSHEAR_ZSPLIT", zsplit)
         dev = pb.SNDevice(mesh, xs, quad)
         if kind == "hex":
             assert dev.info()["flow_classes"] > 0 and dev.info()["sweep_launches"] <= 4
@@ -438,15 +444,18 @@ def test_fused_tail_matches_separate_passes(monkeypatch, kind):
         p5 = dev.get("flux-moments")
         sol = dev.solve_keff(tol_k=1e-10, tol_phi=1e-9)
         dev.close()
-        out[fused] = (k1, p1, k5, p5, sol[0])
-    a, b = out[True], out[False]
-    if kind == "cartesian":
-        assert np.array_equal(a[1], b[1])
-    else:
-        assert util.max_rel(a[1], b[1]) < 1e-13
-    assert abs(a[0] - b[0]) < 1e-13 * abs(b[0])
-    assert abs(a[2] - b[2]) < 1e-13 * abs(b[2]) and util.max_rel(a[3], b[3]) < 1e-12
-    assert abs(a[4] - b[4]) < 1e-9
+        out[(fused, zsplit)] = (k1, p1, k5, p5, sol[0])
+    b = out[(False, None)]
+    for key in variants:
+        a = out[key]
+        # same order of the additions into a cell's moments: fused or not on one tiling, and whatever the slabs
+        if kind == "cartesian" or key[0] is False:
+            assert np.array_equal(a[1], b[1]), key
+        else:
+            assert util.max_rel(a[1], b[1]) < 1e-13, key
+        assert abs(a[0] - b[0]) < 1e-13 * abs(b[0]), key
+        assert abs(a[2] - b[2]) < 1e-13 * abs(b[2]) and util.max_rel(a[3], b[3]) < 1e-12, key
+        assert abs(a[4] - b[4]) < 1e-9, key
 
 
 def test_full_size_properties(monkeypatch):
