@@ -15,9 +15,10 @@ def _torchrun(n, port, *args):
     return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-def test_sharding_host_logic_gloo(mode):
-    r = _torchrun(2, 29611 + mode, "--backend", "gloo", "--shard-mode", str(mode))
+@pytest.mark.parametrize("mode,mesh", [(0, "cartesian"), (1, "cartesian"), (1, "hex")])
+def test_sharding_host_logic_gloo(mode, mesh):
+    r = _torchrun(2, 29611 + mode + (4 if mesh == "hex" else 0), "--backend", "gloo", "--shard-mode", str(mode),
+                  "--mesh", mesh)
     assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout + r.stderr
 
 
