@@ -1343,7 +1343,7 @@ struct UnshearFuse {
    double* partials;             // [5][gridDim.x]
 };
 
-template <bool FUSED>
+template <bool FUSED, bool SPLIT>
 __global__ void __launch_bounds__(PS, 3)
 sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks,
                       const ClassDev* __restrict__ classes, const int32_t* __restrict__ fast_chunks,
@@ -1358,7 +1358,8 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
    const int gl = gp.gloc[g];
    // blockIdx.y: slab of layers [k0, k1) of the column this CTA completes (launch_unshear_phi*: a rank that owns few
    // (patch, group) columns splits them in z to fill the SMs; the rows that straddle two slabs are read by both)
-   const int nblk_all = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+   // (SPLIT = false: one slab, the bounds below are the constants 0 and nz)
+   const int nblk_all = SPLIT ? gridDim.x * gridDim.y : gridDim.x, bid = SPLIT ? blockIdx.y * gridDim.x + blockIdx.x : blockIdx.x;
    if (gl < 0) {
       if (FUSED && t == 0) {               // neutral partials of a group another rank owns
          for (int j = 0; j < 4; j++) fz.partials[(size_t)j * nblk_all + bid] = 0.0;
@@ -1372,11 +1373,12 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
    const bool live = bslot >= 0;
    const double area_l = (FUSED && live) ? fz.area[bslot] : 0.0;
    const int nz = gp.nz;
-   const int k0 = (int)((int64_t)blockIdx.y * nz / gridDim.y), k1 = (int)((int64_t)(blockIdx.y + 1) * nz / gridDim.y);
+   const int k0 = SPLIT ? (int)((int64_t)blockIdx.y * nz / gridDim.y) : 0;
+   const int k1 = SPLIT ? (int)((int64_t)(blockIdx.y + 1) * nz / gridDim.y) : nz;
    double* pg = gp.phi_new + (int64_t)g * nz * gp.Sb + (live ? bslot : 0);
    for (int zpass = 0; zpass < 2; zpass++) {
       // the slab in sweep order of this z direction: layer index a <-> k = a (+z) or nz - 1 - a (-z)
-      const int a_lo = zpass == 0 ? k0 : nz - k1, a_hi = zpass == 0 ? k1 : nz - k0;
+      const int a_lo = SPLIT ? (zpass == 0 ? k0 : nz - k1) : 0, a_hi = SPLIT ? (zpass == 0 ? k1 : nz - k0) : nz;
       for (int c0 = 0; c0 < nfast; c0 += UNSHEAR_NC) {
          // up to UNSHEAR_NC chunks of this z direction, starting the search at chunk c0
          const double* base[UNSHEAR_NC];
@@ -1505,8 +1507,13 @@ void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const 
                         const int32_t* d_fast_chunks, int nfast, int npatch_b, int overwrite_first,
                         const int32_t* cell_of, int zsplit, cudaStream_t st) {
    if (nfast <= 0) return;
-   sn_unshear_phi_kernel<false><<<dim3(npatch_b * gp.G, std::max(1, zsplit)), PS, SHEAR_RING * PS * sizeof(double), st>>>(
-      gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, cell_of, UnshearFuse{});
+   const dim3 grid(npatch_b * gp.G, std::max(1, zsplit));
+   if (grid.y > 1)
+      sn_unshear_phi_kernel<false, true><<<grid, PS, SHEAR_RING * PS * sizeof(double), st>>>(
+         gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, cell_of, UnshearFuse{});
+   else
+      sn_unshear_phi_kernel<false, false><<<grid, PS, SHEAR_RING * PS * sizeof(double), st>>>(
+         gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, cell_of, UnshearFuse{});
 }
 
 // the same pass with the reduction and the delivery of the flux moments fused into its last sweep over the column
@@ -1524,8 +1531,12 @@ void launch_unshear_phi_fused(const SweepGlobals& gp, const ChunkDev* d_chunks, 
    fz.partials = partials;
    zsplit = std::max(1, std::min(zsplit, UNSHEAR_ZSPLIT_MAX));
    const int nblocks = npatch_b * gp.G * zsplit;         // (partials: 5 x npatch_b x G x UNSHEAR_ZSPLIT_MAX doubles)
-   sn_unshear_phi_kernel<true><<<dim3(npatch_b * gp.G, zsplit), PS, SHEAR_RING * PS * sizeof(double), st>>>(
-      gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, nullptr, fz);
+   if (zsplit > 1)
+      sn_unshear_phi_kernel<true, true><<<dim3(npatch_b * gp.G, zsplit), PS, SHEAR_RING * PS * sizeof(double), st>>>(
+         gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, nullptr, fz);
+   else
+      sn_unshear_phi_kernel<true, false><<<npatch_b * gp.G, PS, SHEAR_RING * PS * sizeof(double), st>>>(
+         gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, nullptr, fz);
    sn_reduce_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, sums);
 }
 
@@ -1533,9 +1544,11 @@ cudaError_t configure_shear_kernels() {
    cudaError_t e = cudaFuncSetAttribute(sn_shear_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(ShearSmem));
    if (e != cudaSuccess) return e;
-   e = cudaFuncSetAttribute(sn_unshear_phi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShearSmem));
-   if (e != cudaSuccess) return e;
-   return cudaFuncSetAttribute(sn_unshear_phi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShearSmem));
+   const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+   if ((e = cudaFuncSetAttribute(sn_unshear_phi_kernel<false, false>, attr, (int)sizeof(ShearSmem))) != cudaSuccess) return e;
+   if ((e = cudaFuncSetAttribute(sn_unshear_phi_kernel<false, true>, attr, (int)sizeof(ShearSmem))) != cudaSuccess) return e;
+   if ((e = cudaFuncSetAttribute(sn_unshear_phi_kernel<true, false>, attr, (int)sizeof(ShearSmem))) != cudaSuccess) return e;
+   return cudaFuncSetAttribute(sn_unshear_phi_kernel<true, true>, attr, (int)sizeof(ShearSmem));
 }
 
 // ------------------------------------------------------------------------------------ source

@@ -33,13 +33,14 @@ os.environ["PAMPA_SN_UNSHEAR_ZSPLIT"] = "1"
 k1, p1 = run("cartesian zsplit 1", mesh, xs, quad)
 os.environ["PAMPA_SN_UNSHEAR_ZSPLIT"] = "2"
 k2, p2 = run("cartesian zsplit 2", mesh, xs, quad)
-assert np.array_equal(p1, p2) and abs(k1 - k2) < 1e-13 * abs(k1)
+# (k is summed per un-shear CTA: its last bits, and through 1/k those of the later iterates, depend on the slabs)
+assert np.abs(p1 - p2).max() < 1e-13 * np.abs(p1).max() and abs(k1 - k2) < 1e-13 * abs(k1)
 os.environ.pop("PAMPA_SN_UNSHEAR_ZSPLIT")
 hmesh, hxs, _ = syn.hex_core(12, 32, pitch=1.0, dz=1.0, num_groups=G, seed=54321)
 kh, ph = run("hex lattice", hmesh, hxs, quad)
 os.environ["PAMPA_SN_UNSHEAR_ZSPLIT"] = "2"
 kh2, ph2 = run("hex lattice zsplit 2", hmesh, hxs, quad)
-assert np.array_equal(ph, ph2)
+assert np.abs(ph - ph2).max() < 1e-13 * np.abs(ph).max() and abs(kh - kh2) < 1e-13 * abs(kh)
 os.environ.pop("PAMPA_SN_UNSHEAR_ZSPLIT")
 nx, ny, nz = 24, 20, 16
 kk, jj, ii = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
