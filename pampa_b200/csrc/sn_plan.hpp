@@ -40,7 +40,8 @@ constexpr int RING_MAX = 4;        // smem ring depth for in-patch upwind values
 constexpr int FLOW_FIN = 3;        // incoming lateral faces the dataflow kernel handles (hexagonal lattices: 3)
 constexpr int FLOW_HALO = 64;      // patch-boundary / reflective sources per patch the dataflow kernel stages
 constexpr int FLOW3_DT_CAP = 6;    // widest chunk the three-face variant is instantiated for
-constexpr int FLOW3_DT_DEFAULT = 4;
+constexpr int FLOW3_DT_DEFAULT = 5;  // S8 on a hexagonal lattice: classes of 6 / 7 directions -> 3+3 / 4+3 either way; S12 (14 per
+                                    // class): 5+5+4 instead of 4+4+4+2, measured 2.5 % faster (19 441 hexagons x 100 layers, 16 groups)
 constexpr int FLOW_EXPORT = 32;    // lanes of a patch other patches read (compact edge copies per psi row)
 constexpr uint16_t LVL_EMPTY = 0xFFFF;
 constexpr int PERIM_MAX = 64;           // perimeter lanes of a structured tile (16x16: 60)
@@ -626,11 +627,13 @@ inline void build_plan(const PlanInput& in, Plan& pl) {
       // narrower chunks keep it at two CTAs per SM without spills
       if (cp.fast_flow && !cp.fast)
          dtm = (in.opts.dt_max >= 1 && in.opts.dt_max <= DT_MAX) ? std::min(in.opts.dt_max, FLOW3_DT_CAP) : FLOW3_DT_DEFAULT;
-      int nch = (n + dtm - 1) / dtm;
-      int per = (n + nch - 1) / nch;
-      for (int a = 0; a < n; a += per) {
-         Chunk ch; ch.cls = (int)ci; ch.nd = std::min(per, n - a);
+      // the fewest chunks of <= dtm directions, sizes balanced to within one (S12 on a Cartesian mesh: 21 directions
+      // per octant -> 5+4+4+4+4, not 5+5+5+5+1: a one-direction chunk pays the whole per-step overhead for it)
+      const int nch = (n + dtm - 1) / dtm;
+      for (int c = 0, a = 0; c < nch; c++) {
+         Chunk ch; ch.cls = (int)ci; ch.nd = n / nch + (c < n % nch ? 1 : 0);
          for (int d = 0; d < DT_MAX; d++) ch.m[d] = d < ch.nd ? cp.dirs[a + d] : -1;
+         a += ch.nd;
          pl.chunks.push_back(ch);
       }
    }

@@ -107,6 +107,37 @@ def test_single_sweep_cartesian_3d():
         dev.close()
 
 
+def test_single_sweep_cartesian_s12():
+    """S12 (168 directions, 21 per octant: chunks of 5+4+4+4+4) on a small Cartesian mesh, 2 groups: one sweep against
+    T^-1 q of the oracle, dataflow kernel and wavefront launches."""
+    import scipy.sparse.linalg as spla
+    rng = np.random.default_rng(12)
+    nx, ny, nz, G = 12, 10, 7, 2
+    dx, dy, dz = rng.uniform(0.5, 1.5, nx), rng.uniform(0.5, 1.5, ny), rng.uniform(0.5, 1.5, nz)
+    mats = rng.integers(0, 2, size=(nz, ny, nx))
+    xs = syn.synthetic_xs(G, seed=5)
+    quad = syn.level_symmetric(12)
+    em = syn.cartesian_mesh(dx, dy, dz, mats)
+    mesh, op = _oracle_cart(dx, dy, dz, mats, None, xs, quad, G)
+    N, M = op.N, op.M
+    assert M == 168
+    phi0 = rng.uniform(0.5, 1.5, size=(N, G))
+    keff = 1.1
+    qd = np.einsum("nfg,nf->ng", op.sig_s, phi0) + op.chi * np.sum(op.nusf * phi0, axis=1)[:, None] / keff
+    b = np.repeat((qd * op.vol[:, None]).reshape(N * G), M)
+    psi = spla.splu(op.T.tocsc()).solve(b).reshape(N, G, M)
+    for opts in ({}, {"wave_launch": 1}):
+        dev = pb.SNDevice(em, xs, quad, **opts)
+        assert dev.info()["num_chunks"] == 8 * 5
+        dev.set("flux-moments", phi0.reshape(-1))
+        dev.source(keff)
+        dev.sweep()
+        dev.reduce()
+        assert util.max_rel(dev.get("flux-moments").reshape(N, G), psi @ op.w) < 1e-11
+        assert util.rel_l2(dev.get("angular-flux").reshape(N, G, M), psi) < 1e-12
+        dev.close()
+
+
 def test_keff_cartesian_3d_reflective():
     """3-D Cartesian core with void corner cells, reflective -x/-y/-z and vacuum +x/+y/+z, S4."""
     nx, ny, nz, G = 12, 12, 8, 2
