@@ -28,6 +28,12 @@ def run(tag, mesh, xs, quad, iterations=3, solve_its=12, **opts):
 
 G = 4
 quad = syn.level_symmetric(4)
+if len(sys.argv) > 1 and sys.argv[1] == "hex-small":
+    # (racecheck: one small hexagonal lattice, the three-face dataflow kernel and the per-tiling layout passes)
+    hmesh, hxs, _ = syn.hex_core(8, 16, pitch=1.0, dz=1.0, num_groups=2, seed=54321)
+    run("hex lattice (small)", hmesh, hxs, quad, iterations=2, solve_its=3)
+    print("SANITIZE_R2_DONE")
+    sys.exit(0)
 mesh, xs = syn.checkerboard_core(40, 36, 32, assembly=4, num_groups=G)
 os.environ["PAMPA_SN_UNSHEAR_ZSPLIT"] = "1"
 k1, p1 = run("cartesian zsplit 1", mesh, xs, quad)
