@@ -49,6 +49,7 @@ struct LaunchGroup { int wave, cls, kind, dt, fin, ring; bool extras; int64_t of
 struct FlowLaunch { int dt, fin; int64_t offset; int count; std::vector<double> mw; int nch; };
 // fast classes / chunks of one shared tiling (the shear passes run once per tiling)
 struct TilingDev { int npatch = 0; int32_t* d_cell_of = nullptr; int32_t *d_classes = nullptr, *d_chunks = nullptr; int nclasses = 0, nchunks = 0;
+                   int nplus = 0;       // +z chunks, at the head of d_chunks
                    int zsplit = 1; };   // slabs per column of this tiling's un-shear pass (unshear_zsplit)
 
 }  // namespace
@@ -187,7 +188,6 @@ struct pampa_sn_handle {
    int bcz_refl[2] = {0, 0};
    int uniform_dz = 1;
    int np_stride = 0;                    // patches per (chunk, block) in the dataflow progress counters
-   int unshear_last_zpass = 0;           // z direction of the un-shear pass that completes a column
 };
 
 #define SN_FAIL(h, msg) do { (h)->err = (msg); return 1; } while (0)
@@ -377,7 +377,7 @@ int sweep_launches(pampa_sn_handle* h) {
       for (size_t t = 1; t < h->tilings.size(); t++) {
          const TilingDev& tg = h->tilings[t];
          if (tg.nchunks <= 0) continue;
-         launch_unshear_phi(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.npatch, overwrite ? 1 : 0,
+         launch_unshear_phi(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.nplus, tg.npatch, overwrite ? 1 : 0,
                             tg.d_cell_of, tg.zsplit, h->stream);
          overwrite = false;
          h->launches++;
@@ -385,8 +385,8 @@ int sweep_launches(pampa_sn_handle* h) {
       const TilingDev& tg = h->tilings[0];
       const int out = 1 - h->phi_cur;
       double* phi_out = fuse == 1 ? h->d_phi_buf[out] : h->d_phi_new;
-      launch_unshear_phi_fused(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.npatch, overwrite ? 1 : 0,
-                               h->unshear_last_zpass, h->d_phi, phi_out, fuse == 1 ? h->peer_phi[out] : nullptr,
+      launch_unshear_phi_fused(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.nplus, tg.npatch, overwrite ? 1 : 0,
+                               h->d_phi, phi_out, fuse == 1 ? h->peer_phi[out] : nullptr,
                                fuse == 1 ? h->npeers : 0, h->d_mats, h->d_nusf, h->d_kapsf,
                                h->d_area, h->d_dz, h->plan.has_z, h->d_fuse_partials, h->d_sums, tg.zsplit, h->stream);
       h->launches += 2;
@@ -401,7 +401,7 @@ int sweep_launches(pampa_sn_handle* h) {
    bool overwrite = h->groups_generic == 0;
    for (const TilingDev& tg : h->tilings)
       if (tg.nchunks > 0) {
-         launch_unshear_phi(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.npatch, overwrite ? 1 : 0,
+         launch_unshear_phi(gp, h->d_chunks, h->d_classes, tg.d_chunks, tg.nchunks, tg.nplus, tg.npatch, overwrite ? 1 : 0,
                             tg.d_cell_of, tg.zsplit, h->stream);
          overwrite = false;
          h->launches++;
@@ -940,6 +940,8 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
          std::stable_sort(chunk_list.begin(), chunk_list.end(), [&](int32_t a, int32_t b) {
             return (pl.classes[pl.chunks[a].cls].zdir < 0) < (pl.classes[pl.chunks[b].cls].zdir < 0); });
          td.nclasses = (int)cls_list.size(); td.nchunks = (int)chunk_list.size();
+         td.nplus = 0;
+         for (int32_t c : chunk_list) if (pl.classes[pl.chunks[c].cls].zdir >= 0) td.nplus++;
          td.zsplit = unshear_zsplit(td.npatch * h->Gown, pl.nz, num_sms);
          h->nfast_classes += td.nclasses;
          if (dev_upload(h, &td.d_classes, cls_list) || dev_upload(h, &td.d_chunks, chunk_list)) return 1;
@@ -1033,9 +1035,6 @@ int pampa_sn_create(pampa_sn_handle** out, const pampa_sn_mesh* mesh, const pamp
 
       // fused tail of the iteration: second iterate buffer (one GPU: here; sharded: pampa_sn_comm_init) and the
       // partials of the un-shear CTAs
-      h->unshear_last_zpass = 0;
-      for (int32_t c : fast_chunks)
-         if (pl.classes[pl.chunks[c].cls].tiling == 0 && pl.classes[pl.chunks[c].cls].zdir < 0) h->unshear_last_zpass = 1;
       if (h->groups_generic == 0 && h->tilings[0].nchunks > 0) {
          if (dev_alloc(h, &h->d_fuse_partials, 5LL * pl.npatch_b * h->G * UNSHEAR_ZSPLIT_MAX)) return 1;
          if (h->opts.num_ranks == 1) {

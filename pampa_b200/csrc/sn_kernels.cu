@@ -1339,15 +1339,17 @@ struct UnshearFuse {
    const double *nusf, *kapsf;   // [mat][G]
    const double *area, *dz;
    int has_z;
-   int last_zpass, last_c0;      // the pass that completes the column
    double* partials;             // [5][gridDim.x]
 };
 
-template <bool FUSED, bool SPLIT>
+// NCB chunks per pass over the column x US pipeline steps per loop iteration = 16 independent row loads in flight
+// per thread: 8 x 2, or 4 x 4 for launches whose z directions hold at most four chunks each (hexagonal lattices at
+// S8: four chunks per tiling and z direction -- with 8 x 2 half of the slots would be empty).
+template <bool FUSED, bool SPLIT, int NCB, int US>
 __global__ void __launch_bounds__(PS, 3)
 sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks,
                       const ClassDev* __restrict__ classes, const int32_t* __restrict__ fast_chunks,
-                      int nfast, int npatch_b, int overwrite_first, const int32_t* __restrict__ cell_of,
+                      int nfast, int nplus, int npatch_b, int overwrite_first, const int32_t* __restrict__ cell_of,
                       const UnshearFuse fz) {
    extern __shared__ __align__(16) unsigned char shear_raw[];
    double (*ring)[PS] = reinterpret_cast<double (*)[PS]>(shear_raw);      // [SHEAR_RING][PS]
@@ -1376,49 +1378,50 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
    const int k0 = SPLIT ? (int)((int64_t)blockIdx.y * nz / gridDim.y) : 0;
    const int k1 = SPLIT ? (int)((int64_t)(blockIdx.y + 1) * nz / gridDim.y) : nz;
    double* pg = gp.phi_new + (int64_t)g * nz * gp.Sb + (live ? bslot : 0);
+   // the chunk list holds the nplus +z chunks first: one run of passes per z direction, and the very last pass --
+   // the one that completes the column -- is the fused one
+   const int last_zpass = nplus < nfast ? 1 : 0;
    for (int zpass = 0; zpass < 2; zpass++) {
       // the slab in sweep order of this z direction: layer index a <-> k = a (+z) or nz - 1 - a (-z)
       const int a_lo = SPLIT ? (zpass == 0 ? k0 : nz - k1) : 0, a_hi = SPLIT ? (zpass == 0 ? k1 : nz - k0) : nz;
-      for (int c0 = 0; c0 < nfast; c0 += UNSHEAR_NC) {
-         // up to UNSHEAR_NC chunks of this z direction, starting the search at chunk c0
-         const double* base[UNSHEAR_NC];
-         int lv[UNSHEAR_NC];
-         int maxlev = 1, found = 0;
+      const int c_lo = zpass == 0 ? 0 : nplus, c_hi = zpass == 0 ? nplus : nfast;
+      for (int c0 = c_lo; c0 < c_hi; c0 += NCB) {           // one pass over the column per NCB chunks of this z direction
+         const double* base[NCB];
+         int lv[NCB];
+         int maxlev = 1;
 #pragma unroll
-         for (int j = 0; j < UNSHEAR_NC; j++) {
+         for (int j = 0; j < NCB; j++) {
             base[j] = nullptr; lv[j] = 1 << 20;
             const int c = c0 + j;
-            if (c < nfast) {
+            if (c < c_hi) {
                const ChunkDev* ch = chunks + fast_chunks[c];
                const ClassDev* cl = classes + ch->cls;
-               if ((cl->zdir >= 0 ? 0 : 1) == zpass) {
-                  const int l = cl->lvl[slot];
-                  lv[j] = l == LVL_EMPTY ? (1 << 20) : l;
-                  base[j] = ch->phi_part + block_row0(gl, patch, cl->npatch, cl->nsm, cl->gm, nz) * PS + t;
-                  maxlev = max(maxlev, cl->patch_nlev[patch]);
-                  found = 1;
-               }
+               const int l = cl->lvl[slot];
+               lv[j] = l == LVL_EMPTY ? (1 << 20) : l;
+               base[j] = ch->phi_part + block_row0(gl, patch, cl->npatch, cl->nsm, cl->gm, nz) * PS + t;
+               maxlev = max(maxlev, cl->patch_nlev[patch]);
             }
          }
-         if (!found) continue;                            // uniform over the CTA
+         const bool fuse_pass = FUSED && zpass == last_zpass && c0 + NCB >= c_hi;
          for (int r = 0; r < SHEAR_RING; r++) ring[r][t] = 0.0;
          const int nrow = a_hi + maxlev - 1;
-         for (int s = a_lo; s < nrow; s += 2) {
-            double v0[UNSHEAR_NC], v1[UNSHEAR_NC];
+         for (int s = a_lo; s < nrow; s += US) {
+            double v[US][NCB];
 #pragma unroll
-            for (int j = 0; j < UNSHEAR_NC; j++) {
-               const int a0 = s - lv[j], a1 = s + 1 - lv[j];
-               v0[j] = (a0 >= a_lo && a0 < a_hi) ? __ldcs(base[j] + (int64_t)s * PS) : 0.0;
-               v1[j] = (a1 >= a_lo && a1 < a_hi) ? __ldcs(base[j] + (int64_t)(s + 1) * PS) : 0.0;
+            for (int j = 0; j < NCB; j++) {                // (chunk-major: the US rows of a chunk are adjacent in memory)
+#pragma unroll
+               for (int u = 0; u < US; u++) {
+                  const int a = s + u - lv[j];
+                  v[u][j] = (a >= a_lo && a < a_hi) ? __ldcs(base[j] + (int64_t)(s + u) * PS) : 0.0;
+               }
             }
-            // the (up to two) layers this pair of steps completes: their current phi_new values are
-            // loaded with the chunk rows, not after them (nothing to load in the pass that overwrites)
-            double old[2];
-            double pov[2];                                 // fused pass: previous iterate and material of those layers
-            int matv[2];
-            const bool fuse_pass = FUSED && zpass == fz.last_zpass && c0 == fz.last_c0;
+            // the (up to US) layers these steps complete: their current phi_new values are loaded with the chunk
+            // rows, not after them (nothing to load in the pass that overwrites)
+            double old[US];
+            double pov[US];                                // fused pass: previous iterate and material of those layers
+            int matv[US];
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < US; u++) {
                const int ad = s + u - (maxlev - 1);
                const bool in = live && ad >= a_lo && ad < a_hi;
                const int64_t kk = zpass == 0 ? ad : nz - 1 - ad;
@@ -1429,21 +1432,21 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
                }
             }
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < US; u++) {
 #pragma unroll
-               for (int j = 0; j < UNSHEAR_NC; j++) {
+               for (int j = 0; j < NCB; j++) {
                   const int a = s + u - lv[j];
-                  if (a >= a_lo && a < a_hi) ring[a & (SHEAR_RING - 1)][t] += (u == 0 ? v0[j] : v1[j]);
+                  if (a >= a_lo && a < a_hi) ring[a & (SHEAR_RING - 1)][t] += v[u][j];
                }
                const int ad = s + u - (maxlev - 1);      // complete for every chunk and lane
                if (ad >= a_lo && ad < a_hi) {
                   const int k = zpass == 0 ? ad : nz - 1 - ad;
-                  const double v = old[u] + ring[ad & (SHEAR_RING - 1)][t];
+                  const double vv = old[u] + ring[ad & (SHEAR_RING - 1)][t];
                   if (FUSED && fuse_pass) {
                      if (live) {
                         const int64_t a = (int64_t)g * nz * gp.Sb + (int64_t)k * gp.Sb + bslot;
                         const int mat = matv[u];
-                        const double pn = mat < 0 ? 0.0 : v;
+                        const double pn = mat < 0 ? 0.0 : vv;
                         fz.phi_out[a] = pn;
 #pragma unroll
                         for (int r = 0; r < PEER_MAX; r++) if (r < fz.npeers) __stcs(fz.peers.p[r] + a, pn);
@@ -1457,7 +1460,7 @@ sn_unshear_phi_kernel(const SweepGlobals gp, const ChunkDev* __restrict__ chunks
                            mn = fmin(mn, pn);
                         }
                      }
-                  } else if (live) pg[(int64_t)k * gp.Sb] = v;
+                  } else if (live) pg[(int64_t)k * gp.Sb] = vv;
                   ring[ad & (SHEAR_RING - 1)][t] = 0.0;
                }
             }
@@ -1503,23 +1506,34 @@ int unshear_zsplit(int active_columns, int nz, int num_sms) {
    return best;
 }
 
+// kernel variant of a launch: 4 chunks x 4 steps when neither z direction holds more than four chunks, else 8 x 2
+template <bool FUSED>
+static void launch_unshear_variant(dim3 grid, const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
+                                   const int32_t* d_fast_chunks, int nfast, int nplus, int npatch_b, int overwrite_first,
+                                   const int32_t* cell_of, const UnshearFuse& fz, cudaStream_t st) {
+   const size_t smem = SHEAR_RING * PS * sizeof(double);
+   const bool half = std::max(nplus, nfast - nplus) <= UNSHEAR_NC / 2;
+   const bool split = grid.y > 1;
+#define SN_UNSHEAR_LAUNCH(SPLIT, NCB, US)                                                                             \
+   sn_unshear_phi_kernel<FUSED, SPLIT, NCB, US><<<grid, PS, smem, st>>>(gp, d_chunks, d_classes, d_fast_chunks, nfast, \
+                                                                        nplus, npatch_b, overwrite_first, cell_of, fz)
+   if (half) { if (split) SN_UNSHEAR_LAUNCH(true, UNSHEAR_NC / 2, 4); else SN_UNSHEAR_LAUNCH(false, UNSHEAR_NC / 2, 4); }
+   else      { if (split) SN_UNSHEAR_LAUNCH(true, UNSHEAR_NC, 2);     else SN_UNSHEAR_LAUNCH(false, UNSHEAR_NC, 2); }
+#undef SN_UNSHEAR_LAUNCH
+}
+
 void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
-                        const int32_t* d_fast_chunks, int nfast, int npatch_b, int overwrite_first,
+                        const int32_t* d_fast_chunks, int nfast, int nplus, int npatch_b, int overwrite_first,
                         const int32_t* cell_of, int zsplit, cudaStream_t st) {
    if (nfast <= 0) return;
-   const dim3 grid(npatch_b * gp.G, std::max(1, zsplit));
-   if (grid.y > 1)
-      sn_unshear_phi_kernel<false, true><<<grid, PS, SHEAR_RING * PS * sizeof(double), st>>>(
-         gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, cell_of, UnshearFuse{});
-   else
-      sn_unshear_phi_kernel<false, false><<<grid, PS, SHEAR_RING * PS * sizeof(double), st>>>(
-         gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, cell_of, UnshearFuse{});
+   launch_unshear_variant<false>(dim3(npatch_b * gp.G, std::max(1, zsplit)), gp, d_chunks, d_classes, d_fast_chunks, nfast,
+                                 nplus, npatch_b, overwrite_first, cell_of, UnshearFuse{}, st);
 }
 
 // the same pass with the reduction and the delivery of the flux moments fused into its last sweep over the column
-// (base tiling only); the block partials land in partials[5][npatch_b * G], summed by the caller into sums[5]
+// (base tiling only); the block partials land in partials[5][npatch_b * G * zsplit], summed by the caller into sums[5]
 void launch_unshear_phi_fused(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
-                              const int32_t* d_fast_chunks, int nfast, int npatch_b, int overwrite_first, int last_zpass,
+                              const int32_t* d_fast_chunks, int nfast, int nplus, int npatch_b, int overwrite_first,
                               const double* phi_old, double* phi_out, double* const* peer_out, int npeers,
                               const int32_t* mats, const double* nusf, const double* kapsf, const double* area,
                               const double* dz, int has_z, double* partials, double* sums, int zsplit, cudaStream_t st) {
@@ -1527,28 +1541,30 @@ void launch_unshear_phi_fused(const SweepGlobals& gp, const ChunkDev* d_chunks, 
    fz.phi_old = phi_old; fz.phi_out = phi_out; fz.npeers = npeers;
    for (int r = 0; r < PEER_MAX; r++) fz.peers.p[r] = r < npeers ? peer_out[r] : nullptr;
    fz.mats = mats; fz.nusf = nusf; fz.kapsf = kapsf; fz.area = area; fz.dz = dz; fz.has_z = has_z;
-   fz.last_zpass = last_zpass; fz.last_c0 = ((nfast - 1) / UNSHEAR_NC) * UNSHEAR_NC;
    fz.partials = partials;
    zsplit = std::max(1, std::min(zsplit, UNSHEAR_ZSPLIT_MAX));
    const int nblocks = npatch_b * gp.G * zsplit;         // (partials: 5 x npatch_b x G x UNSHEAR_ZSPLIT_MAX doubles)
-   if (zsplit > 1)
-      sn_unshear_phi_kernel<true, true><<<dim3(npatch_b * gp.G, zsplit), PS, SHEAR_RING * PS * sizeof(double), st>>>(
-         gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, nullptr, fz);
-   else
-      sn_unshear_phi_kernel<true, false><<<npatch_b * gp.G, PS, SHEAR_RING * PS * sizeof(double), st>>>(
-         gp, d_chunks, d_classes, d_fast_chunks, nfast, npatch_b, overwrite_first, nullptr, fz);
+   launch_unshear_variant<true>(dim3(npatch_b * gp.G, zsplit), gp, d_chunks, d_classes, d_fast_chunks, nfast, nplus,
+                                npatch_b, overwrite_first, nullptr, fz, st);
    sn_reduce_final_kernel<<<1, 256, 0, st>>>(partials, nblocks, sums);
+}
+
+template <bool FUSED, bool SPLIT>
+static cudaError_t cfg_unshear() {
+   const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+   cudaError_t e = cudaFuncSetAttribute(sn_unshear_phi_kernel<FUSED, SPLIT, UNSHEAR_NC, 2>, attr, (int)sizeof(ShearSmem));
+   if (e != cudaSuccess) return e;
+   return cudaFuncSetAttribute(sn_unshear_phi_kernel<FUSED, SPLIT, UNSHEAR_NC / 2, 4>, attr, (int)sizeof(ShearSmem));
 }
 
 cudaError_t configure_shear_kernels() {
    cudaError_t e = cudaFuncSetAttribute(sn_shear_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(ShearSmem));
    if (e != cudaSuccess) return e;
-   const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-   if ((e = cudaFuncSetAttribute(sn_unshear_phi_kernel<false, false>, attr, (int)sizeof(ShearSmem))) != cudaSuccess) return e;
-   if ((e = cudaFuncSetAttribute(sn_unshear_phi_kernel<false, true>, attr, (int)sizeof(ShearSmem))) != cudaSuccess) return e;
-   if ((e = cudaFuncSetAttribute(sn_unshear_phi_kernel<true, false>, attr, (int)sizeof(ShearSmem))) != cudaSuccess) return e;
-   return cudaFuncSetAttribute(sn_unshear_phi_kernel<true, true>, attr, (int)sizeof(ShearSmem));
+   if ((e = cfg_unshear<false, false>()) != cudaSuccess) return e;
+   if ((e = cfg_unshear<false, true>()) != cudaSuccess) return e;
+   if ((e = cfg_unshear<true, false>()) != cudaSuccess) return e;
+   return cfg_unshear<true, true>();
 }
 
 // ------------------------------------------------------------------------------------ source

@@ -137,7 +137,7 @@ cudaError_t configure_flow_kernels();
 void launch_shear_q(const SweepGlobals& gp, const ClassDev* d_classes, const int32_t* d_fast_classes,
                     int nfast, int npatch, const int32_t* cell_of, cudaStream_t st);
 void launch_unshear_phi(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
-                        const int32_t* d_fast_chunks, int nfast, int npatch, int overwrite_first,
+                        const int32_t* d_fast_chunks, int nfast, int nplus, int npatch, int overwrite_first,
                         const int32_t* cell_of, int zsplit, cudaStream_t st);
 // slabs per column (grid y) of the un-shear passes for a rank that owns `active_columns` (patch, group) columns
 constexpr int UNSHEAR_ZSPLIT_MAX = 8;
@@ -145,7 +145,7 @@ int unshear_zsplit(int active_columns, int nz, int num_sms);
 
 // un-shear with the reduction pass and the delivery of the flux moments fused into its last sweep over a column
 void launch_unshear_phi_fused(const SweepGlobals& gp, const ChunkDev* d_chunks, const ClassDev* d_classes,
-                              const int32_t* d_fast_chunks, int nfast, int npatch, int overwrite_first, int last_zpass,
+                              const int32_t* d_fast_chunks, int nfast, int nplus, int npatch, int overwrite_first,
                               const double* phi_old, double* phi_out, double* const* peer_out, int npeers,
                               const int32_t* mats, const double* nusf, const double* kapsf, const double* area,
                               const double* dz, int has_z, double* partials, double* sums, int zsplit, cudaStream_t st);
